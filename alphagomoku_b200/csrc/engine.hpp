@@ -1,0 +1,63 @@
+// Host-side engine object behind the C ABI (include/agb200.h).
+#pragma once
+#include "../../include/agb200.h"
+#include "agb_common.cuh"
+
+#include <string>
+#include <vector>
+
+namespace agb
+{
+	struct NetWeights; // resnet.cu
+	struct SelfplayState; // tree.cu
+}
+
+struct AgbEngine
+{
+		AgbConfig cfg { };
+		int cells = 0;
+		cudaStream_t stream = nullptr;
+		std::string error;
+		uint64_t launches = 0;
+
+		// static tables
+		uint8_t *d_pattern = nullptr; // [1<<20]
+		uint8_t *d_threat = nullptr; // [4096]
+		agb::Tables tables { };
+
+		// pattern store
+		agb::BoardStore store { };
+		uint32_t *d_features = nullptr; // [max_boards][cells] staging for host-pointer entry points
+		uint32_t *d_features2 = nullptr; // [max_boards][cells]
+		int8_t *d_io8 = nullptr; // [max_boards][cells] staging
+		int8_t *d_io8b = nullptr; // [max_boards]
+		uint16_t *d_io16 = nullptr; // [max_boards]
+		uint32_t *d_status = nullptr; // device overflow / error word
+
+		agb::NetWeights *net = nullptr;
+		agb::SelfplayState *selfplay = nullptr;
+
+		int fail(int code, const std::string &msg)
+		{
+			error = msg;
+			return code;
+		}
+};
+
+namespace agb
+{
+	// tables.cu
+	int build_tables(AgbEngine *e);
+	// patterns.cu
+	int launch_set_boards(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, int n, uint32_t *features_dev);
+	int launch_add_undo(AgbEngine *e, const uint16_t *moves_dev, int n, bool undo);
+	int launch_encode(AgbEngine *e, int n, uint32_t *features_dev);
+	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n);
+	int launch_outcomes(AgbEngine *e, const int8_t *boards_dev, const uint16_t *moves_dev, int n, int8_t *out_dev);
+	// resnet.cu
+	int net_create(AgbEngine *e);
+	void net_destroy(AgbEngine *e);
+	// selfplay.cu
+	int selfplay_create(AgbEngine *e);
+	void selfplay_destroy(AgbEngine *e);
+}

@@ -1,0 +1,217 @@
+"""Host-side mirror of the reference interfaces on top of the C ABI.
+
+Names follow the reference: GameRules / Sign (include/alphagomoku/game/rules.hpp:18-35, game/Move.hpp:17-23),
+GameConfig (utils/configs.hpp:23-44); Engine methods are named after the PatternCalculator / NNInputFeatures /
+AGNetwork / GameGenerator members they stand in for, batched over many positions."""
+import ctypes
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+class GameRules(enum.IntEnum):
+    FREESTYLE = 0
+    STANDARD = 1
+    RENJU = 2
+    CARO5 = 3
+    CARO6 = 4
+
+
+class Sign(enum.IntEnum):
+    NONE = 0
+    CROSS = 1
+    CIRCLE = 2
+    ILLEGAL = 3
+
+
+@dataclass
+class GameConfig:
+    rules: GameRules = GameRules.FREESTYLE
+    rows: int = 15
+    cols: int = 15
+    draw_after: int = 0  # 0 -> rows * cols (configs.hpp:32)
+
+
+class AgbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"agb200 error {code}: {message}")
+        self.code = code
+
+
+def move_to_short(row, col, sign):
+    """Move::toShort (game/Move.hpp:144-147)."""
+    return int(sign) | (int(row) << 2) | (int(col) << 9)
+
+
+def short_to_move(s):
+    return (s >> 2) & 127, (s >> 9) & 127, s & 3
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """One engine per GPU (one GeneratorThread per DeviceConfig in the reference)."""
+
+    def __init__(self, game: GameConfig, max_boards=1024, device=0, blocks=0, filters=0, q_head=False, games=0, max_batch_size=1,
+                 max_simulations=400, max_nodes_per_game=0, max_edges_per_game=0, init_to="parent", exploration_constant=1.25,
+                 information_leak_threshold=0.01, policy_expansion_threshold=1.0e-4, max_children=0, solver_max_positions=0,
+                 use_symmetries=False, seed=0, first_game_id=0):
+        self._lib = _lib.load()
+        self.game = game
+        self.cells = game.rows * game.cols
+        cfg = _lib.AgbConfig()
+        cfg.rules, cfg.rows, cfg.cols, cfg.draw_after = int(game.rules), game.rows, game.cols, game.draw_after
+        cfg.device, cfg.max_boards = device, max_boards
+        cfg.blocks, cfg.filters, cfg.q_head = blocks, filters, int(q_head)
+        cfg.games, cfg.max_batch_size, cfg.max_simulations = games, max_batch_size, max_simulations
+        cfg.max_nodes_per_game, cfg.max_edges_per_game = max_nodes_per_game, max_edges_per_game
+        cfg.init_to = {"loss": 0, "parent": 1, "draw": 2, "q_head": 3}[init_to]
+        cfg.exploration_constant = exploration_constant
+        cfg.information_leak_threshold = information_leak_threshold
+        cfg.policy_expansion_threshold = policy_expansion_threshold
+        cfg.max_children, cfg.solver_max_positions = max_children, solver_max_positions
+        cfg.use_symmetries, cfg.seed, cfg.first_game_id = int(use_symmetries), seed, first_game_id
+        self.config = cfg
+        self.max_boards = max_boards
+        handle = ctypes.c_void_p()
+        rc = self._lib.agb_create(ctypes.byref(cfg), ctypes.byref(handle))
+        if rc != 0:
+            raise AgbError(rc, self._lib.agb_last_error(None).decode())
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.agb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AgbError(rc, self._lib.agb_last_error(self._h).decode())
+
+    # ---- tables ----------------------------------------------------------------------------------------------
+    def get_tables(self):
+        pt = np.zeros(1 << 20, np.uint8)
+        ho = np.zeros(1 << 20, np.uint8)
+        th = np.zeros((4096, 2), np.uint8)
+        self._check(self._lib.agb_get_tables(self._h, _ptr(pt), _ptr(ho), _ptr(th)))
+        return pt, ho, th
+
+    # ---- PatternCalculator / NNInputFeatures -------------------------------------------------------------------
+    def set_boards(self, boards, sign_to_move):
+        """PatternCalculator::setBoard + NNInputFeatures::encode for n positions -> uint32 [n, cells]."""
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, self.cells)
+        stm = np.ascontiguousarray(sign_to_move, np.int8).reshape(-1)
+        n = boards.shape[0]
+        assert stm.shape[0] == n
+        features = np.zeros((n, self.cells), np.uint32)
+        self._check(self._lib.agb_set_boards(self._h, _ptr(boards), _ptr(stm), n, _ptr(features)))
+        return features
+
+    def add_moves(self, moves):
+        moves = np.ascontiguousarray(moves, np.uint16)
+        self._check(self._lib.agb_add_moves(self._h, _ptr(moves), moves.shape[0]))
+
+    def undo_moves(self, moves):
+        moves = np.ascontiguousarray(moves, np.uint16)
+        self._check(self._lib.agb_undo_moves(self._h, _ptr(moves), moves.shape[0]))
+
+    def encode(self, n):
+        features = np.zeros((n, self.cells), np.uint32)
+        self._check(self._lib.agb_encode(self._h, n, _ptr(features)))
+        return features
+
+    def get_state(self, n, histograms=True):
+        c = self.cells
+        out = {
+            "pattern_types": np.zeros((n, c, 4), np.uint8), "threats": np.zeros((n, c, 2), np.uint8),
+            "legal": np.zeros((n, c), np.uint8), "forbidden": np.zeros((n, c), np.uint8),
+            "hist_counts": np.zeros((n, 2, 10), np.int32) if histograms else None,
+            "hist_cells": np.zeros((n, 2, 10, c), np.uint16) if histograms else None,
+        }
+        self._check(self._lib.agb_get_state(self._h, n, _ptr(out["pattern_types"]), _ptr(out["threats"]), _ptr(out["legal"]),
+                                            _ptr(out["forbidden"]), _ptr(out["hist_counts"]), _ptr(out["hist_cells"])))
+        return out
+
+    def augment(self, features, symmetry):
+        features = np.ascontiguousarray(features, np.uint32).reshape(-1, self.cells).copy()
+        sym = np.ascontiguousarray(symmetry, np.int8).reshape(-1)
+        self._check(self._lib.agb_augment(self._h, _ptr(features), _ptr(sym), features.shape[0]))
+        return features
+
+    def get_outcomes(self, boards, last_moves):
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, self.cells)
+        moves = np.ascontiguousarray(last_moves, np.uint16).reshape(-1)
+        out = np.zeros(boards.shape[0], np.int8)
+        self._check(self._lib.agb_get_outcomes(self._h, _ptr(boards), _ptr(moves), boards.shape[0], _ptr(out)))
+        return out
+
+    # ---- AGNetwork -----------------------------------------------------------------------------------------------
+    def weights_size(self):
+        return self._lib.agb_weights_size(self._h)
+
+    def load_weights(self, blob):
+        blob = np.ascontiguousarray(blob)
+        self._check(self._lib.agb_load_weights(self._h, _ptr(blob), blob.nbytes))
+
+    def forward(self, features, want_q=False):
+        features = np.ascontiguousarray(features, np.uint32).reshape(-1, self.cells)
+        n = features.shape[0]
+        policy = np.zeros((n, self.cells), np.float32)
+        value = np.zeros((n, 3), np.float32)
+        q = np.zeros((n, self.cells, 3), np.float32) if want_q else None
+        self._check(self._lib.agb_forward(self._h, _ptr(features), n, _ptr(policy), _ptr(value), _ptr(q)))
+        return policy, value, q
+
+    # ---- lockstep self-play ------------------------------------------------------------------------------------------
+    def selfplay_reset(self, boards=None, sign_to_move=None):
+        b = None if boards is None else np.ascontiguousarray(boards, np.int8)
+        s = None if sign_to_move is None else np.ascontiguousarray(sign_to_move, np.int8)
+        self._check(self._lib.agb_selfplay_reset(self._h, _ptr(b), _ptr(s)))
+
+    def step(self, n_steps=1):
+        self._check(self._lib.agb_step(self._h, n_steps))
+
+    def stats(self):
+        st = _lib.AgbStats()
+        self._check(self._lib.agb_get_stats(self._h, ctypes.byref(st)))
+        return {name: getattr(st, name) for name, _ in st._fields_ if name != "reserved"}
+
+    def get_root(self, game):
+        visits = np.zeros(self.cells, np.int32)
+        priors = np.zeros(self.cells, np.float32)
+        q = np.zeros(self.cells, np.float32)
+        value = np.zeros(3, np.float32)
+        rv = ctypes.c_int32(0)
+        self._check(self._lib.agb_get_root(self._h, game, _ptr(visits), _ptr(priors), _ptr(q), _ptr(value), ctypes.byref(rv)))
+        return visits, priors, q, value, rv.value
+
+    def get_board(self, game):
+        board = np.zeros(self.cells, np.int8)
+        stm = ctypes.c_int8(0)
+        mv = ctypes.c_int32(0)
+        self._check(self._lib.agb_get_board(self._h, game, _ptr(board), ctypes.byref(stm), ctypes.byref(mv)))
+        return board, stm.value, mv.value
+
+    def pop_finished(self, capacity=1 << 24):
+        buf = np.zeros(capacity, np.uint8)
+        used = ctypes.c_size_t(0)
+        n = ctypes.c_int(0)
+        self._check(self._lib.agb_pop_finished(self._h, _ptr(buf), capacity, ctypes.byref(used), ctypes.byref(n)))
+        return bytes(buf[:used.value]), n.value
+
+    def synchronize(self):
+        self._check(self._lib.agb_synchronize(self._h))
+
+    def stream(self):
+        return self._lib.agb_stream(self._h)

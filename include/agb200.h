@@ -1,0 +1,178 @@
+/*
+ * agb200.h -- C ABI of the B200-native lockstep self-play engine (libagb200.so).
+ *
+ * This is the drop-in boundary for AlphaGomoku's data-parallel hot path. The reference has no FFI for the
+ * search (its seams are C++ classes), so every entry point below names the reference interface it replaces
+ * (paths relative to the reference tree). Conventions follow the reference's only existing C ABI,
+ * include/alphagomoku/dataset/torch_api.h:14-41: extern "C", plain pointers and sizes, caller-owned buffers,
+ * no exceptions across the boundary. Every function returns 0 on success or a negative AGB_E* code;
+ * agb_last_error() returns the text for the calling engine.
+ *
+ * Threading: thread-compatible, not thread-safe -- one host thread per engine, one engine per GPU
+ * (mirrors one GeneratorThread per DeviceConfig, src/selfplay/GeneratorManager.cpp:29-53).
+ *
+ * Pointers named *_host are host memory (pinned or pageable); pointers named *_dev are device memory on the
+ * engine's GPU. Board cells are int8: 0 empty, 1 cross/black, 2 circle/white (Sign, include/alphagomoku/game/Move.hpp:17-23).
+ */
+#ifndef AGB200_H_
+#define AGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+/* GameRules, include/alphagomoku/game/rules.hpp:18-25 */
+enum
+{
+	AGB_FREESTYLE = 0,
+	AGB_STANDARD = 1,
+	AGB_RENJU = 2,
+	AGB_CARO5 = 3,
+	AGB_CARO6 = 4
+};
+/* GameOutcome, include/alphagomoku/game/rules.hpp:29-35 */
+enum
+{
+	AGB_OUTCOME_UNKNOWN = 0,
+	AGB_OUTCOME_DRAW = 1,
+	AGB_OUTCOME_CROSS_WIN = 2,
+	AGB_OUTCOME_CIRCLE_WIN = 3
+};
+enum
+{
+	AGB_OK = 0,
+	AGB_EINVAL = -1, /* bad argument */
+	AGB_ECUDA = -2, /* CUDA runtime error (text in agb_last_error) */
+	AGB_ENOMEM = -3, /* capacity exceeded (boards, nodes, edges, records) */
+	AGB_ESTATE = -4, /* call made in the wrong state (e.g. forward before weights) */
+	AGB_EOVERFLOW = -5 /* a device-side bounded structure overflowed (reported, never silent) */
+};
+
+typedef struct AgbEngine AgbEngine;
+
+/* GameConfig + the parts of SelfplayConfig / SearchConfig the device engine honours
+ * (include/alphagomoku/utils/configs.hpp:23-255). */
+typedef struct AgbConfig
+{
+	int32_t rules; /* AGB_FREESTYLE .. AGB_CARO6 */
+	int32_t rows, cols; /* 15x15 or 20x20 (square, <= 20: RawPatternCalculator.hpp:48) */
+	int32_t draw_after; /* GameConfig::draw_after; <= 0 means rows*cols */
+	int32_t device; /* CUDA device ordinal */
+	int32_t max_boards; /* capacity of the pattern store = max concurrent positions per call */
+	/* network shape (ResnetPV / ResnetPVQ, src/networks/networks.cpp:71-93, 143-168) */
+	int32_t blocks, filters; /* residual blocks, channels (64 or 128) */
+	int32_t q_head; /* 0 = "pv", 1 = "pvq" */
+	/* search (SearchConfig, MCTSConfig, EdgeSelectorConfig, TreeConfig) */
+	int32_t games; /* concurrent self-play games on this engine */
+	int32_t max_batch_size; /* SearchConfig::max_batch_size: leaves selected per game per step */
+	int32_t max_simulations; /* Constraints::max_simulations */
+	int32_t max_nodes_per_game; /* node arena capacity per game */
+	int32_t max_edges_per_game; /* edge arena capacity per game */
+	int32_t init_to; /* 0 loss, 1 parent, 2 draw, 3 q_head (EdgeSelectorConfig::init_to) */
+	float exploration_constant; /* EdgeSelectorConfig::exploration_constant (1.25) */
+	float information_leak_threshold; /* TreeConfig (0.01) */
+	float policy_expansion_threshold; /* MCTSConfig (1e-4) */
+	int32_t max_children; /* MCTSConfig::max_children; <= 0 means unlimited */
+	int32_t solver_max_positions; /* TSSConfig::max_positions */
+	int32_t use_symmetries; /* SelfplayConfig::use_symmetries */
+	uint64_t seed; /* base seed; per-game streams are keyed by (seed, global game id) */
+	int32_t first_game_id; /* global id of this engine's game 0 (rank * games when sharded) */
+	int32_t reserved[7];
+} AgbConfig;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------- */
+int agb_create(const AgbConfig *config, AgbEngine **engine);
+void agb_destroy(AgbEngine *engine);
+const char* agb_last_error(const AgbEngine *engine); /* engine may be NULL: error of the last failed agb_create */
+int agb_get_config(const AgbEngine *engine, AgbConfig *config);
+const char* agb_version(void);
+
+/* ---- static tables (replaces PatternTable::get / ThreatTable::get, src/patterns/PatternTable.cpp:110-142,
+ *      src/patterns/ThreatTable.cpp:135-167). Built on the device at agb_create; these read them back. --------- */
+/* pattern_types[1<<20]: low nibble cross PatternType, high nibble circle PatternType, indexed by the 20-bit
+ * narrowed window (PatternTable.hpp:135-138); half_open_3[1<<20]: bit0 cross, bit1 circle (PatternTable.hpp:118-127);
+ * threats[4096*2]: (cross, circle) ThreatType per 12-bit pattern-type group (ThreatTable.hpp:79-100). Any may be NULL. */
+int agb_get_tables(AgbEngine *engine, uint8_t *pattern_types_host, uint8_t *half_open_3_host, uint8_t *threats_host);
+
+/* ---- K1 + K3: PatternCalculator::setBoard (src/patterns/PatternCalculator.cpp:40-67) followed by
+ *      NNInputFeatures::encode (src/networks/NNInputFeatures.cpp:59-113) for n independent positions ------------- */
+/* boards[n][rows*cols] int8, sign_to_move[n] int8 (1 or 2) -> features[n][rows*cols] uint32. The persistent
+ * state of board slot i (lines, pattern types, threats, threat lists) is kept for agb_add_move / agb_get_state. */
+int agb_set_boards(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, uint32_t *features_host);
+/* same, device pointers, asynchronous on the engine's stream (use agb_synchronize) */
+int agb_set_boards_dev(AgbEngine *engine, const int8_t *boards_dev, const int8_t *sign_to_move_dev, int n, uint32_t *features_dev);
+
+/* ---- K2: PatternCalculator::addMove / undoMove (PatternCalculator.cpp:68-106, 278-366), one move per board slot.
+ *      moves[n]: Move::toShort wire form sign | row<<2 | col<<9 (Move.hpp:144-147); sign 0 = skip this slot. ----- */
+int agb_add_moves(AgbEngine *engine, const uint16_t *moves_host, int n);
+int agb_undo_moves(AgbEngine *engine, const uint16_t *moves_host, int n);
+/* re-encode features from the persistent state (NNInputFeatures::encode on the incremental calculator) */
+int agb_encode(AgbEngine *engine, int n, uint32_t *features_host);
+
+/* read back the persistent state of the first n slots; any pointer may be NULL.
+ * pattern_types[n][cells][4]: PatternEncoding byte per direction (H,V,D,A); threats[n][cells][2] (cross, circle);
+ * legal[n][cells]; forbidden[n][cells] (PatternCalculator::isForbidden(CROSS,..), renju only, else 0);
+ * hist_counts[n][2][10] and hist_cells[n][2][10][cells] uint16 (row | col<<8, Location::toShort) in list order
+ * (ThreatHistogram.hpp:21-140). */
+int agb_get_state(AgbEngine *engine, int n, uint8_t *pattern_types_host, uint8_t *threats_host, uint8_t *legal_host,
+		uint8_t *forbidden_host, int32_t *hist_counts_host, uint16_t *hist_cells_host);
+
+/* NNInputFeatures::augment (NNInputFeatures.cpp:114-154) on n feature planes, in place; symmetry[n] in -7..7 */
+int agb_augment(AgbEngine *engine, uint32_t *features_host, const int8_t *symmetry_host, int n);
+
+/* getOutcome (src/game/rules.cpp:110-133) for n (board, last move) pairs; outcomes[n] int8 AGB_OUTCOME_* */
+int agb_get_outcomes(AgbEngine *engine, const int8_t *boards_host, const uint16_t *last_moves_host, int n, int8_t *outcomes_host);
+
+/* ---- K4: AGNetwork (src/networks/AGNetwork.cpp:61-87) -- ResNet policy/value forward ---------------------------- */
+/* weight blob layout: see DESIGN.md "network blob"; fp32, BN already folded (AGNetwork::optimize, AGNetwork.cpp:136-149) */
+int agb_load_weights(AgbEngine *engine, const void *blob_host, size_t bytes);
+size_t agb_weights_size(const AgbEngine *engine); /* expected blob size for the configured network */
+/* features[n][cells] uint32 -> policy[n][cells] f32 (softmax), value[n][3] f32 (win, draw, loss; softmax),
+ * q[n][cells][3] f32 or NULL (NetworkDataPack.cpp:112-129, 200-235) */
+int agb_forward(AgbEngine *engine, const uint32_t *features_host, int n, float *policy_host, float *value_host, float *q_host);
+int agb_forward_dev(AgbEngine *engine, const uint32_t *features_dev, int n, float *policy_dev, float *value_dev, float *q_dev);
+
+/* ---- lockstep self-play (GameGenerator::generate, src/selfplay/GameGenerator.cpp:46-121, over all games) ------- */
+/* start (or restart) all games from given positions: boards[games][cells], sign_to_move[games]; NULL = empty boards, cross to move */
+int agb_selfplay_reset(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host);
+/* advance every game by n_steps lockstep iterations of select -> solve/encode -> evaluate -> expand -> backup (-> move) */
+int agb_step(AgbEngine *engine, int n_steps);
+/* pop finished-game records (GameDataStorage::serialize, src/dataset/GameDataStorage.cpp:217-251, format 201) */
+int agb_pop_finished(AgbEngine *engine, void *records_host, size_t capacity, size_t *used, int *n_games);
+
+typedef struct AgbStats
+{
+	/* SearchStats / NNEvaluatorStats (Search.hpp:33-54, NNEvaluator.hpp:28-40) */
+	uint64_t nb_network_evaluations;
+	uint64_t nb_node_count;
+	uint64_t nb_duplicate_nodes;
+	uint64_t nb_information_leaks;
+	uint64_t nb_proven_states;
+	uint64_t nb_wasted_expansions;
+	uint64_t nb_moves_played;
+	uint64_t nb_games_finished;
+	uint64_t nb_kernel_launches; /* kernels this engine launched since creation */
+	uint64_t overflow_flags; /* non-zero: a bounded device structure overflowed */
+	uint64_t reserved[6];
+} AgbStats;
+int agb_get_stats(AgbEngine *engine, AgbStats *stats);
+
+/* read-only view of game g's root: visits[cells] int32, priors[cells] f32, q[cells] f32 (expectation) -- for parity tests
+ * against Tree::getInfo({}) (src/search/monte_carlo/Tree.cpp:394-416) */
+int agb_get_root(AgbEngine *engine, int game, int32_t *visits_host, float *priors_host, float *q_host, float *root_value3_host,
+		int32_t *root_visits);
+int agb_get_board(AgbEngine *engine, int game, int8_t *board_host, int8_t *sign_to_move, int32_t *move_number);
+
+int agb_synchronize(AgbEngine *engine);
+/* CUDA stream (cudaStream_t) the engine launches on, for callers that time with events */
+void* agb_stream(AgbEngine *engine);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* AGB200_H_ */

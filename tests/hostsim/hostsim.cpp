@@ -1,0 +1,92 @@
+// TEST-ONLY: compiles the host+device logic headers of alphagomoku_b200/csrc with g++ so the kernel logic can be
+// checked against the oracle on a box without a GPU (tests marked "not gpu"). The product never builds or loads this.
+#include "../../alphagomoku_b200/csrc/tables_logic.cuh"
+
+#include <cstdint>
+#include <vector>
+
+using namespace agb;
+using namespace agb::tables_logic;
+
+extern "C" void hostsim_pattern_table(int rules, uint8_t *table)
+{
+	RuleBuilder cross { rules, CROSS, { } }, circle { rules, CIRCLE, { } };
+	cross.build();
+	circle.build();
+	for (uint32_t i = 0; i < (1u << 20); i++)
+		table[i] = pattern_table_entry(i, cross.out.data(), (int) cross.out.size(), circle.out.data(), (int) circle.out.size());
+}
+extern "C" void hostsim_threat_table(int rules, uint8_t *table)
+{
+	for (int idx = 0; idx < 4096; idx++)
+	{
+		const int t[4] = { idx & 7, (idx >> 3) & 7, (idx >> 6) & 7, (idx >> 9) & 7 };
+		int cross, circle;
+		threat_of(t, rules, cross, circle);
+		table[idx] = static_cast<uint8_t>(cross | (circle << 4));
+	}
+}
+
+#include "../../alphagomoku_b200/csrc/patterns_logic.cuh"
+using namespace agb::plogic;
+
+// sequential model of the K1+K3 kernel (one board): same per-cell functions, plain loops instead of a warp
+extern "C" void hostsim_set_board(int rules, int S, const int8_t *board, int stm, const uint8_t *pattern_table, const uint8_t *threat_table,
+		uint8_t *ptypes_out, uint8_t *threats_out, uint32_t *features_out, uint8_t *forbidden_out, int *overflow)
+{
+	uint64_t lines[kMaxLines];
+	for (int l = 0; l < line_count(S); l++)
+		lines[l] = build_line(board, S, l);
+	Tables tables { pattern_table, threat_table };
+	*overflow = 0;
+	for (int r = 0; r < S; r++)
+		for (int c = 0; c < S; c++)
+		{
+			const int idx = r * S + c;
+			const uint32_t p = (board[idx] == NONE) ? classify_cell(lines, pattern_table, r, c, S) : 0u;
+			const uint8_t t = (board[idx] == NONE) ? threat_of_cell(p, threat_table) : 0;
+			for (int d = 0; d < 4; d++)
+				ptypes_out[4 * idx + d] = (p >> (8 * d)) & 0x77;
+			threats_out[2 * idx + 0] = t & 15;
+			threats_out[2 * idx + 1] = t >> 4;
+			uint32_t f = encode_cell(board[idx], p, stm);
+			bool forb = false;
+			if (rules == RULE_RENJU and board[idx] == NONE)
+			{
+				const int tc = t & 15;
+				if (tc == TT_OVERLINE or tc == TT_FORK_4x4)
+					forb = true;
+				else if (tc == TT_FORK_3x3)
+				{
+					Overlay ov;
+					forb = is_forbidden_raw(board, S, r, c, tables, ov);
+					*overflow |= ov.overflow;
+				}
+			}
+			forbidden_out[idx] = forb;
+			if (forb and stm == CROSS)
+				f |= 1u << 6;
+			features_out[idx] = f;
+		}
+}
+extern "C" uint32_t hostsim_open3_promotions(uint32_t window)
+{
+	return open_three_promotions(window);
+}
+extern "C" int hostsim_outcome(int rules, int S, const int8_t *board, int r, int c, int sign, int draw_after, const uint8_t *pattern_table,
+		const uint8_t *threat_table)
+{
+	Tables tables { pattern_table, threat_table };
+	bool overflow = false;
+	return outcome_of(board, S, rules, draw_after, r, c, sign, tables, overflow);
+}
+extern "C" void hostsim_augment(uint32_t *dst, const uint32_t *src, int S, int mode)
+{
+	for (int r = 0; r < S; r++)
+		for (int c = 0; c < S; c++)
+		{
+			int sr, sc;
+			symmetry_source(mode, S, r, c, sr, sc);
+			dst[r * S + c] = permute_direction_bits(src[sr * S + sc], mode);
+		}
+}

@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE: ctypes view of oracle/_ref/libagref.so (the reference's own classes behind oracle/ref_shim.cpp).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg import this."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libagref.so")
+REF_LIB_FAST = os.path.join(ROOT, "oracle", "_ref", "libagref_fast.so")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def available():
+    return os.path.exists(REF_LIB)
+
+
+class RefOracle:
+    def __init__(self, fast=False):
+        path = REF_LIB_FAST if fast else REF_LIB
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = ctypes.CDLL(path)
+        self.lib.agref_calc_create.restype = ctypes.c_void_p
+        self.lib.agref_calc_create.argtypes = [ctypes.c_int] * 3
+        for name in ("agref_calc_destroy", "agref_calc_set_board", "agref_calc_add_move", "agref_calc_undo_move", "agref_calc_dump",
+                     "agref_calc_histogram", "agref_calc_encode"):
+            getattr(self.lib, name).argtypes = None
+        self.lib.agref_defensive_moves.restype = ctypes.c_uint16
+        self.lib.agref_open3_promotion_moves.restype = ctypes.c_uint16
+        self._calcs = {}
+
+    def tables(self, rules, with_update_mask=False):
+        pt = np.zeros(1 << 20, np.uint8)
+        ho = np.zeros(1 << 20, np.uint8)
+        um = np.zeros((1 << 20, 2), np.uint32) if with_update_mask else None
+        th = np.zeros((4096, 2), np.uint8)
+        self.lib.agref_dump_tables(rules, _p(pt), _p(ho), _p(um), _p(th))
+        return pt, ho, th, um
+
+    def calc(self, rules, size):
+        key = (rules, size)
+        if key not in self._calcs:
+            self._calcs[key] = ctypes.c_void_p(self.lib.agref_calc_create(rules, size, size))
+        return self._calcs[key]
+
+    def dump(self, rules, size, hist_only=False):
+        h = self.calc(rules, size)
+        c = size * size
+        out = {"pattern_types": np.zeros((c, 4), np.uint8), "threats": np.zeros((c, 2), np.uint8), "legal": np.zeros(c, np.uint8),
+               "forbidden": np.zeros(c, np.uint8), "features": np.zeros(c, np.uint32), "hist_counts": np.zeros((2, 10), np.int32),
+               "hist_cells": np.zeros((2, 10, c), np.uint16)}
+        # threat lists first: PatternCalculator::isForbidden (used by the forbidden dump and by encode in renju) runs
+        # addMove/undoMove internally and thereby reorders the lists (swap-with-last removal, ThreatHistogram.hpp:61-66)
+        for colour in (0, 1):
+            self.lib.agref_calc_histogram(h, colour + 1, _p(out["hist_counts"][colour]), _p(out["hist_cells"][colour]), c)
+        if hist_only:
+            return out
+        self.lib.agref_calc_dump(h, _p(out["pattern_types"]), _p(out["threats"]), _p(out["legal"]), _p(out["forbidden"]), None)
+        self.lib.agref_calc_encode(h, _p(out["features"]))
+        return out
+
+    def set_board(self, rules, size, board, stm):
+        board = np.ascontiguousarray(board, np.int8)
+        self.lib.agref_calc_set_board(self.calc(rules, size), _p(board), int(stm))
+        return self.dump(rules, size)
+
+    def add_move(self, rules, size, row, col, sign):
+        self.lib.agref_calc_add_move(self.calc(rules, size), int(row), int(col), int(sign))
+
+    def undo_move(self, rules, size, row, col, sign):
+        self.lib.agref_calc_undo_move(self.calc(rules, size), int(row), int(col), int(sign))
+
+    def augment(self, features, size, mode):
+        f = np.ascontiguousarray(features, np.uint32).copy()
+        self.lib.agref_augment(_p(f), size, size, int(mode))
+        return f
+
+    def outcome(self, rules, size, board, row, col, sign, draw_after):
+        board = np.ascontiguousarray(board, np.int8)
+        return self.lib.agref_get_outcome(rules, size, size, _p(board), int(row), int(col), int(sign), int(draw_after))
+
+    def is_forbidden(self, size, board, row, col, sign):
+        board = np.ascontiguousarray(board, np.int8)
+        return bool(self.lib.agref_is_forbidden(size, size, _p(board), int(row), int(col), int(sign)))

@@ -1,0 +1,162 @@
+"""CPU tests (-m "not gpu"): pin the oracle against the reference's own known answers, check the host-compiled kernel
+logic against the oracle, and check that the C-ABI library loads, exports every declared symbol and refuses to run
+without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_boards
+
+P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+
+def test_reference_known_answers_pin_the_oracle(ref, golden):
+    """Every hand-written expectation transcribed from the reference's unit tests holds for oracle/_ref."""
+    known, _ = golden
+    assert len(known) >= 150
+    for k in known:
+        size, board = k["size"], np.array(k["board"], np.int8)
+        if k["kind"] == "forbidden":
+            assert ref.is_forbidden(size, board, k["row"], k["col"], k["sign"]) == k["expected"], k
+            # incremental path (PatternCalculator::isForbidden) must agree, as test_renju.cpp:45-51 demands
+            st = ref.set_board(k["rules"], size, board, 1)
+            if board[k["row"] * size + k["col"]] == 0:
+                assert bool(st["forbidden"][k["row"] * size + k["col"]]) == k["expected"], k
+        elif k["kind"] == "outcome":
+            assert ref.outcome(k["rules"], size, board, k["row"], k["col"], k["sign"], -1) == k["expected"], k
+        elif k["kind"] == "feature_bit":
+            st = ref.set_board(k["rules"], size, board, k["stm"])
+            bit = (int(st["features"][k["row"] * size + k["col"]]) >> k["bit"]) & 1
+            assert bool(bit) == k["expected"], k
+
+
+def test_golden_states_match_the_reference_build(ref, golden):
+    """The committed reference_states.npz is what oracle/_ref produces today (guards against a stale fixture)."""
+    _, states = golden
+    for i in range(0, len(states["rules"]), 7):
+        rules, size, stm = int(states["rules"][i]), int(states["size"][i]), int(states["stm"][i])
+        c = size * size
+        st = ref.set_board(rules, size, states["board"][i][:c], stm)
+        assert (st["features"] == states["features"][i][:c]).all()
+        assert (st["pattern_types"] == states["pattern_types"][i][:c]).all()
+        assert (st["hist_counts"] == states["hist_counts"][i]).all()
+
+
+@pytest.mark.parametrize("rules", [0, 1, 2, 3, 4])
+def test_table_logic_matches_reference_tables(ref, hostsim, rules):
+    """tables_logic.cuh (the code the device kernel runs) reproduces PatternTable / ThreatTable bit for bit."""
+    pt, ho, th, _ = ref.tables(rules)
+    mine = np.zeros(1 << 20, np.uint8)
+    hostsim.hostsim_pattern_table(rules, P(mine))
+    expected = (pt & 7) | ((ho & 1) << 3) | (((pt >> 4) & 7) << 4) | (((ho >> 1) & 1) << 7)
+    assert (mine == expected).all()
+    mt = np.zeros(4096, np.uint8)
+    hostsim.hostsim_threat_table(rules, P(mt))
+    assert (mt == (th[:, 0] | (th[:, 1] << 4))).all()
+
+
+def _hostsim_tables(hostsim, rules):
+    pt = np.zeros(1 << 20, np.uint8)
+    tt = np.zeros(4096, np.uint8)
+    hostsim.hostsim_pattern_table(rules, P(pt))
+    hostsim.hostsim_threat_table(rules, P(tt))
+    return pt, tt
+
+
+def _hostsim_set_board(hostsim, rules, size, board, stm, pt, tt):
+    c = size * size
+    mp, mt = np.zeros((c, 4), np.uint8), np.zeros((c, 2), np.uint8)
+    mf, mforb = np.zeros(c, np.uint32), np.zeros(c, np.uint8)
+    ov = ctypes.c_int(0)
+    board = np.ascontiguousarray(board, np.int8)
+    hostsim.hostsim_set_board(rules, size, P(board), stm, P(pt), P(tt), P(mp), P(mt), P(mf), P(mforb), ctypes.byref(ov))
+    assert ov.value == 0
+    return mp, mt, mf, mforb
+
+
+def test_kernel_logic_on_golden_states(hostsim, golden):
+    """patterns_logic.cuh against the committed reference outputs (no reference needed: runs on any box)."""
+    _, states = golden
+    tables = {}
+    for i in range(len(states["rules"])):
+        rules, size, stm = int(states["rules"][i]), int(states["size"][i]), int(states["stm"][i])
+        if rules not in tables:
+            tables[rules] = _hostsim_tables(hostsim, rules)
+        c = size * size
+        mp, mt, mf, mforb = _hostsim_set_board(hostsim, rules, size, states["board"][i][:c], stm, *tables[rules])
+        assert (mp == states["pattern_types"][i][:c]).all(), i
+        assert (mt == states["threats"][i][:c]).all(), i
+        assert (mf == states["features"][i][:c]).all(), i
+        assert (mforb == states["forbidden"][i][:c]).all(), i
+
+
+def test_kernel_logic_on_known_answers(hostsim, golden):
+    known, _ = golden
+    tables = {}
+    for k in known:
+        rules, size, board = k["rules"], k["size"], np.array(k["board"], np.int8)
+        if rules not in tables:
+            tables[rules] = _hostsim_tables(hostsim, rules)
+        pt, tt = tables[rules]
+        if k["kind"] == "outcome":
+            got = hostsim.hostsim_outcome(rules, size, P(board), k["row"], k["col"], k["sign"], 0, P(pt), P(tt))
+            assert got == k["expected"], k
+        elif k["kind"] == "forbidden" and board[k["row"] * size + k["col"]] == 0:
+            _, _, _, mforb = _hostsim_set_board(hostsim, rules, size, board, 1, pt, tt)
+            assert bool(mforb[k["row"] * size + k["col"]]) == k["expected"], k
+        elif k["kind"] == "feature_bit":
+            _, _, mf, _ = _hostsim_set_board(hostsim, rules, size, board, k["stm"], pt, tt)
+            assert bool((int(mf[k["row"] * size + k["col"]]) >> k["bit"]) & 1) == k["expected"], k
+
+
+@pytest.mark.parametrize("rules,size", [(0, 15), (2, 15), (4, 20)])
+def test_kernel_logic_random_boards_vs_reference(ref, hostsim, rules, size):
+    rng = np.random.default_rng(rules * 100 + size)
+    pt, tt = _hostsim_tables(hostsim, rules)
+    for board in random_boards(rng, size, 60):
+        stm = int(rng.integers(1, 3))
+        st = ref.set_board(rules, size, board, stm)
+        mp, mt, mf, mforb = _hostsim_set_board(hostsim, rules, size, board, stm, pt, tt)
+        assert (mp == st["pattern_types"]).all() and (mt == st["threats"]).all()
+        assert (mf == st["features"]).all() and (mforb == st["forbidden"]).all()
+        mode = int(rng.integers(0, 8))
+        aug = np.zeros_like(mf)
+        hostsim.hostsim_augment(P(aug), P(mf), size, mode)
+        assert (aug == ref.augment(st["features"], size, mode)).all()
+
+
+def test_open_three_promotions_match_reference(ref, hostsim):
+    """All 11-cell windows with an empty centre that contain one of the open-three shapes."""
+    rng = np.random.default_rng(5)
+    checked = 0
+    for _ in range(200000):
+        w = int(rng.integers(0, 1 << 22)) & ~(3 << 10)
+        mine = hostsim.hostsim_open3_promotions(w)
+        if mine:
+            assert mine == ref.lib.agref_open3_promotion_moves(w)
+            checked += 1
+    assert checked > 100
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from alphagomoku_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "agb200.h")).read()
+    declared = set(re.findall(r"\b(agb_\w+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.agb_version()
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import alphagomoku_b200 as agb
+    with pytest.raises(agb.AgbError) as err:
+        agb.Engine(agb.GameConfig(), max_boards=4)
+    assert err.value.code == -2
