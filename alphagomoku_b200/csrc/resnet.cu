@@ -1,13 +1,722 @@
+// K4: the ResNet policy/value(/Q) forward as ONE persistent tcgen05 kernel + a small dense kernel for the value head.
+//
+// Replaces AGNetwork::asyncForwardLaunch -> ml::Graph::predict (src/networks/AGNetwork.cpp:61-68) for the graphs built by
+// ResnetPV / ResnetPVQ (src/networks/networks.cpp:71-93, 143-168; blocks.cpp:32-127), BN folded (AGNetwork.cpp:136-149).
+//
+// Design (B200-first):
+//  * one CTA owns one board for the WHOLE network: activations never leave shared memory between layers. Two bf16 board
+//    images (x, h) of [C/8][rows][8] live in smem with a zero halo and two zero columns per row (row pitch S+2), so every
+//    conv tap is the same image read at a shifted start address -- implicit GEMM without im2col and without border code.
+//  * per layer: D[256 positions x F] (fp32, TMEM) = sum over taps of A_tap[256 x C] * W_tap[F x C]^T with tcgen05.mma
+//    (M=128 x2 tiles, N=F, K=16), operands K-major / no swizzle (umma.cuh). One elected thread issues.
+//  * weights stream from L2 through a ring of 32 KiB stages filled by cp.async.bulk (mbarrier complete_tx).
+//  * epilogue warps read TMEM (tcgen05.ld), add bias, ReLU (+ residual, in place), and write the next layer's image;
+//    the policy 1x1 + softmax, the value 1x1 and the Q 1x1 + softmax are fused into the epilogues of their convs.
+//  * input: the 32-bit feature words are unpacked into the stem's bf16 image by the same warps (replaces ml::unpackInput).
 #include "engine.hpp"
+#include "umma.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 namespace agb
 {
-	int net_create(AgbEngine *e) { return e->fail(AGB_ESTATE, "network not built yet"); }
-	void net_destroy(AgbEngine *) {}
+	using namespace umma;
+
+	enum : int { MODE_STEM = 0, MODE_CONV1 = 1, MODE_CONV2 = 2, MODE_POLICY = 3, MODE_QHEAD = 4 };
+	constexpr int kMaxConvLayers = 48;
+	constexpr int kStageBytes = 32768;
+	constexpr int kThreads = 320; // warp 0: weight producer, warp 1: MMA issuer, warps 2..9: epilogue
+	constexpr int kEpilogueThreads = 256;
+
+	struct ConvDesc
+	{
+			uint32_t w_offset; // bytes into the bf16 weight images
+			uint32_t bias_offset; // floats into the bias array
+			uint16_t cin_chunks; // C_in / 8
+			uint8_t radius; // 1 (3x3) or 2 (5x5)
+			uint8_t mode;
+			uint8_t n_taps;
+			uint8_t taps_per_chunk;
+			uint8_t last_trunk; // value 1x1 conv runs after this layer's epilogue
+			uint8_t pad;
+	};
+	struct NetParams
+	{
+			ConvDesc layers[kMaxConvLayers];
+			int n_layers;
+			int S, P, F; // board size, row pitch (S + 2), filters
+			int n_stages;
+			int buf_bytes; // one trunk image: (F / 8) * img_rows * 16
+			int img_rows, in_img_rows;
+			const uint8_t *w_images;
+			const float *bias;
+			const float *policy_w1; // [F], then b1
+			const float *value_w; // [4][F], then b[4]
+			const float *q_w1; // [3][F], then b[3]
+			const uint32_t *features; // [n][S*S]
+			float *policy; // [n][S*S]
+			float *value_hidden; // [n][S*S*4]
+			float *q; // [n][S*S][3] or null
+			int n_boards;
+	};
+
+	struct NetWeights
+	{
+			NetParams params { };
+			uint8_t *d_w_images = nullptr;
+			float *d_small = nullptr; // biases + head vectors
+			float *d_wd1 = nullptr, *d_bd1 = nullptr, *d_wd2 = nullptr, *d_bd2 = nullptr;
+			float *d_value_hidden = nullptr;
+			float *d_policy = nullptr, *d_value = nullptr, *d_q = nullptr; // staging for host entry point
+			int dense_width = 0;
+			size_t smem_bytes = 0;
+			bool loaded = false;
+	};
+
+	namespace
+	{
+		__device__ __forceinline__ void named_barrier_epilogue()
+		{
+			asm volatile("bar.sync 1, 256;" ::: "memory");
+		}
+		__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+		{
+			const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+			return *reinterpret_cast<const uint32_t*>(&v);
+		}
+		__device__ __forceinline__ void unpack_bf16(uint32_t w, float &lo, float &hi)
+		{
+			lo = __uint_as_float(w << 16);
+			hi = __uint_as_float(w & 0xFFFF0000u);
+		}
+
+		__global__ void __launch_bounds__(kThreads, 1) resnet_board_kernel(const __grid_constant__ NetParams prm)
+		{
+			extern __shared__ __align__(1024) uint8_t smem[];
+			const int S = prm.S, P = prm.P, F = prm.F;
+			const int NS = prm.n_stages;
+			uint8_t *buf_x = smem;
+			uint8_t *buf_h = smem + prm.buf_bytes;
+			uint8_t *stages = smem + 2 * prm.buf_bytes;
+			float *partial = reinterpret_cast<float*>(stages + NS * kStageBytes); // [2][3][256]
+			float *logits = partial + 2 * 3 * 256; // [256]
+			float *reduce = logits + 256; // [8]
+			uint64_t *bars = reinterpret_cast<uint64_t*>(reduce + 8);
+			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *img_ready = bars + 17;
+			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+			const uint32_t img_chunk_bytes = prm.img_rows * 16;
+			const uint32_t in_chunk_bytes = prm.in_img_rows * 16;
+			const uint32_t tmem_cols = (2 * F <= 128) ? 128 : 256;
+
+			if (threadIdx.x == 0)
+			{
+				for (int s = 0; s < NS; s++)
+				{
+					mbar_init(&w_full[s], 1);
+					mbar_init(&w_empty[s], 1);
+				}
+				mbar_init(acc_full, 1);
+				mbar_init(img_ready, kEpilogueThreads);
+				fence_mbar_init();
+			}
+			if (warp == 1)
+			{
+				tmem_alloc(tmem_slot, tmem_cols);
+				tmem_relinquish();
+			}
+			// x image: the halo and the two pad columns stay zero for the whole kernel (only valid cells are ever written)
+			for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kThreads)
+				reinterpret_cast<uint4*>(buf_x)[i] = make_uint4(0, 0, 0, 0);
+			tc_fence_before();
+			__syncthreads();
+			tc_fence_after();
+			const uint32_t tmem_base = *tmem_slot;
+
+			if (warp == 0)
+			{ // ===== weight producer: one lane streams every layer's taps through the stage ring =====
+				if (lane == 0)
+				{
+					int stage = 0;
+					uint32_t phase = 0;
+					for (int b = blockIdx.x; b < prm.n_boards; b += gridDim.x)
+						for (int l = 0; l < prm.n_layers; l++)
+						{
+							const ConvDesc &L = prm.layers[l];
+							const uint32_t tap_bytes = L.cin_chunks * F * 16;
+							for (int t0 = 0; t0 < L.n_taps; t0 += L.taps_per_chunk)
+							{
+								const int nt = min(static_cast<int>(L.taps_per_chunk), L.n_taps - t0);
+								mbar_wait(&w_empty[stage], phase ^ 1);
+								mbar_arrive_expect_tx(&w_full[stage], nt * tap_bytes);
+								bulk_g2s(stages + stage * kStageBytes, prm.w_images + L.w_offset + static_cast<size_t>(t0) * tap_bytes, nt * tap_bytes,
+										&w_full[stage]);
+								if (++stage == NS)
+								{
+									stage = 0;
+									phase ^= 1;
+								}
+							}
+						}
+				}
+			}
+			else if (warp == 1)
+			{ // ===== MMA issuer =====
+				if (lane == 0)
+				{
+					int stage = 0;
+					uint32_t phase = 0, img_phase = 0;
+					const uint32_t idesc = idesc_bf16_f32(128, F);
+					for (int b = blockIdx.x; b < prm.n_boards; b += gridDim.x)
+						for (int l = 0; l < prm.n_layers; l++)
+						{
+							const ConvDesc &L = prm.layers[l];
+							const int R = L.radius, KW = 2 * R + 1;
+							const uint32_t tap_bytes = L.cin_chunks * F * 16;
+							const uint32_t a_lbo = (L.mode == MODE_STEM) ? in_chunk_bytes : img_chunk_bytes;
+							const uint8_t *a_img = (L.mode == MODE_STEM or L.mode == MODE_CONV2) ? buf_h : buf_x;
+							mbar_wait(img_ready, img_phase & 1); // input image written, accumulators drained
+							img_phase++;
+							tc_fence_after();
+							for (int t0 = 0; t0 < L.n_taps; t0 += L.taps_per_chunk)
+							{
+								const int nt = min(static_cast<int>(L.taps_per_chunk), L.n_taps - t0);
+								mbar_wait(&w_full[stage], phase);
+								tc_fence_after();
+								const uint32_t stage_addr = smem_u32(stages + stage * kStageBytes);
+								for (int ti = 0; ti < nt; ti++)
+								{
+									const int tap = t0 + ti;
+									const int ky = tap / KW, kx = tap - ky * KW;
+									const uint32_t row0 = ky * P + kx; // image row read by output position 0 for this tap
+									for (int tile = 0; tile < 2; tile++)
+										for (int ks = 0; ks < L.cin_chunks / 2; ks++)
+										{
+											const uint64_t ad = smem_desc(smem_u32(a_img) + (tile * 128 + row0) * 16 + ks * 2 * a_lbo, a_lbo, 128);
+											const uint64_t bd = smem_desc(stage_addr + ti * tap_bytes + ks * 2 * F * 16, F * 16, 128);
+											mma_bf16(tmem_base + tile * F, ad, bd, idesc, (tap | ks) != 0);
+										}
+								}
+								mma_commit(&w_empty[stage]); // stage may be refilled once these MMAs have read it
+								if (++stage == NS)
+								{
+									stage = 0;
+									phase ^= 1;
+								}
+							}
+							mma_commit(acc_full);
+						}
+				}
+			}
+			else
+			{ // ===== epilogue warps (also build the input image and run the fused heads) =====
+				const int et = threadIdx.x - 64;
+				const int quadrant = warp & 3; // TMEM lanes 32*quadrant .. +31 are the ones this warp may read
+				const int half = (warp - 2) >> 2; // which half of the output channels
+				const int cells = S * S;
+				uint32_t acc_phase = 0;
+				for (int b = blockIdx.x; b < prm.n_boards; b += gridDim.x)
+				{
+					// ---- prologue: feature words -> bf16 stem image (32 channels, halo 2) in the h buffer ----
+					for (uint32_t i = et; i < 4 * in_chunk_bytes / 16; i += kEpilogueThreads)
+						reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
+					named_barrier_epilogue();
+					for (int cell = et; cell < cells; cell += kEpilogueThreads)
+					{
+						const uint32_t f = prm.features[static_cast<size_t>(b) * cells + cell];
+						const int y = cell / S, x = cell - y * S;
+						const uint32_t idx = (y + 2) * P + x + 2;
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+						{
+							const uint32_t bits = (f >> (8 * k)) & 0xFFu;
+							uint4 v;
+							v.x = ((bits & 1u) ? 0x3F80u : 0u) | ((bits & 2u) ? 0x3F800000u : 0u);
+							v.y = ((bits & 4u) ? 0x3F80u : 0u) | ((bits & 8u) ? 0x3F800000u : 0u);
+							v.z = ((bits & 16u) ? 0x3F80u : 0u) | ((bits & 32u) ? 0x3F800000u : 0u);
+							v.w = ((bits & 64u) ? 0x3F80u : 0u) | ((bits & 128u) ? 0x3F800000u : 0u);
+							*reinterpret_cast<uint4*>(buf_h + k * in_chunk_bytes + idx * 16) = v;
+						}
+					}
+					fence_proxy_async();
+					tc_fence_before();
+					mbar_arrive(img_ready);
+
+					for (int l = 0; l < prm.n_layers; l++)
+					{
+						const ConvDesc &L = prm.layers[l];
+						mbar_wait(acc_full, acc_phase & 1);
+						acc_phase++;
+						tc_fence_after();
+						if (L.mode == MODE_STEM)
+						{ // the stem image is dead now: give the h buffer its zero halo back
+							for (uint32_t i = et; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kEpilogueThreads)
+								reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
+						}
+						uint8_t *out_img = (L.mode == MODE_CONV1) ? buf_h : buf_x;
+						const float *bias = prm.bias + L.bias_offset;
+						float head[2][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
+						for (int tile = 0; tile < 2; tile++)
+						{
+							const int p = tile * 128 + quadrant * 32 + lane;
+							const int y = p / P, x = p - y * P;
+							const bool valid = (y < S) and (x < S);
+							const uint32_t out_idx = p + P + 1;
+							for (int cb = 0; cb < F / 2; cb += 16)
+							{
+								const int c0 = half * (F / 2) + cb;
+								uint32_t v[16];
+								tmem_ld16(tmem_base + ((quadrant * 32u) << 16) + tile * F + c0, v);
+								tmem_ld_wait();
+								float a[16];
+#pragma unroll
+								for (int j = 0; j < 16; j += 4)
+								{
+									const float4 bj = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+									a[j] = __uint_as_float(v[j]) + bj.x;
+									a[j + 1] = __uint_as_float(v[j + 1]) + bj.y;
+									a[j + 2] = __uint_as_float(v[j + 2]) + bj.z;
+									a[j + 3] = __uint_as_float(v[j + 3]) + bj.w;
+								}
+								if (L.mode == MODE_CONV2)
+								{ // residual: x is updated in place
+#pragma unroll
+									for (int h8 = 0; h8 < 2; h8++)
+									{
+										const uint4 r = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16);
+										float lo, hi;
+										unpack_bf16(r.x, lo, hi); a[8 * h8 + 0] += lo; a[8 * h8 + 1] += hi;
+										unpack_bf16(r.y, lo, hi); a[8 * h8 + 2] += lo; a[8 * h8 + 3] += hi;
+										unpack_bf16(r.z, lo, hi); a[8 * h8 + 4] += lo; a[8 * h8 + 5] += hi;
+										unpack_bf16(r.w, lo, hi); a[8 * h8 + 6] += lo; a[8 * h8 + 7] += hi;
+									}
+								}
+								if (L.mode == MODE_QHEAD)
+								{
+#pragma unroll
+									for (int j = 0; j < 16; j++)
+									{
+										const float t = tanhf(a[j]);
+										head[tile][0] += t * __ldg(prm.q_w1 + c0 + j);
+										head[tile][1] += t * __ldg(prm.q_w1 + F + c0 + j);
+										head[tile][2] += t * __ldg(prm.q_w1 + 2 * F + c0 + j);
+									}
+								}
+								else
+								{
+#pragma unroll
+									for (int j = 0; j < 16; j++)
+										a[j] = fmaxf(a[j], 0.0f);
+									if (L.mode == MODE_POLICY)
+									{
+#pragma unroll
+										for (int j = 0; j < 16; j++)
+											head[tile][0] += a[j] * __ldg(prm.policy_w1 + c0 + j);
+									}
+									else if (valid)
+									{
+#pragma unroll
+										for (int h8 = 0; h8 < 2; h8++)
+										{
+											uint4 o;
+											o.x = pack_bf16(a[8 * h8 + 0], a[8 * h8 + 1]);
+											o.y = pack_bf16(a[8 * h8 + 2], a[8 * h8 + 3]);
+											o.z = pack_bf16(a[8 * h8 + 4], a[8 * h8 + 5]);
+											o.w = pack_bf16(a[8 * h8 + 6], a[8 * h8 + 7]);
+											*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
+										}
+									}
+								}
+							}
+						}
+						tc_fence_before();
+
+						if (L.mode == MODE_POLICY)
+						{ // 1x1 conv to one logit per cell, softmax over the board (createPolicyHead, blocks.cpp:99-107)
+							for (int tile = 0; tile < 2; tile++)
+								partial[half * 256 + tile * 128 + quadrant * 32 + lane] = head[tile][0];
+							named_barrier_epilogue();
+							{
+								const int p = et, y = p / P, x = p - y * P;
+								const bool valid = (y < S) and (x < S);
+								logits[p] = valid ? (partial[p] + partial[256 + p] + __ldg(prm.policy_w1 + F)) : -INFINITY;
+							}
+							named_barrier_epilogue();
+							float m = logits[et];
+							for (int o = 16; o > 0; o >>= 1)
+								m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+							if (lane == 0)
+								reduce[warp - 2] = m;
+							named_barrier_epilogue();
+							m = reduce[0];
+							for (int w = 1; w < 8; w++)
+								m = fmaxf(m, reduce[w]);
+							const float e = expf(logits[et] - m);
+							float s = e;
+							for (int o = 16; o > 0; o >>= 1)
+								s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+							named_barrier_epilogue();
+							if (lane == 0)
+								reduce[warp - 2] = s;
+							named_barrier_epilogue();
+							s = 0.0f;
+							for (int w = 0; w < 8; w++)
+								s += reduce[w];
+							const int p = et, y = p / P, x = p - y * P;
+							if (y < S and x < S)
+								prm.policy[static_cast<size_t>(b) * cells + y * S + x] = e / s;
+							named_barrier_epilogue();
+						}
+						else if (L.mode == MODE_QHEAD)
+						{ // 1x1 conv to 3 logits per cell, softmax over them (createActionValuesHead, blocks.cpp:119-127)
+							for (int tile = 0; tile < 2; tile++)
+								for (int k = 0; k < 3; k++)
+									partial[(half * 3 + k) * 256 + tile * 128 + quadrant * 32 + lane] = head[tile][k];
+							named_barrier_epilogue();
+							const int p = et, y = p / P, x = p - y * P;
+							if (y < S and x < S and prm.q != nullptr)
+							{
+								float z[3];
+								for (int k = 0; k < 3; k++)
+									z[k] = partial[k * 256 + p] + partial[(3 + k) * 256 + p] + __ldg(prm.q_w1 + 3 * F + k);
+								const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
+								const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
+								const float inv = 1.0f / (e0 + e1 + e2);
+								float *dst = prm.q + (static_cast<size_t>(b) * cells + y * S + x) * 3;
+								dst[0] = e0 * inv;
+								dst[1] = e1 * inv;
+								dst[2] = e2 * inv;
+							}
+							named_barrier_epilogue();
+						}
+						else if (L.last_trunk)
+						{ // value head 1x1 conv F -> 4 + ReLU on the final trunk output (createValueHead, blocks.cpp:108-111)
+							named_barrier_epilogue();
+							for (int cell = et; cell < cells; cell += kEpilogueThreads)
+							{
+								const int y = cell / S, x = cell - y * S;
+								const uint32_t idx = (y + 1) * P + x + 1;
+								float s4[4] = { 0.f, 0.f, 0.f, 0.f };
+								for (int ch = 0; ch < F / 8; ch++)
+								{
+									const uint4 r = *reinterpret_cast<const uint4*>(buf_x + ch * img_chunk_bytes + idx * 16);
+									float xv[8];
+									unpack_bf16(r.x, xv[0], xv[1]);
+									unpack_bf16(r.y, xv[2], xv[3]);
+									unpack_bf16(r.z, xv[4], xv[5]);
+									unpack_bf16(r.w, xv[6], xv[7]);
+#pragma unroll
+									for (int k = 0; k < 4; k++)
+#pragma unroll
+										for (int j = 0; j < 8; j++)
+											s4[k] += xv[j] * __ldg(prm.value_w + k * F + ch * 8 + j);
+								}
+								float4 o;
+								o.x = fmaxf(s4[0] + __ldg(prm.value_w + 4 * F + 0), 0.f);
+								o.y = fmaxf(s4[1] + __ldg(prm.value_w + 4 * F + 1), 0.f);
+								o.z = fmaxf(s4[2] + __ldg(prm.value_w + 4 * F + 2), 0.f);
+								o.w = fmaxf(s4[3] + __ldg(prm.value_w + 4 * F + 3), 0.f);
+								*reinterpret_cast<float4*>(prm.value_hidden + (static_cast<size_t>(b) * cells + cell) * 4) = o;
+							}
+						}
+						if (l + 1 < prm.n_layers)
+						{ // hand the image (and the drained accumulators) to the MMA warp
+							fence_proxy_async();
+							mbar_arrive(img_ready);
+						}
+					}
+				}
+			}
+			tc_fence_before();
+			__syncthreads();
+			if (warp == 1)
+				tmem_dealloc(tmem_base, tmem_cols);
+		}
+
+		// ---- value head: dense(4*cells -> D) + ReLU, dense(D -> 3), softmax (createValueHead, blocks.cpp:112-117) --------
+		// one CTA per board, D threads; 0.02 % of the network's FLOPs
+		__global__ void value_head_kernel(const float *__restrict__ hidden, const float *__restrict__ wd1, const float *__restrict__ bd1,
+				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D)
+		{
+			extern __shared__ float sh[]; // [in_dim] + [D]
+			float *sx = sh, *sd = sh + in_dim;
+			for (int b = blockIdx.x; b < n; b += gridDim.x)
+			{
+				for (int i = threadIdx.x; i < in_dim; i += blockDim.x)
+					sx[i] = hidden[static_cast<size_t>(b) * in_dim + i];
+				__syncthreads();
+				const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+				for (int o = warp; o < D; o += nwarps)
+				{ // one warp per output neuron: coalesced reads of its weight row
+					const float *w = wd1 + static_cast<size_t>(o) * in_dim;
+					float s = 0.f;
+					for (int i = lane; i < in_dim; i += 32)
+						s += sx[i] * __ldg(w + i);
+					for (int k = 16; k > 0; k >>= 1)
+						s += __shfl_xor_sync(0xFFFFFFFFu, s, k);
+					if (lane == 0)
+						sd[o] = fmaxf(s + bd1[o], 0.f);
+				}
+				__syncthreads();
+				if (warp == 0)
+				{
+					float z[3];
+					for (int k = 0; k < 3; k++)
+					{
+						float s = 0.f;
+						for (int i = lane; i < D; i += 32)
+							s += sd[i] * wd2[k * D + i];
+						for (int o = 16; o > 0; o >>= 1)
+							s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+						z[k] = s + bd2[k];
+					}
+					if (lane == 0)
+					{
+						const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
+						const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
+						const float inv = 1.0f / (e0 + e1 + e2);
+						value[b * 3 + 0] = e0 * inv;
+						value[b * 3 + 1] = e1 * inv;
+						value[b * 3 + 2] = e2 * inv;
+					}
+				}
+				__syncthreads();
+			}
+		}
+
+		size_t blob_floats(const AgbConfig &c)
+		{
+			const size_t f = c.filters, cells = static_cast<size_t>(c.rows) * c.cols, d = std::min<size_t>(256, 2 * f);
+			size_t n = f * 25 * 32 + f;
+			n += static_cast<size_t>(c.blocks) * 2 * (f * 9 * f + f);
+			n += f * 9 * f + f + f + 1;
+			n += 4 * f + 4 + d * cells * 4 + d + 3 * d + 3;
+			if (c.q_head)
+				n += f * 9 * f + f + 3 * f + 3;
+			return n;
+		}
+		// fp32 W[F][k][k][cin] -> bf16 tap images [tap][cin/8][F][8]
+		void append_conv_image(std::vector<uint16_t> &img, const float *w, int F, int k, int cin)
+		{
+			const auto to_bf16 = [](float x)
+			{
+				uint32_t u;
+				std::memcpy(&u, &x, 4);
+				const uint32_t rounded = u + 0x7FFFu + ((u >> 16) & 1u); // round to nearest even
+				return static_cast<uint16_t>(rounded >> 16);
+			};
+			for (int tap = 0; tap < k * k; tap++)
+				for (int kc = 0; kc < cin / 8; kc++)
+					for (int co = 0; co < F; co++)
+						for (int e = 0; e < 8; e++)
+							img.push_back(to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]));
+		}
+	}
+
+	int net_create(AgbEngine *e)
+	{
+		const AgbConfig &c = e->cfg;
+		if (c.filters != 64 and c.filters != 128)
+			return e->fail(AGB_EINVAL, "filters must be 64 or 128");
+		if (c.rows * (c.rows + 2) > 256)
+			return e->fail(AGB_EINVAL, "network kernel supports boards up to 15x15 in this build (20x20 planned, see DESIGN.md)");
+		if (1 + 2 * c.blocks + 2 > kMaxConvLayers)
+			return e->fail(AGB_EINVAL, "too many blocks");
+		e->net = new NetWeights();
+		return AGB_OK;
+	}
+	void net_destroy(AgbEngine *e)
+	{
+		if (e->net == nullptr)
+			return;
+		NetWeights *n = e->net;
+		void *ptrs[] = { n->d_w_images, n->d_small, n->d_wd1, n->d_bd1, n->d_wd2, n->d_bd2, n->d_value_hidden, n->d_policy, n->d_value, n->d_q };
+		for (void *p : ptrs)
+			if (p)
+				cudaFree(p);
+		delete n;
+		e->net = nullptr;
+	}
+
+	int net_load(AgbEngine *e, const float *blob, size_t bytes)
+	{
+		NetWeights *n = e->net;
+		if (n == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without a network (blocks == 0)");
+		const AgbConfig &c = e->cfg;
+		if (bytes != blob_floats(c) * sizeof(float))
+			return e->fail(AGB_EINVAL, "weight blob has the wrong size: expected " + std::to_string(blob_floats(c) * 4) + " bytes");
+		const int F = c.filters, S = c.rows, cells = S * S, D = std::min(256, 2 * F);
+		NetParams &p = n->params;
+		p = NetParams { };
+		p.S = S;
+		p.P = S + 2;
+		p.F = F;
+		p.img_rows = ((256 + 2 * p.P + 2) + 7) / 8 * 8;
+		p.in_img_rows = ((256 + 4 * p.P + 4) + 7) / 8 * 8;
+		p.buf_bytes = (F / 8) * p.img_rows * 16;
+		p.n_stages = (F == 128) ? 2 : 4;
+
+		std::vector<uint16_t> images;
+		std::vector<float> small; // per-conv biases, then head vectors
+		const float *cur = blob;
+		int nl = 0;
+		const auto add_conv = [&](int k, int cin, int mode, bool last_trunk)
+		{
+			ConvDesc &L = p.layers[nl++];
+			while (small.size() % 4 != 0)
+				small.push_back(0.0f); // biases are read as float4
+			L.w_offset = static_cast<uint32_t>(images.size() * 2);
+			L.bias_offset = static_cast<uint32_t>(small.size());
+			L.cin_chunks = static_cast<uint16_t>(cin / 8);
+			L.radius = static_cast<uint8_t>(k / 2);
+			L.mode = static_cast<uint8_t>(mode);
+			L.n_taps = static_cast<uint8_t>(k * k);
+			const int tap_bytes = cin * F * 2;
+			L.taps_per_chunk = static_cast<uint8_t>(std::max(1, kStageBytes / tap_bytes));
+			L.last_trunk = last_trunk;
+			append_conv_image(images, cur, F, k, cin);
+			cur += static_cast<size_t>(F) * k * k * cin;
+			small.insert(small.end(), cur, cur + F);
+			cur += F;
+		};
+		add_conv(5, 32, MODE_STEM, c.blocks == 0);
+		for (int i = 0; i < c.blocks; i++)
+		{
+			add_conv(3, F, MODE_CONV1, false);
+			add_conv(3, F, MODE_CONV2, i + 1 == c.blocks);
+		}
+		add_conv(3, F, MODE_POLICY, false);
+		const size_t policy_w1_off = small.size();
+		small.insert(small.end(), cur, cur + F + 1);
+		cur += F + 1;
+		const size_t value_w_off = small.size();
+		small.insert(small.end(), cur, cur + 4 * F + 4);
+		cur += 4 * F + 4;
+		const float *wd1 = cur;
+		cur += static_cast<size_t>(D) * cells * 4;
+		const float *bd1 = cur;
+		cur += D;
+		const float *wd2 = cur;
+		cur += 3 * D;
+		const float *bd2 = cur;
+		cur += 3;
+		size_t q_w1_off = 0;
+		if (c.q_head)
+		{
+			add_conv(3, F, MODE_QHEAD, false);
+			q_w1_off = small.size();
+			small.insert(small.end(), cur, cur + 3 * F + 3);
+			cur += 3 * F + 3;
+		}
+		p.n_layers = nl;
+
+		const size_t cap = static_cast<size_t>(c.max_boards);
+		const auto upload = [&](auto **dst, const void *src, size_t nbytes) -> cudaError_t
+		{
+			if (*dst)
+				cudaFree(*dst);
+			cudaError_t err = cudaMalloc(reinterpret_cast<void**>(dst), nbytes);
+			if (err != cudaSuccess)
+				return err;
+			return src ? cudaMemcpyAsync(*dst, src, nbytes, cudaMemcpyHostToDevice, e->stream) : cudaSuccess;
+		};
+		AGB_CUDA_CHECK(e, upload(&n->d_w_images, images.data(), images.size() * 2));
+		AGB_CUDA_CHECK(e, upload(&n->d_small, small.data(), small.size() * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_wd1, wd1, static_cast<size_t>(D) * cells * 4 * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_bd1, bd1, D * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_wd2, wd2, 3 * D * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_bd2, bd2, 3 * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_value_hidden, nullptr, cap * cells * 4 * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_policy, nullptr, cap * cells * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_value, nullptr, cap * 3 * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_q, nullptr, cap * cells * 3 * 4));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		p.w_images = n->d_w_images;
+		p.bias = n->d_small;
+		p.policy_w1 = n->d_small + policy_w1_off;
+		p.value_w = n->d_small + value_w_off;
+		p.q_w1 = c.q_head ? n->d_small + q_w1_off : nullptr;
+		p.value_hidden = n->d_value_hidden;
+		n->dense_width = D;
+		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * kStageBytes + (2 * 3 * 256 + 256 + 8) * 4 + 20 * 8;
+		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
+		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cells * 4 + D) * 4));
+		n->loaded = true;
+		return AGB_OK;
+	}
+
+	int net_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n_boards, float *policy_dev, float *value_dev, float *q_dev)
+	{
+		NetWeights *n = e->net;
+		if (n == nullptr or not n->loaded)
+			return e->fail(AGB_ESTATE, "no weights loaded");
+		NetParams p = n->params;
+		p.features = features_dev;
+		p.policy = policy_dev;
+		p.q = e->cfg.q_head ? q_dev : nullptr;
+		p.n_boards = n_boards;
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
+		const int grid = n_boards < sms ? n_boards : sms;
+		resnet_board_kernel<<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		const int cells = e->cells, D = n->dense_width;
+		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, e->stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
+				n->d_bd2, value_dev, n_boards, cells * 4, D);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		return AGB_OK;
+	}
 }
+
 extern "C"
 {
-	int agb_load_weights(AgbEngine *e, const void *, size_t) { return e->fail(AGB_ESTATE, "network not built yet"); }
-	size_t agb_weights_size(const AgbEngine *) { return 0; }
-	int agb_forward(AgbEngine *e, const uint32_t *, int, float *, float *, float *) { return e->fail(AGB_ESTATE, "network not built yet"); }
-	int agb_forward_dev(AgbEngine *e, const uint32_t *, int, float *, float *, float *) { return e->fail(AGB_ESTATE, "network not built yet"); }
+	size_t agb_weights_size(const AgbEngine *e)
+	{
+		return (e == nullptr or e->net == nullptr) ? 0 : agb::blob_floats(e->cfg) * sizeof(float);
+	}
+	int agb_load_weights(AgbEngine *e, const void *blob_host, size_t bytes)
+	{
+		if (blob_host == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		return agb::net_load(e, static_cast<const float*>(blob_host), bytes);
+	}
+	int agb_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n, float *policy_dev, float *value_dev, float *q_dev)
+	{
+		if (n < 0 or n > e->store.capacity)
+			return e->fail(AGB_EINVAL, "n exceeds max_boards");
+		if (features_dev == nullptr or policy_dev == nullptr or value_dev == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		if (n == 0)
+			return AGB_OK;
+		return agb::net_forward_dev(e, features_dev, n, policy_dev, value_dev, q_dev);
+	}
+	int agb_forward(AgbEngine *e, const uint32_t *features_host, int n, float *policy_host, float *value_host, float *q_host)
+	{
+		if (n < 0 or n > e->store.capacity)
+			return e->fail(AGB_EINVAL, "n exceeds max_boards");
+		if (features_host == nullptr or policy_host == nullptr or value_host == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		if (n == 0)
+			return AGB_OK;
+		agb::NetWeights *net = e->net;
+		if (net == nullptr or not net->loaded)
+			return e->fail(AGB_ESTATE, "no weights loaded");
+		const size_t cells = e->cells;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_features, features_host, n * cells * 4, cudaMemcpyHostToDevice, e->stream));
+		const int rc = agb::net_forward_dev(e, e->d_features, n, net->d_policy, net->d_value, net->d_q);
+		if (rc != AGB_OK)
+			return rc;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(policy_host, net->d_policy, n * cells * 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(value_host, net->d_value, n * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+		if (q_host != nullptr and e->cfg.q_head)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(q_host, net->d_q, n * cells * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		return AGB_OK;
+	}
 }

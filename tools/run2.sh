@@ -1,0 +1,3 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_resnet_gpu.py -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_resnet.log
