@@ -17,6 +17,8 @@
 #include "umma.cuh"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -26,7 +28,7 @@ namespace agb
 
 	enum : int { MODE_STEM = 0, MODE_CONV1 = 1, MODE_CONV2 = 2, MODE_POLICY = 3, MODE_QHEAD = 4 };
 	constexpr int kMaxConvLayers = 48;
-	constexpr int kStageBytes = 32768;
+	constexpr int kMaxStages = 8;
 	constexpr int kThreads = 320; // warp 0: weight producer, warp 1: MMA issuer, warps 2..9: epilogue
 	constexpr int kEpilogueThreads = 256;
 
@@ -38,7 +40,7 @@ namespace agb
 			uint8_t radius; // 1 (3x3) or 2 (5x5)
 			uint8_t mode;
 			uint8_t n_taps;
-			uint8_t taps_per_chunk;
+			uint8_t unused;
 			uint8_t last_trunk; // value 1x1 conv runs after this layer's epilogue
 			uint8_t pad;
 	};
@@ -47,7 +49,8 @@ namespace agb
 			ConvDesc layers[kMaxConvLayers];
 			int n_layers;
 			int S, P, F; // board size, row pitch (S + 2), filters
-			int n_stages;
+			int n_stages, stage_bytes; // weight ring: stage_bytes = kc_per_stage * F * 16
+			int kc_per_stage; // 8-channel weight slices (F rows x 16 bytes) per stage, even
 			int buf_bytes; // one trunk image: (F / 8) * img_rows * 16
 			int img_rows, in_img_rows;
 			const uint8_t *w_images;
@@ -60,6 +63,7 @@ namespace agb
 			float *value_hidden; // [n][S*S*4]
 			float *q; // [n][S*S][3] or null
 			int n_boards;
+			long long *trace; // optional [n_layers][4] clock64 stamps of CTA 0's first board (AGB_NET_TRACE)
 	};
 
 	struct NetWeights
@@ -100,7 +104,7 @@ namespace agb
 			uint8_t *buf_x = smem;
 			uint8_t *buf_h = smem + prm.buf_bytes;
 			uint8_t *stages = smem + 2 * prm.buf_bytes;
-			float *partial = reinterpret_cast<float*>(stages + NS * kStageBytes); // [2][3][256]
+			float *partial = reinterpret_cast<float*>(stages + NS * prm.stage_bytes); // [2][3][256]
 			float *logits = partial + 2 * 3 * 256; // [256]
 			float *reduce = logits + 256; // [8]
 			uint64_t *bars = reinterpret_cast<uint64_t*>(reduce + 8);
@@ -146,14 +150,13 @@ namespace agb
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
-							const uint32_t tap_bytes = L.cin_chunks * F * 16;
-							for (int t0 = 0; t0 < L.n_taps; t0 += L.taps_per_chunk)
+							const int total_kc = L.n_taps * L.cin_chunks; // the layer's weights as a stream of 8-channel slices
+							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
-								const int nt = min(static_cast<int>(L.taps_per_chunk), L.n_taps - t0);
+								const uint32_t bytes = min(prm.kc_per_stage, total_kc - kc0) * F * 16;
 								mbar_wait(&w_empty[stage], phase ^ 1);
-								mbar_arrive_expect_tx(&w_full[stage], nt * tap_bytes);
-								bulk_g2s(stages + stage * kStageBytes, prm.w_images + L.w_offset + static_cast<size_t>(t0) * tap_bytes, nt * tap_bytes,
-										&w_full[stage]);
+								mbar_arrive_expect_tx(&w_full[stage], bytes);
+								bulk_g2s(stages + stage * prm.stage_bytes, prm.w_images + L.w_offset + static_cast<size_t>(kc0) * F * 16, bytes, &w_full[stage]);
 								if (++stage == NS)
 								{
 									stage = 0;
@@ -174,31 +177,43 @@ namespace agb
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
-							const int R = L.radius, KW = 2 * R + 1;
-							const uint32_t tap_bytes = L.cin_chunks * F * 16;
+							const int KW = 2 * L.radius + 1;
 							const uint32_t a_lbo = (L.mode == MODE_STEM) ? in_chunk_bytes : img_chunk_bytes;
-							const uint8_t *a_img = (L.mode == MODE_STEM or L.mode == MODE_CONV2) ? buf_h : buf_x;
+							const uint32_t a_img = smem_u32((L.mode == MODE_STEM or L.mode == MODE_CONV2) ? buf_h : buf_x);
+							const int total_kc = L.n_taps * L.cin_chunks, cin_chunks = L.cin_chunks;
+							// descriptors are advanced by adding to their 14-bit start-address field (16-byte units); no field can carry
+							const uint64_t a_desc0 = smem_desc(a_img, a_lbo, 128), b_desc0 = smem_desc(smem_u32(stages), F * 16, 128);
+							const uint32_t a_kc_step = a_lbo >> 4, b_kc_step = F, stage_step = prm.stage_bytes >> 4;
 							mbar_wait(img_ready, img_phase & 1); // input image written, accumulators drained
 							img_phase++;
 							tc_fence_after();
-							for (int t0 = 0; t0 < L.n_taps; t0 += L.taps_per_chunk)
+							if (prm.trace and b == 0)
+								prm.trace[4 * l + 0] = clock64();
+							int tap = 0, kin = 0, ky = 0, kx = 0; // position in the layer's stream of 8-channel weight slices
+							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
-								const int nt = min(static_cast<int>(L.taps_per_chunk), L.n_taps - t0);
+								const int nkc = min(prm.kc_per_stage, total_kc - kc0);
 								mbar_wait(&w_full[stage], phase);
 								tc_fence_after();
-								const uint32_t stage_addr = smem_u32(stages + stage * kStageBytes);
-								for (int ti = 0; ti < nt; ti++)
-								{
-									const int tap = t0 + ti;
-									const int ky = tap / KW, kx = tap - ky * KW;
-									const uint32_t row0 = ky * P + kx; // image row read by output position 0 for this tap
-									for (int tile = 0; tile < 2; tile++)
-										for (int ks = 0; ks < L.cin_chunks / 2; ks++)
+								uint64_t bd = b_desc0 + stage * stage_step;
+								for (int j = 0; j < nkc; j += 2)
+								{ // one K=16 step: two 8-channel slices of one tap
+									const uint64_t ad = a_desc0 + (ky * P + kx) + kin * a_kc_step;
+									const bool acc = (kc0 + j) != 0;
+									mma_bf16(tmem_base, ad, bd, idesc, acc);
+									mma_bf16(tmem_base + F, ad + 128, bd, idesc, acc);
+									bd += 2 * b_kc_step;
+									kin += 2;
+									if (kin == cin_chunks)
+									{
+										kin = 0;
+										tap++;
+										if (++kx == KW)
 										{
-											const uint64_t ad = smem_desc(smem_u32(a_img) + (tile * 128 + row0) * 16 + ks * 2 * a_lbo, a_lbo, 128);
-											const uint64_t bd = smem_desc(stage_addr + ti * tap_bytes + ks * 2 * F * 16, F * 16, 128);
-											mma_bf16(tmem_base + tile * F, ad, bd, idesc, (tap | ks) != 0);
+											kx = 0;
+											ky++;
 										}
+									}
 								}
 								mma_commit(&w_empty[stage]); // stage may be refilled once these MMAs have read it
 								if (++stage == NS)
@@ -207,6 +222,8 @@ namespace agb
 									phase ^= 1;
 								}
 							}
+							if (prm.trace and b == 0)
+								prm.trace[4 * l + 1] = clock64();
 							mma_commit(acc_full);
 						}
 				}
@@ -251,6 +268,8 @@ namespace agb
 						mbar_wait(acc_full, acc_phase & 1);
 						acc_phase++;
 						tc_fence_after();
+						if (prm.trace and b == 0 and et == 0)
+							prm.trace[4 * l + 2] = clock64();
 						if (L.mode == MODE_STEM)
 						{ // the stem image is dead now: give the h buffer its zero halo back
 							for (uint32_t i = et; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kEpilogueThreads)
@@ -422,6 +441,8 @@ namespace agb
 								*reinterpret_cast<float4*>(prm.value_hidden + (static_cast<size_t>(b) * cells + cell) * 4) = o;
 							}
 						}
+						if (prm.trace and b == 0 and et == 0)
+							prm.trace[4 * l + 3] = clock64();
 						if (l + 1 < prm.n_layers)
 						{ // hand the image (and the drained accumulators) to the MMA warp
 							fence_proxy_async();
@@ -558,7 +579,14 @@ namespace agb
 		p.img_rows = ((256 + 2 * p.P + 2) + 7) / 8 * 8;
 		p.in_img_rows = ((256 + 4 * p.P + 4) + 7) / 8 * 8;
 		p.buf_bytes = (F / 8) * p.img_rows * 16;
-		p.n_stages = (F == 128) ? 2 : 4;
+		{ // weight ring geometry (tunable: AGB_NET_STAGE_KB / AGB_NET_STAGES)
+			const char *kb = getenv("AGB_NET_STAGE_KB"), *ns = getenv("AGB_NET_STAGES");
+			p.stage_bytes = (kb ? atoi(kb) : 32) * 1024; // measured best on B200 (profiles/r01_k4_weight_ring.txt)
+			p.kc_per_stage = p.stage_bytes / (F * 16);
+			p.n_stages = ns ? atoi(ns) : ((F == 128) ? 2 : 4);
+			if (p.kc_per_stage < 2 or p.kc_per_stage % 2 != 0 or p.n_stages < 2 or p.n_stages > kMaxStages)
+				return e->fail(AGB_EINVAL, "bad weight ring geometry");
+		}
 
 		std::vector<uint16_t> images;
 		std::vector<float> small; // per-conv biases, then head vectors
@@ -575,8 +603,6 @@ namespace agb
 			L.radius = static_cast<uint8_t>(k / 2);
 			L.mode = static_cast<uint8_t>(mode);
 			L.n_taps = static_cast<uint8_t>(k * k);
-			const int tap_bytes = cin * F * 2;
-			L.taps_per_chunk = static_cast<uint8_t>(std::max(1, kStageBytes / tap_bytes));
 			L.last_trunk = last_trunk;
 			append_conv_image(images, cur, F, k, cin);
 			cur += static_cast<size_t>(F) * k * k * cin;
@@ -642,7 +668,7 @@ namespace agb
 		p.q_w1 = c.q_head ? n->d_small + q_w1_off : nullptr;
 		p.value_hidden = n->d_value_hidden;
 		n->dense_width = D;
-		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * kStageBytes + (2 * 3 * 256 + 256 + 8) * 4 + 20 * 8;
+		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (2 * 3 * 256 + 256 + 8) * 4 + 20 * 8;
 		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
 		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cells * 4 + D) * 4));
 		n->loaded = true;
@@ -659,12 +685,30 @@ namespace agb
 		p.policy = policy_dev;
 		p.q = e->cfg.q_head ? q_dev : nullptr;
 		p.n_boards = n_boards;
+		static long long *d_trace = nullptr;
+		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
+		if (trace and d_trace == nullptr)
+			cudaMalloc(&d_trace, kMaxConvLayers * 4 * sizeof(long long));
+		p.trace = trace ? d_trace : nullptr;
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
 		const int grid = n_boards < sms ? n_boards : sms;
 		resnet_board_kernel<<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
+		if (trace)
+		{
+			std::vector<long long> h(kMaxConvLayers * 4);
+			cudaStreamSynchronize(e->stream);
+			cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+			FILE *f = fopen(getenv("AGB_NET_TRACE"), "w");
+			if (f)
+			{
+				for (int l = 0; l < p.n_layers; l++)
+					fprintf(f, "%d %lld %lld %lld %lld\n", l, h[4 * l] - h[0], h[4 * l + 1] - h[0], h[4 * l + 2] - h[0], h[4 * l + 3] - h[0]);
+				fclose(f);
+			}
+		}
 		const int cells = e->cells, D = n->dense_width;
 		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, e->stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
 				n->d_bd2, value_dev, n_boards, cells * 4, D);

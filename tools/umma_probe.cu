@@ -12,7 +12,7 @@ using namespace agb::umma;
 
 constexpr int M = 128, K = 64, A_ROWS = 192;
 
-__global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16 *a_img, const __nv_bfloat16 *b_img, float *d, int n, int swap, int shift, int bulk)
+__global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16 *a_img, const __nv_bfloat16 *b_img, float *d, int n, int swap, int shift, int bulk, int timing_reps, long long *cycles)
 {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	__shared__ uint64_t bar_load, bar_mma;
@@ -75,6 +75,21 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16 *a_img, 
 			mma_bf16(tmem, ad, bd, idesc, k > 0);
 		}
 		mma_commit(&bar_mma);
+		if (timing_reps > 0)
+		{ // throughput: timing_reps x (2 tiles x 4 K-steps) back-to-back MMAs on resident operands, second accumulator
+			mbar_wait(&bar_mma, 0);
+			const long long t0 = clock64();
+			for (int rep = 0; rep < timing_reps; rep++)
+				for (int k = 0; k < K / 16; k++)
+				{
+					const uint64_t ad = smem_desc(smem_u32(sa) + ((rep & 7) * 3) * 16 + k * 2 * A_ROWS * 16, a_lbo, a_sbo);
+					const uint64_t bd = smem_desc(smem_u32(sb) + k * 2 * n * 16, b_lbo, b_sbo);
+					mma_bf16(tmem + 128, ad, bd, idesc, true);
+				}
+			mma_commit(&bar_load);
+			mbar_wait(&bar_load, bulk ? 1 : 0);
+			cycles[0] = clock64() - t0;
+		}
 	}
 	mbar_wait(&bar_mma, 0);
 	tc_fence_after();
@@ -95,6 +110,10 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16 *a_img, 
 int main(int argc, char **argv)
 {
 	const int swap = argc > 1 ? atoi(argv[1]) : 0, shift = argc > 2 ? atoi(argv[2]) : 0, n = argc > 3 ? atoi(argv[3]) : 128, bulk = argc > 4 ? atoi(argv[4]) : 0;
+	const int timing_reps = argc > 5 ? atoi(argv[5]) : 0;
+	long long *dcycles;
+	cudaMalloc(&dcycles, 8);
+	cudaMemset(dcycles, 0, 8);
 	std::vector<float> a(A_ROWS * K), b(n * K);
 	srand(1);
 	for (auto &x : a) x = (rand() % 17 - 8) / 8.0f;
@@ -116,7 +135,7 @@ int main(int argc, char **argv)
 	cudaMemset(dd, 0, M * n * 4);
 	const int smem_bytes = (K / 8) * (A_ROWS + n) * 16;
 	cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-	probe_kernel<<<1, 128, smem_bytes>>>(da, db, dd, n, swap, shift, bulk);
+	probe_kernel<<<1, 128, smem_bytes>>>(da, db, dd, n, swap, shift, bulk, timing_reps, dcycles);
 	cudaError_t err = cudaDeviceSynchronize();
 	if (err != cudaSuccess)
 	{
@@ -135,5 +154,11 @@ int main(int argc, char **argv)
 			max_err = fmax(max_err, fabs(ref - d[m * n + j]));
 		}
 	printf("swap=%d shift=%d n=%d bulk=%d : max_err=%g %s\n", swap, shift, n, bulk, max_err, max_err < 1e-3 ? "PASS" : "FAIL");
+	if (timing_reps > 0)
+	{
+		long long c = 0;
+		cudaMemcpy(&c, dcycles, 8, cudaMemcpyDeviceToHost);
+		printf("  timing: %d MMAs (M=128 N=%d K=16) in %lld cycles = %.1f cycles/MMA\n", timing_reps * 4, n, c, (double) c / (timing_reps * 4));
+	}
 	return 0;
 }
