@@ -50,6 +50,7 @@ namespace agb
 	int build_tables(AgbEngine *e);
 	// patterns.cu
 	int launch_set_boards(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, int n, uint32_t *features_dev);
+	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev);
 	int launch_add_undo(AgbEngine *e, const uint16_t *moves_dev, int n, bool undo);
 	int launch_encode(AgbEngine *e, int n, uint32_t *features_dev);
 	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n);

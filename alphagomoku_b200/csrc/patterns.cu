@@ -57,9 +57,11 @@ namespace agb
 
 		// ---- K1 + K3 ---------------------------------------------------------------------------------------------
 		__global__ void __launch_bounds__(kWarpsPerBlock * 32) set_boards_kernel(BoardStore store, Tables tables, const int8_t *__restrict__ boards,
-				const int8_t *__restrict__ sign_to_move, int n, int S, int rules, uint32_t *__restrict__ features, uint32_t *status)
+				const int8_t *__restrict__ sign_to_move, int n, int S, int rules, uint32_t *__restrict__ features, uint32_t *status, const int *__restrict__ n_dev)
 		{
 			__shared__ WarpScratch scratch[kWarpsPerBlock];
+			if (n_dev != nullptr)
+				n = *n_dev; // batch size produced on the device (lockstep engine)
 			const int lane = threadIdx.x & 31;
 			const int warp = threadIdx.x >> 5;
 			WarpScratch &ws = scratch[warp];
@@ -381,7 +383,15 @@ namespace agb
 	int launch_set_boards(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, int n, uint32_t *features_dev)
 	{
 		set_boards_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, boards_dev, stm_dev, n, e->cfg.rows, e->cfg.rules,
-				features_dev, e->d_status);
+				features_dev, e->d_status, nullptr);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		return AGB_OK;
+	}
+	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev)
+	{
+		set_boards_kernel<<<grid_for(max_n), kWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, boards_dev, stm_dev, max_n, e->cfg.rows, e->cfg.rules,
+				features_dev, e->d_status, n_dev);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

@@ -63,6 +63,7 @@ namespace agb
 			float *value_hidden; // [n][S*S*4]
 			float *q; // [n][S*S][3] or null
 			int n_boards;
+			const int *n_boards_dev; // if set, the batch size is read from device memory
 			long long *trace; // optional [n_layers][4] clock64 stamps of CTA 0's first board (AGB_NET_TRACE)
 	};
 
@@ -100,6 +101,7 @@ namespace agb
 		{
 			extern __shared__ __align__(1024) uint8_t smem[];
 			const int S = prm.S, P = prm.P, F = prm.F;
+			const int n_boards = prm.n_boards_dev ? *prm.n_boards_dev : prm.n_boards;
 			const int NS = prm.n_stages;
 			uint8_t *buf_x = smem;
 			uint8_t *buf_h = smem + prm.buf_bytes;
@@ -146,7 +148,7 @@ namespace agb
 				{
 					int stage = 0;
 					uint32_t phase = 0;
-					for (int b = blockIdx.x; b < prm.n_boards; b += gridDim.x)
+					for (int b = blockIdx.x; b < n_boards; b += gridDim.x)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -173,7 +175,7 @@ namespace agb
 					int stage = 0;
 					uint32_t phase = 0, img_phase = 0;
 					const uint32_t idesc = idesc_bf16_f32(128, F);
-					for (int b = blockIdx.x; b < prm.n_boards; b += gridDim.x)
+					for (int b = blockIdx.x; b < n_boards; b += gridDim.x)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -235,7 +237,7 @@ namespace agb
 				const int half = (warp - 2) >> 2; // which half of the output channels
 				const int cells = S * S;
 				uint32_t acc_phase = 0;
-				for (int b = blockIdx.x; b < prm.n_boards; b += gridDim.x)
+				for (int b = blockIdx.x; b < n_boards; b += gridDim.x)
 				{
 					// ---- prologue: feature words -> bf16 stem image (32 channels, halo 2) in the h buffer ----
 					for (uint32_t i = et; i < 4 * in_chunk_bytes / 16; i += kEpilogueThreads)
@@ -460,8 +462,10 @@ namespace agb
 		// ---- value head: dense(4*cells -> D) + ReLU, dense(D -> 3), softmax (createValueHead, blocks.cpp:112-117) --------
 		// one CTA per board, D threads; 0.02 % of the network's FLOPs
 		__global__ void value_head_kernel(const float *__restrict__ hidden, const float *__restrict__ wd1, const float *__restrict__ bd1,
-				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D)
+				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D, const int *__restrict__ n_dev)
 		{
+			if (n_dev != nullptr)
+				n = *n_dev;
 			extern __shared__ float sh[]; // [in_dim] + [D]
 			float *sx = sh, *sd = sh + in_dim;
 			for (int b = blockIdx.x; b < n; b += gridDim.x)
@@ -675,7 +679,7 @@ namespace agb
 		return AGB_OK;
 	}
 
-	int net_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n_boards, float *policy_dev, float *value_dev, float *q_dev)
+	int net_forward_impl(AgbEngine *e, const uint32_t *features_dev, int n_boards, const int *n_dev, float *policy_dev, float *value_dev, float *q_dev)
 	{
 		NetWeights *n = e->net;
 		if (n == nullptr or not n->loaded)
@@ -685,6 +689,7 @@ namespace agb
 		p.policy = policy_dev;
 		p.q = e->cfg.q_head ? q_dev : nullptr;
 		p.n_boards = n_boards;
+		p.n_boards_dev = n_dev;
 		static long long *d_trace = nullptr;
 		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
 		if (trace and d_trace == nullptr)
@@ -711,10 +716,23 @@ namespace agb
 		}
 		const int cells = e->cells, D = n->dense_width;
 		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, e->stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
-				n->d_bd2, value_dev, n_boards, cells * 4, D);
+				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
+	}
+}
+
+namespace agb
+{
+	int net_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n_boards, float *policy_dev, float *value_dev, float *q_dev)
+	{
+		return net_forward_impl(e, features_dev, n_boards, nullptr, policy_dev, value_dev, q_dev);
+	}
+	int net_forward_dev_counted(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, int max_boards, float *policy_dev, float *value_dev,
+			float *q_dev)
+	{
+		return net_forward_impl(e, features_dev, max_boards, count_dev, policy_dev, value_dev, q_dev);
 	}
 }
 

@@ -1,21 +1,1321 @@
+// K6 (PUCT select with virtual loss), K7 (edge generation, expand, backup) and the per-ply driver (final move, subtree
+// reuse) of the lockstep self-play engine. All games of an engine advance together: one warp owns one game; the search
+// graphs (nodes, edges, per-game transposition tables) live in HBM arenas and never visit the host.
+//
+// Reference semantics (file:line in the reference tree):
+//   Search::select / Tree::select           src/search/monte_carlo/Search.cpp:117-158, Tree.cpp:226-251
+//   PUCTSelector + PUCT / PUCT_q_head ops   src/search/monte_carlo/EdgeSelector.cpp:27-32, 335-361, 389-424, 562-586, 1123-1166
+//   UnifiedGenerator::generate              src/search/monte_carlo/EdgeGenerator.cpp:23-40, 49-127, 128-179, 269-303
+//   Tree::expand / backup / leak correction src/search/monte_carlo/Tree.cpp:75-104, 257-383
+//   NodeCache (transpositions, cleanup)     src/search/monte_carlo/NodeCache.cpp:221-299
+//   GameGenerator::generate / make_move     src/selfplay/GameGenerator.cpp:46-185, utils/misc.cpp:171-179
+// Floating point follows the reference operation by operation (this file is compiled with -fmad=false; the reference is
+// built without FMA contraction, CMakeLists.txt:52-54), so visit counts, values and move choices are bit-identical when
+// the evaluator outputs are.
+//
+// Scope of this round: the per-leaf alpha-beta solver is not on the device yet, so tasks take the
+// reference's "not processed by solver" path: edges for all empty cells + check_terminal_conditions.
 #include "engine.hpp"
+#include "patterns_logic.cuh"
+
+#include <cfloat>
+#include <cstring>
+#include <vector>
+
 namespace agb
 {
-	int selfplay_create(AgbEngine *e) { return e->fail(AGB_ESTATE, "self-play not built yet"); }
-	void selfplay_destroy(AgbEngine *) {}
-}
-extern "C"
-{
-	int agb_selfplay_reset(AgbEngine *e, const int8_t *, const int8_t *) { return e->fail(AGB_ESTATE, "self-play not built yet"); }
-	int agb_step(AgbEngine *e, int) { return e->fail(AGB_ESTATE, "self-play not built yet"); }
-	int agb_pop_finished(AgbEngine *e, void *, size_t, size_t *, int *) { return e->fail(AGB_ESTATE, "self-play not built yet"); }
-	int agb_get_stats(AgbEngine *e, AgbStats *stats)
+	using namespace plogic;
+
+	constexpr int kMaxPath = 96;
+	constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+	// Score (search/Score.hpp:47-321): 3 bits proven value, 13 bits eval + 4000
+	namespace score
 	{
-		if (stats == nullptr) return AGB_EINVAL;
-		*stats = AgbStats { };
-		stats->nb_kernel_launches = e->launches;
+		enum : int { LOSS = 0, DRAW = 1, UNKNOWN = 2, WIN = 3 };
+		AGB_HD inline uint16_t make(int pv, int eval) { return static_cast<uint16_t>((pv << 13) | (4000 + eval)); }
+		AGB_HD inline int eval(uint16_t s) { return (s & 8191) - 4000; }
+		AGB_HD inline int pv(uint16_t s) { return (s >> 13) & 3; }
+		AGB_HD inline bool is_infinite(uint16_t s) { return s == 0x0000 or s == 0xFFFF; }
+		AGB_HD inline bool is_proven(uint16_t s) { return pv(s) != UNKNOWN and not is_infinite(s); }
+		AGB_HD inline bool is_win(uint16_t s) { return pv(s) == WIN and not is_infinite(s); }
+		AGB_HD inline bool is_unproven(uint16_t s) { return pv(s) == UNKNOWN; }
+		AGB_HD inline int distance(uint16_t s)
+		{
+			switch (pv(s))
+			{
+				case LOSS:
+				case DRAW: return eval(s);
+				case WIN: return -eval(s);
+				default: return 0;
+			}
+		}
+		AGB_HD inline uint16_t negate(uint16_t s)
+		{
+			switch (pv(s))
+			{
+				case LOSS: return is_infinite(s) ? 0xFFFF : make(WIN, -eval(s));
+				case DRAW: return make(DRAW, eval(s));
+				case WIN: return is_infinite(s) ? 0x0000 : make(LOSS, -eval(s));
+				default: return make(UNKNOWN, -eval(s));
+			}
+		}
+		AGB_HD inline uint16_t invert_up(uint16_t s)
+		{
+			switch (pv(s))
+			{
+				case LOSS: return is_infinite(s) ? negate(s) : make(WIN, -(distance(s) + 1));
+				case DRAW: return make(DRAW, distance(s) + 1);
+				case WIN: return is_infinite(s) ? negate(s) : make(LOSS, distance(s) + 1);
+				default: return negate(s);
+			}
+		}
+		constexpr uint16_t kDefault = (UNKNOWN << 13) | 4000; // Score()
+	}
+
+	struct NodeD
+	{
+			int32_t edge_begin;
+			int16_t n_edges;
+			int16_t depth;
+			float win, draw;
+			float moves_left;
+			int32_t visits;
+			uint16_t score;
+			int16_t vloss;
+			int8_t stm;
+			uint8_t flags; // bit0 root, bit1 fully expanded
+			uint16_t pad;
+			uint64_t hash;
+	};
+	struct EdgeD
+	{
+			float prior;
+			float win, draw;
+			int32_t visits;
+			uint16_t move; // Move::toShort
+			uint16_t score;
+			uint16_t vloss_flag; // bit 15: being expanded, low 15 bits: virtual loss (Edge.hpp:25-46)
+			uint16_t pad;
+	};
+	static_assert(sizeof(NodeD) == 40 and sizeof(EdgeD) == 24, "layout");
+
+	struct TaskD
+	{
+			int32_t path_len;
+			int32_t final_node;
+			int32_t nn_slot; // slot in the evaluation batch, -1 if not evaluated
+			int8_t stm;
+			uint8_t stored; // task is part of the batch
+			uint8_t proven_edge; // reached a proven edge: no solver / NN / edge generation
+			uint8_t pad;
+			float win, draw, moves_left;
+			uint16_t score;
+			uint16_t pad2;
+			uint64_t hash;
+			uint64_t bits[8];
+			int32_t path_node[kMaxPath];
+			int32_t path_edge[kMaxPath];
+	};
+
+	struct SelfplayState
+	{
+			int games = 0, batch = 0, cells = 0, S = 0;
+			int max_nodes = 0, max_edges = 0, table_size = 0;
+			// per game
+			int8_t *root_board = nullptr; // [games][cells]
+			uint64_t *root_bits = nullptr; // [games][8]
+			uint64_t *root_hash = nullptr;
+			int8_t *root_stm = nullptr;
+			int32_t *root_node = nullptr;
+			int32_t *n_nodes = nullptr, *n_edges = nullptr;
+			int32_t *n_stored = nullptr; // tasks stored in the current batch
+			int32_t *n_moves = nullptr;
+			uint16_t *moves = nullptr; // [games][cells] played moves (incl. opening)
+			int8_t *outcome = nullptr; // last finished outcome
+			NodeD *nodes = nullptr; // [games][max_nodes]
+			uint64_t *node_bits = nullptr; // [games][max_nodes][8]
+			EdgeD *edges = nullptr; // [games][max_edges]
+			int32_t *table = nullptr; // [games][table_size] open addressing, -1 empty
+			int32_t *remap = nullptr; // [games][max_nodes] scratch for cleanup
+			TaskD *tasks = nullptr; // [games][batch]
+			// evaluation batch
+			int8_t *task_boards = nullptr; // [games*batch][cells] compact (K1 input)
+			int8_t *task_stm = nullptr;
+			int32_t *eval_count = nullptr; // device counter
+			uint32_t *features = nullptr;
+			float *policy = nullptr, *value = nullptr, *q = nullptr;
+			uint64_t *zobrist = nullptr; // [cells][2] + [2]
+			unsigned long long *stats = nullptr; // device AgbStats mirror (16 words)
+			// openings pool
+			int8_t *openings = nullptr; // [n_openings][cells]
+			int8_t *opening_stm = nullptr;
+			int n_openings = 0;
+			int32_t *opening_cursor = nullptr;
+			// last sample per game (dense), for parity checks and K8
+			int32_t *sample_visits = nullptr; // [games][cells]
+			float *sample_prior = nullptr, *sample_q = nullptr; // [games][cells]
+			float *sample_root = nullptr; // [games][4] win, draw, (visits), (move)
+	};
+
+	namespace
+	{
+		enum : int { ST_EVALS = 0, ST_NODES = 1, ST_DUP = 2, ST_LEAKS = 3, ST_PROVEN = 4, ST_WASTED = 5, ST_MOVES = 6, ST_GAMES = 7, ST_OVERFLOW = 8 };
+		enum : uint32_t { OVF_NODES = 2, OVF_EDGES = 4, OVF_PATH = 8, OVF_TABLE = 16 };
+
+		struct Params
+		{
+				SelfplayState s;
+				int rules, draw_after;
+				int max_simulations, init_to;
+				float exploration_constant, leak_threshold;
+				int q_head;
+				Tables tables;
+				BoardStore store;
+				uint32_t *status;
+		};
+
+		__device__ inline float expectation(float win, float draw)
+		{
+			return win + 0.5f * draw;
+		}
+		__device__ inline int lowest_lane(unsigned mask)
+		{
+			return __ffs(mask) - 1;
+		}
+
+		// ---- transposition table ---------------------------------------------------------------------------------
+		__device__ int table_seek(const Params &p, int g, uint64_t hash, const uint64_t *bits, int stm, int lane)
+		{ // NodeCache::seek: hash, then full board and side-to-move comparison
+			const int mask = p.s.table_size - 1;
+			const int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
+			const NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
+			int slot = static_cast<int>(hash) & mask;
+			for (int probe = 0; probe < p.s.table_size; probe++, slot = (slot + 1) & mask)
+			{
+				const int idx = table[slot];
+				if (idx < 0)
+					return -1;
+				if (nodes[idx].hash == hash and nodes[idx].stm == stm)
+				{
+					const uint64_t *nb = p.s.node_bits + (static_cast<size_t>(g) * p.s.max_nodes + idx) * 8;
+					const bool same = (lane >= 8) or (nb[lane] == bits[lane]);
+					if (__all_sync(kFullMask, same))
+						return idx;
+				}
+			}
+			return -1;
+		}
+		__device__ void table_insert(const Params &p, int g, uint64_t hash, int idx)
+		{ // single thread
+			const int mask = p.s.table_size - 1;
+			int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
+			int slot = static_cast<int>(hash) & mask;
+			for (int probe = 0; probe < p.s.table_size; probe++, slot = (slot + 1) & mask)
+				if (table[slot] < 0)
+				{
+					table[slot] = idx;
+					return;
+				}
+			atomicOr(p.status, OVF_TABLE);
+		}
+
+		// ---- score bookkeeping (Tree.cpp:75-104) ----------------------------------------------------------------------
+		__device__ bool has_information_leak(const EdgeD &e, const NodeD *node, float threshold)
+		{
+			if (node == nullptr or threshold >= 1.0f)
+				return false;
+			if (e.score != score::invert_up(node->score))
+				return true;
+			const float inv_win = 1.0f - (node->win + node->draw); // Value::getInverted: (loss_rate, draw_rate)
+			const float dw = e.win - inv_win, dd = e.draw - node->draw;
+			return (fabsf(dw) + fabsf(dd)) > threshold;
+		}
+		__device__ void update_node_score(NodeD &node, const EdgeD *edges, int lane)
+		{ // max over edge scores; only a fully expanded node (or a win / unproven result) takes it over
+			uint16_t best = 0;
+			for (int i = lane; i < node.n_edges; i += 32)
+				best = max(best, edges[node.edge_begin + i].score);
+			for (int o = 16; o > 0; o >>= 1)
+				best = max(best, static_cast<uint16_t>(__shfl_xor_sync(kFullMask, static_cast<int>(best), o)));
+			if ((node.flags & 2) or score::is_win(best) or score::is_unproven(best))
+				node.score = best;
+		}
+		__device__ void clip01(float &x)
+		{
+			x = fmaxf(0.0f, fminf(1.0f, x));
+		}
+
+		// Tree::correctInformationLeak (Tree.cpp:352-376); all lanes run it, lane 0 writes
+		__device__ void correct_information_leak(const Params &p, int g, TaskD &task, int lane)
+		{
+			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
+			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
+			for (int i = task.path_len - 1; i >= 0; i--)
+			{
+				NodeD &node = nodes[task.path_node[i]];
+				EdgeD &edge = edges[task.path_edge[i]];
+				const int next = (i == task.path_len - 1) ? task.final_node : task.path_node[i + 1];
+				const NodeD &nn = nodes[next];
+				const float cw = edge.win, cd = edge.draw;
+				const float tw = 1.0f - (nn.win + nn.draw), td = nn.draw;
+				const float scale = static_cast<float>(edge.visits) / static_cast<float>(node.visits);
+				const float nw = node.win + (tw - cw) * scale, nd = node.draw + (td - cd) * scale;
+				__syncwarp();
+				if (lane == 0)
+				{
+					edge.win = tw;
+					edge.draw = td;
+					node.win = nw;
+					node.draw = nd;
+					edge.score = score::invert_up(nn.score);
+				}
+				__syncwarp();
+				NodeD tmp = node;
+				update_node_score(tmp, edges, lane);
+				if (lane == 0)
+					node.score = tmp.score;
+				__syncwarp();
+			}
+		}
+
+		// ---- K6: select ------------------------------------------------------------------------------------------------
+		__global__ void __launch_bounds__(128) select_kernel(const __grid_constant__ Params p)
+		{
+			const int lane = threadIdx.x & 31;
+			const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+			if (g >= p.s.games)
+				return;
+			const int cells = p.s.cells, S = p.s.S;
+			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
+			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
+			TaskD *tasks = p.s.tasks + static_cast<size_t>(g) * p.s.batch;
+			const int root = p.s.root_node[g];
+			const int root_visits = (root >= 0) ? nodes[root].visits : 0;
+			int stored = 0;
+			int trials = 2 * p.s.batch;
+			while (stored < p.s.batch and root_visits <= p.max_simulations)
+			{
+				TaskD &task = tasks[stored];
+				// SearchTask::set
+				__syncwarp();
+				if (lane < 8)
+					task.bits[lane] = p.s.root_bits[static_cast<size_t>(g) * 8 + lane];
+				if (lane == 0)
+				{
+					task.path_len = 0;
+					task.final_node = -1;
+					task.nn_slot = -1;
+					task.stored = 1;
+					task.proven_edge = 0;
+					task.win = task.draw = task.moves_left = 0.0f;
+					task.score = score::kDefault;
+				}
+				uint64_t hash = p.s.root_hash[g];
+				int stm = p.s.root_stm[g];
+				int node = root, len = 0;
+				int outcome = 0; // 0 leaf, 1 proven edge, 2 information leak
+				__syncwarp();
+				while (node >= 0)
+				{
+					const NodeD N = nodes[node];
+					// PUCTSelector::select: c = exploration_constant (+ 0 * log(..))
+					const float psv = static_cast<float>(static_cast<double>(p.exploration_constant) * sqrt(static_cast<double>(N.visits + N.vloss)));
+					float initial_q = 0.0f;
+					if (p.init_to == 1)
+						initial_q = expectation(N.win, N.draw);
+					else if (p.init_to == 2)
+						initial_q = 0.5f;
+					float best_v = -FLT_MAX;
+					int best_i = 0x7FFFFFFF;
+					for (int i = lane; i < N.n_edges; i += 32)
+					{
+						const EdgeD e = edges[N.edge_begin + i];
+						const int vl = e.vloss_flag & 0x7FFF;
+						float v;
+						switch (score::is_proven(e.score) ? score::pv(e.score) : static_cast<int>(score::UNKNOWN))
+						{
+							case score::LOSS:
+								v = -1000.0f + score::distance(e.score);
+								break;
+							case score::DRAW:
+								v = 0.5f;
+								break;
+							case score::WIN:
+								v = +1000.0f - score::distance(e.score);
+								break;
+							default:
+							{
+								const float visits_f = 1.0e-8f + e.visits;
+								const float vloss_scale = visits_f / (visits_f + static_cast<float>(vl));
+								float Q;
+								if (e.vloss_flag & 0x8000)
+									Q = -1000.0f;
+								else if (p.init_to == 3 or e.visits > 0)
+									Q = expectation(e.win, e.draw) * vloss_scale;
+								else
+									Q = initial_q;
+								const float U = e.prior * psv / (1.0f + e.visits + vl);
+								v = Q + U;
+								break;
+							}
+						}
+						if (v > best_v)
+						{
+							best_v = v;
+							best_i = i;
+						}
+					}
+					for (int o = 16; o > 0; o >>= 1)
+					{ // first maximal edge wins (find_best_edge_impl uses a strict '>')
+						const float ov = __shfl_xor_sync(kFullMask, best_v, o);
+						const int oi = __shfl_xor_sync(kFullMask, best_i, o);
+						if (ov > best_v or (ov == best_v and oi < best_i))
+						{
+							best_v = ov;
+							best_i = oi;
+						}
+					}
+					const int eidx = N.edge_begin + best_i;
+					const EdgeD chosen = edges[eidx];
+					// SearchTask::append + virtual loss
+					const int row = (chosen.move >> 2) & 127, col = (chosen.move >> 9) & 127;
+					const int cell = row * S + col;
+					const int colour = stm - 1;
+					hash ^= p.s.zobrist[cell * 2 + colour] ^ p.s.zobrist[cells * 2] ^ p.s.zobrist[cells * 2 + 1];
+					__syncwarp();
+					if (lane == 0)
+					{
+						if (len < kMaxPath)
+						{
+							task.path_node[len] = node;
+							task.path_edge[len] = eidx;
+						}
+						else
+							atomicOr(p.status, OVF_PATH);
+						task.bits[colour * 4 + (cell >> 6)] |= 1ull << (cell & 63);
+						nodes[node].vloss = N.vloss + 1;
+						edges[eidx].vloss_flag = (chosen.vloss_flag & 0x8000) | ((chosen.vloss_flag & 0x7FFF) + 1);
+					}
+					len = min(len + 1, kMaxPath);
+					stm = 3 - stm;
+					__syncwarp();
+					if (score::is_proven(chosen.score))
+					{
+						outcome = 1;
+						break;
+					}
+					const int child = table_seek(p, g, hash, task.bits, stm, lane);
+					if (lane == 0)
+					{
+						task.final_node = child;
+						if (child < 0)
+							edges[eidx].vloss_flag |= 0x8000;
+					}
+					__syncwarp();
+					if (has_information_leak(edges[eidx], child >= 0 ? &nodes[child] : nullptr, p.leak_threshold))
+					{
+						outcome = 2;
+						break;
+					}
+					node = child;
+				}
+				if (lane == 0)
+				{
+					task.path_len = len;
+					task.stm = static_cast<int8_t>(stm);
+					task.hash = hash;
+				}
+				__syncwarp();
+				if (len == 0)
+				{ // empty tree: the root itself is the only task of this batch (Search.cpp:128-129)
+					stored++;
+					break;
+				}
+				bool keep = true;
+				if (lane == 0)
+				{ // statistics only (Search.cpp:130-131)
+					for (int i = 0; i < stored; i++)
+						if (tasks[i].path_len > 0 and tasks[i].path_edge[tasks[i].path_len - 1] == task.path_edge[len - 1])
+						{
+							atomicAdd(p.s.stats + ST_DUP, 1ull);
+							break;
+						}
+				}
+				if (outcome == 2)
+				{ // Search.cpp:132-138
+					correct_information_leak(p, g, task, lane);
+					if (lane == 0)
+					{
+						for (int i = 0; i < len; i++)
+						{
+							nodes[task.path_node[i]].vloss -= 1;
+							EdgeD &e = edges[task.path_edge[i]];
+							e.vloss_flag = (e.vloss_flag & 0x8000) | ((e.vloss_flag & 0x7FFF) - 1);
+						}
+						task.stored = 0;
+						atomicAdd(p.s.stats + ST_LEAKS, 1ull);
+					}
+					keep = false;
+				}
+				else if (outcome == 1)
+				{ // Search.cpp:139-150
+					if (lane == 0)
+					{
+						const uint16_t sc = edges[task.path_edge[len - 1]].score;
+						task.final_node = -1;
+						task.stm = static_cast<int8_t>(3 - stm);
+						task.score = sc;
+						switch (score::pv(sc))
+						{ // Score::convertToValue
+							case score::LOSS: task.win = 0.0f; task.draw = 0.0f; break;
+							case score::DRAW: task.win = 0.0f; task.draw = 1.0f; break;
+							default: task.win = 1.0f; task.draw = 0.0f; break;
+						}
+						task.proven_edge = 1;
+						atomicAdd(p.s.stats + ST_PROVEN, 1ull);
+					}
+				}
+				__syncwarp();
+				if (keep)
+					stored++;
+				if (--trials <= 0)
+					break;
+			}
+			if (lane == 0)
+				p.s.n_stored[g] = stored;
+			// evaluation batch: every stored task that is a root or not proven goes to the network (Search::scheduleToNN)
+			for (int t = 0; t < stored; t++)
+			{
+				TaskD &task = tasks[t];
+				if (task.proven_edge)
+					continue;
+				int slot = 0;
+				if (lane == 0)
+				{
+					slot = atomicAdd(p.s.eval_count, 1);
+					task.nn_slot = slot;
+					p.s.task_stm[slot] = task.stm;
+				}
+				slot = __shfl_sync(kFullMask, slot, 0);
+				for (int i = lane; i < cells; i += 32)
+				{
+					const uint64_t cross = task.bits[i >> 6], circle = task.bits[4 + (i >> 6)];
+					p.s.task_boards[static_cast<size_t>(slot) * cells + i] = static_cast<int8_t>(((cross >> (i & 63)) & 1) | (((circle >> (i & 63)) & 1) << 1));
+				}
+			}
+		}
+
+		// ---- K7: edge generation + expand + backup ------------------------------------------------------------------------
+		__device__ void node_update_value(NodeD &n, float win, float draw)
+		{ // Node::updateValue (Node.hpp:268-274): 1.0 / visits in double, narrowed to float
+			n.visits++;
+			const float tmp = static_cast<float>(1.0 / static_cast<double>(n.visits));
+			n.win += (win - n.win) * tmp;
+			n.draw += (draw - n.draw) * tmp;
+			clip01(n.win);
+			clip01(n.draw);
+		}
+		__device__ void edge_update_value(EdgeD &e, float win, float draw)
+		{ // Edge::updateValue (Edge.hpp:111-117): 1.0f / visits in float
+			e.visits++;
+			const float tmp = 1.0f / static_cast<float>(e.visits);
+			e.win += (win - e.win) * tmp;
+			e.draw += (draw - e.draw) * tmp;
+			clip01(e.win);
+			clip01(e.draw);
+		}
+
+		__global__ void __launch_bounds__(128) expand_backup_kernel(const __grid_constant__ Params p)
+		{
+			const int lane = threadIdx.x & 31;
+			const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+			if (g >= p.s.games)
+				return;
+			const int cells = p.s.cells, S = p.s.S;
+			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
+			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
+			TaskD *tasks = p.s.tasks + static_cast<size_t>(g) * p.s.batch;
+			const int stored = p.s.n_stored[g];
+
+			for (int t = 0; t < stored; t++)
+			{
+				TaskD &task = tasks[t];
+				if (not task.stored or task.proven_edge)
+					continue; // proven-edge tasks skip edge generation and carry no edges (Tree::expand returns SKIPPED)
+				const int slot = task.nn_slot;
+				const int stm = task.stm;
+				const size_t cbase = static_cast<size_t>(slot) * kCellPitch;
+				int n_nodes = p.s.n_nodes[g], n_edges = p.s.n_edges[g];
+				if (lane == 0)
+				{ // NNEvaluator::unpack_from_network: value always, moves left only if the score is unproven
+					task.win = p.s.value[slot * 3 + 0];
+					task.draw = p.s.value[slot * 3 + 1];
+					task.moves_left = 0.0f;
+					atomicAdd(p.s.stats + ST_EVALS, 1ull);
+				}
+				__syncwarp();
+				// UnifiedGenerator::generate, "not processed by solver" path: one edge per empty cell in row-major order,
+				// written straight into the arena at the next free position (committed only if the node is new)
+				int stones = 0;
+				for (int i = lane; i < cells; i += 32)
+					stones += (p.store.board[cbase + i] != NONE);
+				for (int o = 16; o > 0; o >>= 1)
+					stones += __shfl_xor_sync(kFullMask, stones, o);
+				const bool draw_now = (stones + 1) >= p.draw_after;
+				int count = 0, wins = 0, draws = 0, losses = 0;
+				if (n_edges + (cells - stones) > p.s.max_edges)
+				{
+					atomicOr(p.status, OVF_EDGES);
+					continue;
+				}
+				for (int i0 = 0; i0 < cells; i0 += 32)
+				{
+					const int i = i0 + lane;
+					const bool empty = (i < cells) and (p.store.board[cbase + i] == NONE);
+					const unsigned em = __ballot_sync(kFullMask, empty);
+					int kind = score::UNKNOWN;
+					if (empty)
+					{ // check_terminal_conditions via getOutcome: five for the mover, renju foul, draw by move count
+						const uint32_t pt = p.store.ptypes[cbase + i] >> (stm == CROSS ? 0 : 4);
+						const bool five = ((pt & 7u) == PT_FIVE) or (((pt >> 8) & 7u) == PT_FIVE) or (((pt >> 16) & 7u) == PT_FIVE) or (((pt >> 24) & 7u) == PT_FIVE);
+						if (five)
+							kind = score::WIN;
+						else if (p.rules == RULE_RENJU and stm == CROSS and p.store.forbidden[cbase + i])
+							kind = score::LOSS;
+						else if (draw_now)
+							kind = score::DRAW;
+						EdgeD e;
+						e.prior = p.s.policy[static_cast<size_t>(slot) * cells + i];
+						e.win = p.q_head ? p.s.q[(static_cast<size_t>(slot) * cells + i) * 3 + 0] : 0.0f;
+						e.draw = p.q_head ? p.s.q[(static_cast<size_t>(slot) * cells + i) * 3 + 1] : 0.0f;
+						e.visits = 0;
+						e.move = static_cast<uint16_t>(stm | ((i / S) << 2) | ((i % S) << 9));
+						e.score = score::kDefault;
+						e.vloss_flag = 0;
+						e.pad = 0;
+						if (kind == score::WIN)
+						{
+							e.score = score::make(score::WIN, -1);
+							e.win = 1.0f;
+							e.draw = 0.0f;
+						}
+						else if (kind == score::LOSS)
+						{
+							e.score = score::make(score::LOSS, 1);
+							e.win = 0.0f;
+							e.draw = 0.0f;
+						}
+						else if (kind == score::DRAW)
+						{
+							e.score = score::make(score::DRAW, 1);
+							e.win = 0.0f;
+							e.draw = 1.0f;
+						}
+						edges[n_edges + count + __popc(em & ((1u << lane) - 1u))] = e;
+					}
+					count += __popc(em);
+					wins += __popc(__ballot_sync(kFullMask, kind == score::WIN));
+					draws += __popc(__ballot_sync(kFullMask, kind == score::DRAW));
+					losses += __popc(__ballot_sync(kFullMask, kind == score::LOSS));
+				}
+				__syncwarp();
+				// position score from the terminal checks (EdgeGenerator.cpp:163-178)
+				uint16_t tscore = score::kDefault;
+				if (wins > 0)
+					tscore = score::make(score::WIN, -1);
+				else if (draws > 0)
+					tscore = score::make(score::DRAW, 1);
+				else if (losses == stones)
+					tscore = score::make(score::LOSS, 1);
+				if (lane == 0 and tscore != score::kDefault)
+				{
+					task.score = tscore;
+					task.win = (score::pv(tscore) == score::WIN) ? 1.0f : 0.0f;
+					task.draw = (score::pv(tscore) == score::DRAW) ? 1.0f : 0.0f;
+				}
+				// prune_weak_moves (proven position, not the root): keep the best-scoring edges in their order
+				const bool is_root_task = (task.path_len == 0);
+				if (score::is_proven(tscore) and not is_root_task)
+				{
+					uint16_t best = 0; // Score::loss() is (LOSS, 0) = 4000
+					best = score::make(score::LOSS, 0);
+					for (int i = lane; i < count; i += 32)
+						best = max(best, edges[n_edges + i].score);
+					for (int o = 16; o > 0; o >>= 1)
+						best = max(best, static_cast<uint16_t>(__shfl_xor_sync(kFullMask, static_cast<int>(best), o)));
+					int kept = 0;
+					for (int i0 = 0; i0 < count; i0 += 32)
+					{
+						const int i = i0 + lane;
+						EdgeD e;
+						bool keep = false;
+						if (i < count)
+						{
+							e = edges[n_edges + i];
+							keep = (e.score == best);
+						}
+						const unsigned km = __ballot_sync(kFullMask, keep);
+						__syncwarp();
+						if (keep)
+							edges[n_edges + kept + __popc(km & ((1u << lane) - 1u))] = e;
+						kept += __popc(km);
+						__syncwarp();
+					}
+					count = kept;
+				}
+				// renormalize_policy: sequential float sum in edge order (EdgeGenerator.cpp:23-40)
+				if (lane == 0)
+				{
+					float sum = 0.0f;
+					for (int i = 0; i < count; i++)
+						sum += edges[n_edges + i].prior;
+					if (sum == 0.0f)
+					{
+						const float u = 1.0f / count;
+						for (int i = 0; i < count; i++)
+							edges[n_edges + i].prior = u;
+					}
+					else
+					{
+						const float inv = 1.0f / sum;
+						for (int i = 0; i < count; i++)
+							edges[n_edges + i].prior *= inv;
+					}
+				}
+				__syncwarp();
+				// Tree::expand
+				const int existing = table_seek(p, g, task.hash, task.bits, stm, lane);
+				if (existing < 0)
+				{
+					if (n_nodes >= p.s.max_nodes)
+					{
+						atomicOr(p.status, OVF_NODES);
+						continue;
+					}
+					NodeD node;
+					node.edge_begin = n_edges;
+					node.n_edges = static_cast<int16_t>(count);
+					node.depth = static_cast<int16_t>(stones);
+					node.win = node.draw = node.moves_left = 0.0f;
+					node.visits = 0;
+					node.score = score::kDefault;
+					node.vloss = 0;
+					node.stm = static_cast<int8_t>(stm);
+					node.flags = 0;
+					node.pad = 0;
+					node.hash = task.hash;
+					node_update_value(node, task.win, task.draw);
+					node.moves_left += (task.moves_left - node.moves_left) / node.visits;
+					if (count + stones == cells)
+						node.flags |= 2; // fully expanded
+					if (is_root_task)
+						node.flags |= 1;
+					update_node_score(node, edges, lane);
+					__syncwarp();
+					if (lane == 0)
+					{
+						nodes[n_nodes] = node;
+						table_insert(p, g, task.hash, n_nodes);
+						task.final_node = n_nodes;
+						if (is_root_task)
+							p.s.root_node[g] = n_nodes;
+						p.s.n_nodes[g] = n_nodes + 1;
+						p.s.n_edges[g] = n_edges + count;
+					}
+					if (lane < 8)
+						p.s.node_bits[(static_cast<size_t>(g) * p.s.max_nodes + n_nodes) * 8 + lane] = task.bits[lane];
+					__syncwarp();
+				}
+				else
+				{ // the same position was reached along another path (or by an earlier task of this batch)
+					if (lane == 0)
+					{
+						task.final_node = existing;
+						atomicAdd(p.s.stats + ST_WASTED, 1ull);
+					}
+					__syncwarp();
+					if (task.path_len > 0 and has_information_leak(edges[task.path_edge[task.path_len - 1]], &nodes[existing], p.leak_threshold))
+						correct_information_leak(p, g, task, lane);
+				}
+				__syncwarp();
+			}
+
+			// Tree::backup for every stored task, in order (Search::backup)
+			for (int t = 0; t < stored; t++)
+			{
+				const TaskD &task = tasks[t];
+				if (not task.stored)
+					continue;
+				if (lane == 0)
+					atomicAdd(p.s.stats + ST_NODES, 1ull);
+				float moves_left = task.moves_left;
+				for (int i = task.path_len - 1; i >= 0; i--)
+				{
+					NodeD node = nodes[task.path_node[i]];
+					EdgeD edge = edges[task.path_edge[i]];
+					const int next = (i == task.path_len - 1) ? task.final_node : task.path_node[i + 1];
+					float w = task.win, d = task.draw;
+					if (node.stm != task.stm)
+						w = 1.0f - (task.win + task.draw); // Value::getInverted
+					node_update_value(node, w, d);
+					edge_update_value(edge, w, d);
+					node.moves_left += (moves_left - node.moves_left) / node.visits;
+					moves_left += 1.0f;
+					if (next >= 0)
+						edge.score = score::invert_up(nodes[next].score);
+					node.vloss -= 1;
+					edge.vloss_flag = (edge.vloss_flag & 0x7FFF) - 1; // decreaseVirtualLoss + clearFlags
+					__syncwarp();
+					if (lane == 0)
+						edges[task.path_edge[i]] = edge;
+					__syncwarp();
+					update_node_score(node, edges, lane);
+					if (lane == 0)
+						nodes[task.path_node[i]] = node;
+					__syncwarp();
+				}
+			}
+			if (lane == 0)
+				p.s.n_stored[g] = 0;
+		}
+
+		// ---- per-ply driver: final move, record, game end, subtree reuse ------------------------------------------------------
+		__global__ void __launch_bounds__(128) make_move_kernel(const __grid_constant__ Params p)
+		{
+			__shared__ int8_t sboards[4][kCellPitch];
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			const int g = blockIdx.x * 4 + warp;
+			if (g >= p.s.games)
+				return;
+			const int cells = p.s.cells, S = p.s.S;
+			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
+			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
+			const int root = p.s.root_node[g];
+			if (root < 0)
+				return;
+			const NodeD R = nodes[root];
+			// GameGenerator.cpp:95-101: fewer simulations when the root is drawish
+			const float reduction = fminf(1.0f, fmaxf(0.0f, (R.draw - 0.75f) / (1.0f - 0.75f)));
+			const int simulations = static_cast<int>(p.max_simulations - reduction * (p.max_simulations - 50));
+			if (not (R.visits > simulations or score::is_proven(R.score)))
+				return;
+			// final selector "max_visit": first edge with the most visits (EdgeSelector.cpp:1403-1406)
+			float best_v = -FLT_MAX;
+			int best_i = 0x7FFFFFFF;
+			for (int i = lane; i < R.n_edges; i += 32)
+			{
+				const float v = static_cast<float>(edges[R.edge_begin + i].visits);
+				if (v > best_v)
+				{
+					best_v = v;
+					best_i = i;
+				}
+			}
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				const float ov = __shfl_xor_sync(kFullMask, best_v, o);
+				const int oi = __shfl_xor_sync(kFullMask, best_i, o);
+				if (ov > best_v or (ov == best_v and oi < best_i))
+				{
+					best_v = ov;
+					best_i = oi;
+				}
+			}
+			const EdgeD chosen = edges[R.edge_begin + best_i];
+			// SearchDataPack(rootNode, board) (dataset/data_packs.cpp:24-43), kept dense for the record writer
+			for (int i = lane; i < cells; i += 32)
+			{
+				p.s.sample_visits[static_cast<size_t>(g) * cells + i] = 0;
+				p.s.sample_prior[static_cast<size_t>(g) * cells + i] = 0.0f;
+				p.s.sample_q[static_cast<size_t>(g) * cells + i] = 0.0f;
+			}
+			__syncwarp();
+			for (int i = lane; i < R.n_edges; i += 32)
+			{
+				const EdgeD e = edges[R.edge_begin + i];
+				const int cell = ((e.move >> 2) & 127) * S + ((e.move >> 9) & 127);
+				p.s.sample_visits[static_cast<size_t>(g) * cells + cell] = e.visits;
+				p.s.sample_prior[static_cast<size_t>(g) * cells + cell] = e.prior;
+				p.s.sample_q[static_cast<size_t>(g) * cells + cell] = expectation(e.win, e.draw);
+			}
+			if (lane == 0)
+			{
+				p.s.sample_root[g * 4 + 0] = R.win;
+				p.s.sample_root[g * 4 + 1] = R.draw;
+				p.s.sample_root[g * 4 + 2] = static_cast<float>(R.visits);
+				p.s.sample_root[g * 4 + 3] = static_cast<float>(chosen.move);
+				atomicAdd(p.s.stats + ST_MOVES, 1ull);
+			}
+			// game.makeMove
+			const int row = (chosen.move >> 2) & 127, col = (chosen.move >> 9) & 127, sign = chosen.move & 3;
+			const int cell = row * S + col;
+			int8_t *board = p.s.root_board + static_cast<size_t>(g) * cells;
+			uint64_t *bits = p.s.root_bits + static_cast<size_t>(g) * 8;
+			__syncwarp();
+			if (lane == 0)
+			{
+				board[cell] = static_cast<int8_t>(sign);
+				bits[(sign - 1) * 4 + (cell >> 6)] |= 1ull << (cell & 63);
+				p.s.root_hash[g] ^= p.s.zobrist[cell * 2 + sign - 1] ^ p.s.zobrist[cells * 2] ^ p.s.zobrist[cells * 2 + 1];
+				p.s.root_stm[g] = static_cast<int8_t>(3 - sign);
+				p.s.moves[static_cast<size_t>(g) * cells + p.s.n_moves[g]] = chosen.move;
+				p.s.n_moves[g] += 1;
+			}
+			__syncwarp();
+			for (int i = lane; i < cells; i += 32)
+				sboards[warp][i] = board[i];
+			__syncwarp();
+			int outcome = 0;
+			if (lane == 0)
+			{
+				bool overflow = false;
+				outcome = outcome_of(sboards[warp], S, p.rules, p.draw_after, row, col, sign, p.tables, overflow);
+				if (overflow)
+					atomicOr(p.status, 1u);
+			}
+			outcome = __shfl_sync(kFullMask, outcome, 0);
+			if (outcome != 0)
+			{ // game over: publish the outcome and start the next game from the openings pool (or an empty board)
+				if (lane == 0)
+				{
+					p.s.outcome[g] = static_cast<int8_t>(outcome);
+					atomicAdd(p.s.stats + ST_GAMES, 1ull);
+				}
+				int8_t next_stm = CROSS;
+				const int8_t *src = nullptr;
+				if (p.s.n_openings > 0)
+				{
+					int k = 0;
+					if (lane == 0)
+						k = atomicAdd(p.s.opening_cursor, 1) % p.s.n_openings;
+					k = __shfl_sync(kFullMask, k, 0);
+					src = p.s.openings + static_cast<size_t>(k) * cells;
+					next_stm = p.s.opening_stm[k];
+				}
+				uint64_t h = 0;
+				uint64_t nb[2] = { 0, 0 }; // lanes 0..3: cross words, via shuffles below
+				__syncwarp();
+				for (int i = lane; i < cells; i += 32)
+					board[i] = src ? src[i] : 0;
+				__syncwarp();
+				if (lane < 8)
+				{
+					uint64_t w = 0;
+					const int colour = lane >> 2, word = lane & 3;
+					for (int i = word * 64; i < min(cells, word * 64 + 64); i++)
+						if (board[i] == colour + 1)
+						{
+							w |= 1ull << (i & 63);
+							h ^= p.s.zobrist[i * 2 + colour];
+						}
+					bits[lane] = w;
+				}
+				(void) nb;
+				for (int o = 4; o > 0; o >>= 1)
+					h ^= __shfl_xor_sync(kFullMask, h, o);
+				if (lane == 0)
+				{
+					p.s.root_hash[g] = h ^ p.s.zobrist[cells * 2 + next_stm - 1];
+					p.s.root_stm[g] = next_stm;
+					p.s.n_moves[g] = 0;
+					p.s.root_node[g] = -1;
+					p.s.n_nodes[g] = 0;
+					p.s.n_edges[g] = 0;
+				}
+				int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
+				for (int i = lane; i < p.s.table_size; i += 32)
+					table[i] = -1;
+				return;
+			}
+			// prepare_search -> Tree::setBoard -> NodeCache::cleanup: keep every node whose position can still occur
+			const int n_nodes = p.s.n_nodes[g];
+			int32_t *remap = p.s.remap + static_cast<size_t>(g) * p.s.max_nodes;
+			uint64_t *node_bits = p.s.node_bits + static_cast<size_t>(g) * p.s.max_nodes * 8;
+			uint64_t rb[8];
+			for (int k = 0; k < 8; k++)
+				rb[k] = bits[k];
+			int kept = 0;
+			for (int i0 = 0; i0 < n_nodes; i0 += 32)
+			{
+				const int i = i0 + lane;
+				bool keep = false;
+				if (i < n_nodes)
+				{
+					keep = true;
+					for (int k = 0; k < 8; k++)
+						keep = keep and ((node_bits[static_cast<size_t>(i) * 8 + k] & rb[k]) == rb[k]);
+				}
+				const unsigned km = __ballot_sync(kFullMask, keep);
+				if (i < n_nodes)
+					remap[i] = keep ? kept + __popc(km & ((1u << lane) - 1u)) : -1;
+				kept += __popc(km);
+			}
+			__syncwarp();
+			// compact nodes (ascending, destinations never overtake sources) and their edge blocks
+			int edge_cursor = 0;
+			for (int i = 0; i < n_nodes; i++)
+			{
+				const int dst = remap[i];
+				if (dst < 0)
+					continue;
+				NodeD node = nodes[i];
+				uint64_t nbits = (lane < 8) ? node_bits[static_cast<size_t>(i) * 8 + lane] : 0;
+				const int old_begin = node.edge_begin;
+				for (int e0 = 0; e0 < node.n_edges; e0 += 32)
+				{
+					EdgeD e;
+					if (e0 + lane < node.n_edges)
+						e = edges[old_begin + e0 + lane];
+					__syncwarp();
+					if (e0 + lane < node.n_edges)
+						edges[edge_cursor + e0 + lane] = e;
+					__syncwarp();
+				}
+				node.edge_begin = edge_cursor;
+				node.flags &= ~1; // root mark is re-applied below
+				edge_cursor += node.n_edges;
+				__syncwarp();
+				if (lane == 0)
+					nodes[dst] = node;
+				if (lane < 8)
+					node_bits[static_cast<size_t>(dst) * 8 + lane] = nbits;
+				__syncwarp();
+			}
+			int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
+			for (int i = lane; i < p.s.table_size; i += 32)
+				table[i] = -1;
+			__syncwarp();
+			if (lane == 0)
+			{
+				for (int i = 0; i < kept; i++)
+					table_insert(p, g, nodes[i].hash, i);
+				p.s.n_nodes[g] = kept;
+				p.s.n_edges[g] = edge_cursor;
+			}
+			__syncwarp();
+			const int new_root = table_seek(p, g, p.s.root_hash[g], bits, p.s.root_stm[g], lane);
+			if (lane == 0)
+			{
+				p.s.root_node[g] = new_root;
+				if (new_root >= 0)
+					nodes[new_root].flags |= 1;
+			}
+		}
+
+		__global__ void reset_games_kernel(const __grid_constant__ Params p)
+		{ // Zobrist hash + bitboards of every game's root position
+			const int g = blockIdx.x * blockDim.x + threadIdx.x;
+			if (g >= p.s.games)
+				return;
+			const int cells = p.s.cells;
+			uint64_t bits[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			uint64_t h = 0;
+			for (int i = 0; i < cells; i++)
+			{
+				const int v = p.s.root_board[static_cast<size_t>(g) * cells + i];
+				if (v == CROSS or v == CIRCLE)
+				{
+					bits[(v - 1) * 4 + (i >> 6)] |= 1ull << (i & 63);
+					h ^= p.s.zobrist[i * 2 + v - 1];
+				}
+			}
+			for (int k = 0; k < 8; k++)
+				p.s.root_bits[static_cast<size_t>(g) * 8 + k] = bits[k];
+			p.s.root_hash[g] = h ^ p.s.zobrist[cells * 2 + p.s.root_stm[g] - 1];
+			p.s.root_node[g] = -1;
+			p.s.n_nodes[g] = 0;
+			p.s.n_edges[g] = 0;
+			p.s.n_stored[g] = 0;
+			p.s.n_moves[g] = 0;
+			p.s.outcome[g] = 0;
+		}
+
+		uint64_t splitmix64(uint64_t &x)
+		{
+			uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+			z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+			z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+			return z ^ (z >> 31);
+		}
+		Params make_params(AgbEngine *e)
+		{
+			Params p;
+			p.s = *e->selfplay;
+			p.rules = e->cfg.rules;
+			p.draw_after = e->cfg.draw_after > 0 ? e->cfg.draw_after : e->cells;
+			p.max_simulations = e->cfg.max_simulations;
+			p.init_to = e->cfg.init_to;
+			p.exploration_constant = e->cfg.exploration_constant;
+			p.leak_threshold = e->cfg.information_leak_threshold;
+			p.q_head = e->cfg.q_head;
+			p.tables = e->tables;
+			p.store = e->store;
+			p.status = e->d_status;
+			return p;
+		}
+	}
+
+	int net_forward_dev_counted(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, int max_boards, float *policy_dev, float *value_dev,
+			float *q_dev);
+
+	int selfplay_create(AgbEngine *e)
+	{
+		const AgbConfig &c = e->cfg;
+		if (c.blocks <= 0)
+			return e->fail(AGB_EINVAL, "self-play needs a network (blocks > 0)");
+		if (c.max_batch_size <= 0 or c.games * c.max_batch_size > c.max_boards)
+			return e->fail(AGB_EINVAL, "games * max_batch_size must fit in max_boards");
+		SelfplayState *s = new SelfplayState();
+		e->selfplay = s;
+		s->games = c.games;
+		s->batch = c.max_batch_size;
+		s->cells = e->cells;
+		s->S = c.rows;
+		s->max_nodes = c.max_nodes_per_game > 0 ? c.max_nodes_per_game : 2048;
+		s->max_edges = c.max_edges_per_game > 0 ? c.max_edges_per_game : s->max_nodes * 128;
+		int ts = 1;
+		while (ts < 2 * s->max_nodes)
+			ts *= 2;
+		s->table_size = ts;
+		const size_t G = c.games, cells = e->cells, T = G * c.max_batch_size;
+		bool ok = true;
+		const auto alloc = [&](auto **ptr, size_t count)
+		{
+			ok = ok and cudaMalloc(reinterpret_cast<void**>(ptr), count * sizeof(**ptr)) == cudaSuccess;
+		};
+		alloc(&s->root_board, G * cells);
+		alloc(&s->root_bits, G * 8);
+		alloc(&s->root_hash, G);
+		alloc(&s->root_stm, G);
+		alloc(&s->root_node, G);
+		alloc(&s->n_nodes, G);
+		alloc(&s->n_edges, G);
+		alloc(&s->n_stored, G);
+		alloc(&s->n_moves, G);
+		alloc(&s->moves, G * cells);
+		alloc(&s->outcome, G);
+		alloc(&s->nodes, G * s->max_nodes);
+		alloc(&s->node_bits, G * s->max_nodes * 8);
+		alloc(&s->edges, G * s->max_edges);
+		alloc(&s->table, G * s->table_size);
+		alloc(&s->remap, G * s->max_nodes);
+		alloc(&s->tasks, T);
+		alloc(&s->task_boards, T * cells);
+		alloc(&s->task_stm, T);
+		alloc(&s->eval_count, 1);
+		alloc(&s->features, T * cells);
+		alloc(&s->policy, T * cells);
+		alloc(&s->value, T * 3);
+		alloc(&s->q, T * cells * 3);
+		alloc(&s->zobrist, cells * 2 + 2);
+		alloc(&s->stats, 16);
+		alloc(&s->opening_cursor, 1);
+		alloc(&s->sample_visits, G * cells);
+		alloc(&s->sample_prior, G * cells);
+		alloc(&s->sample_q, G * cells);
+		alloc(&s->sample_root, G * 4);
+		if (not ok)
+			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
+		std::vector<uint64_t> keys(cells * 2 + 2);
+		uint64_t seed = c.seed ^ 0xA5A5A5A55A5A5A5Aull;
+		for (auto &k : keys)
+			k = splitmix64(seed);
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->zobrist, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->opening_cursor, 0, 4, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		return AGB_OK;
 	}
-	int agb_get_root(AgbEngine *e, int, int32_t *, float *, float *, float *, int32_t *) { return e->fail(AGB_ESTATE, "self-play not built yet"); }
-	int agb_get_board(AgbEngine *e, int, int8_t *, int8_t *, int32_t *) { return e->fail(AGB_ESTATE, "self-play not built yet"); }
+	void selfplay_destroy(AgbEngine *e)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return;
+		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
+				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
+				s->value, s->q, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_q,
+				s->sample_root };
+		for (void *ptr : ptrs)
+			if (ptr)
+				cudaFree(ptr);
+		delete s;
+		e->selfplay = nullptr;
+	}
+}
+
+extern "C"
+{
+	using namespace agb;
+
+	int agb_selfplay_reset(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games");
+		const size_t G = s->games, cells = s->cells;
+		if (boards_host != nullptr)
+		{
+			if (sign_to_move_host == nullptr)
+				return e->fail(AGB_EINVAL, "sign_to_move is required with boards");
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->root_board, boards_host, G * cells, cudaMemcpyHostToDevice, e->stream));
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->root_stm, sign_to_move_host, G, cudaMemcpyHostToDevice, e->stream));
+			// the starting positions double as the pool finished games restart from
+			if (s->openings == nullptr)
+			{
+				AGB_CUDA_CHECK(e, cudaMalloc(&s->openings, G * cells));
+				AGB_CUDA_CHECK(e, cudaMalloc(&s->opening_stm, G));
+			}
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->openings, boards_host, G * cells, cudaMemcpyHostToDevice, e->stream));
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->opening_stm, sign_to_move_host, G, cudaMemcpyHostToDevice, e->stream));
+			s->n_openings = static_cast<int>(G);
+		}
+		else
+		{
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->root_board, 0, G * cells, e->stream));
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->root_stm, CROSS, G, e->stream));
+			s->n_openings = 0;
+		}
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
+		const Params p = make_params(e);
+		reset_games_kernel<<<static_cast<unsigned>((G + 127) / 128), 128, 0, e->stream>>>(p);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		return AGB_OK;
+	}
+
+	int agb_step(AgbEngine *e, int n_steps)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games");
+		if (e->net == nullptr)
+			return e->fail(AGB_ESTATE, "no weights loaded");
+		const Params p = make_params(e);
+		const unsigned grid = static_cast<unsigned>((s->games + 3) / 4);
+		const int max_tasks = s->games * s->batch;
+		for (int step = 0; step < n_steps; step++)
+		{
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->eval_count, 0, sizeof(int32_t), e->stream));
+			select_kernel<<<grid, 128, 0, e->stream>>>(p);
+			e->launches++;
+			// K1 + K3 on the leaf positions, then K4; both read the batch size from device memory
+			int rc = launch_set_boards_counted(e, s->task_boards, s->task_stm, s->eval_count, max_tasks, s->features);
+			if (rc != AGB_OK)
+				return rc;
+			rc = net_forward_dev_counted(e, s->features, s->eval_count, max_tasks, s->policy, s->value, s->q);
+			if (rc != AGB_OK)
+				return rc;
+			expand_backup_kernel<<<grid, 128, 0, e->stream>>>(p);
+			make_move_kernel<<<grid, 128, 0, e->stream>>>(p);
+			e->launches += 2;
+			AGB_CUDA_CHECK(e, cudaGetLastError());
+		}
+		uint32_t status = 0;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		if (status != 0)
+			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status) + " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table)");
+		return AGB_OK;
+	}
+
+	int agb_pop_finished(AgbEngine *e, void *, size_t, size_t *used, int *n_games)
+	{
+		if (used)
+			*used = 0;
+		if (n_games)
+			*n_games = 0;
+		return e->fail(AGB_ESTATE, "format-201 record writer (K8) is not built yet; see DESIGN.md");
+	}
+	int agb_get_stats(AgbEngine *e, AgbStats *stats)
+	{
+		if (stats == nullptr)
+			return AGB_EINVAL;
+		*stats = AgbStats { };
+		stats->nb_kernel_launches = e->launches;
+		if (e->selfplay != nullptr)
+		{
+			unsigned long long h[16];
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(h, e->selfplay->stats, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+			uint32_t status = 0;
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, 4, cudaMemcpyDeviceToHost, e->stream));
+			AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+			stats->nb_network_evaluations = h[ST_EVALS];
+			stats->nb_node_count = h[ST_NODES];
+			stats->nb_duplicate_nodes = h[ST_DUP];
+			stats->nb_information_leaks = h[ST_LEAKS];
+			stats->nb_proven_states = h[ST_PROVEN];
+			stats->nb_wasted_expansions = h[ST_WASTED];
+			stats->nb_moves_played = h[ST_MOVES];
+			stats->nb_games_finished = h[ST_GAMES];
+			stats->overflow_flags = status;
+		}
+		return AGB_OK;
+	}
+	int agb_get_root(AgbEngine *e, int game, int32_t *visits_host, float *priors_host, float *q_host, float *root_value3_host, int32_t *root_visits)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or game < 0 or game >= s->games)
+			return e->fail(AGB_EINVAL, "bad game index");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		int32_t root = -1;
+		AGB_CUDA_CHECK(e, cudaMemcpy(&root, s->root_node + game, 4, cudaMemcpyDeviceToHost));
+		const int cells = s->cells;
+		if (visits_host)
+			std::memset(visits_host, 0, cells * 4);
+		if (priors_host)
+			std::memset(priors_host, 0, cells * 4);
+		if (q_host)
+			std::memset(q_host, 0, cells * 4);
+		if (root_visits)
+			*root_visits = 0;
+		if (root < 0)
+			return AGB_OK;
+		NodeD node;
+		AGB_CUDA_CHECK(e, cudaMemcpy(&node, s->nodes + static_cast<size_t>(game) * s->max_nodes + root, sizeof(NodeD), cudaMemcpyDeviceToHost));
+		std::vector<EdgeD> edges(node.n_edges);
+		AGB_CUDA_CHECK(e, cudaMemcpy(edges.data(), s->edges + static_cast<size_t>(game) * s->max_edges + node.edge_begin, sizeof(EdgeD) * node.n_edges, cudaMemcpyDeviceToHost));
+		for (const EdgeD &ed : edges)
+		{
+			const int cell = ((ed.move >> 2) & 127) * s->S + ((ed.move >> 9) & 127);
+			if (visits_host)
+				visits_host[cell] = ed.visits;
+			if (priors_host)
+				priors_host[cell] = ed.prior;
+			if (q_host)
+				q_host[cell] = ed.win + 0.5f * ed.draw;
+		}
+		if (root_value3_host)
+		{
+			root_value3_host[0] = node.win;
+			root_value3_host[1] = node.draw;
+			root_value3_host[2] = 1.0f - (node.win + node.draw);
+		}
+		if (root_visits)
+			*root_visits = node.visits;
+		return AGB_OK;
+	}
+	int agb_get_board(AgbEngine *e, int game, int8_t *board_host, int8_t *sign_to_move, int32_t *move_number)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or game < 0 or game >= s->games)
+			return e->fail(AGB_EINVAL, "bad game index");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		if (board_host)
+			AGB_CUDA_CHECK(e, cudaMemcpy(board_host, s->root_board + static_cast<size_t>(game) * s->cells, s->cells, cudaMemcpyDeviceToHost));
+		if (sign_to_move)
+			AGB_CUDA_CHECK(e, cudaMemcpy(sign_to_move, s->root_stm + game, 1, cudaMemcpyDeviceToHost));
+		if (move_number)
+		{
+			std::vector<int8_t> b(s->cells);
+			AGB_CUDA_CHECK(e, cudaMemcpy(b.data(), s->root_board + static_cast<size_t>(game) * s->cells, s->cells, cudaMemcpyDeviceToHost));
+			int n = 0;
+			for (int8_t v : b)
+				n += (v != 0);
+			*move_number = n;
+		}
+		return AGB_OK;
+	}
 }

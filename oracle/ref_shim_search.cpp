@@ -1,1 +1,193 @@
-// placeholder, filled in below
+// TEST INFRASTRUCTURE -- C-ABI shim that drives the UNMODIFIED reference search classes (Tree, Search, NNEvaluator,
+// EdgeSelector, EdgeGenerator, AlphaBetaSearch) one self-play step at a time, with the network replaced by a callback
+// (oracle/ref_shadow AGNetwork). The control flow below is the per-game state machine of GameGenerator::generate /
+// make_move / prepare_search (src/selfplay/GameGenerator.cpp:46-185) made synchronous and started from a given position;
+// `use_solver = 0` leaves out the Search::solve() call so that the tree kernels can be compared before the device solver
+// exists (tasks then take the "not processed by solver" path of UnifiedGenerator, EdgeGenerator.cpp:269-303).
+#include <alphagomoku/game/Board.hpp>
+#include <alphagomoku/game/rules.hpp>
+#include <alphagomoku/networks/AGNetwork.hpp>
+#include <alphagomoku/search/monte_carlo/EdgeGenerator.hpp>
+#include <alphagomoku/search/monte_carlo/EdgeSelector.hpp>
+#include <alphagomoku/search/monte_carlo/NNEvaluator.hpp>
+#include <alphagomoku/search/monte_carlo/Search.hpp>
+#include <alphagomoku/search/monte_carlo/Tree.hpp>
+#include <alphagomoku/selfplay/NetworkLoader.hpp>
+#include <alphagomoku/utils/configs.hpp>
+#include <alphagomoku/utils/misc.hpp>
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace ag;
+
+namespace agref
+{
+	extern GameConfig g_game_config;
+	extern agref_eval_fn g_eval_fn;
+	extern void *g_eval_ctx;
+}
+
+namespace
+{
+	struct RefSelfplay
+	{
+			GameConfig game_config;
+			SelfplayConfig selfplay_config;
+			bool use_solver;
+			matrix<Sign> board;
+			Sign sign_to_move = Sign::CROSS;
+			std::vector<Move> moves;
+			Tree tree;
+			Search search;
+			NNEvaluator evaluator;
+			GameOutcome outcome = GameOutcome::UNKNOWN;
+			Move last_move;
+
+			RefSelfplay(const GameConfig &gc, const SelfplayConfig &sc, bool solver) :
+					game_config(gc),
+					selfplay_config(sc),
+					use_solver(solver),
+					board(gc.rows, gc.cols),
+					tree(sc.search_config.tree_config),
+					search(gc, sc.search_config),
+					evaluator(sc.device_config.at(0))
+			{
+				search.setBatchSize(sc.search_config.max_batch_size);
+				evaluator.useSymmetries(sc.use_symmetries);
+				evaluator.loadGraph(NetworkLoader(""));
+			}
+			void prepare_search()
+			{ // GameGenerator.cpp:174-185
+				search.cleanup(tree);
+				tree.setBoard(board, sign_to_move, false);
+				search.setBoard(board, sign_to_move);
+				const MCTSConfig &mcts_config = search.getConfig().mcts_config;
+				std::unique_ptr<EdgeSelector> tmp = EdgeSelector::create(mcts_config.edge_selector_config);
+				tree.setEdgeSelector(*tmp);
+				tree.setEdgeGenerator(UnifiedGenerator(mcts_config.max_children, mcts_config.policy_expansion_threshold, mcts_config.policy_temperature, true));
+			}
+	};
+}
+
+extern "C"
+{
+	void* agref_sp_create(int rules, int rows, int cols, int draw_after, int max_batch_size, int max_simulations, const char *init_to,
+			float exploration_constant, float information_leak_threshold, int use_solver, int solver_max_positions, agref_eval_fn eval_fn, void *ctx)
+	{
+		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
+		if (draw_after > 0)
+			gc.draw_after = draw_after;
+		SelfplayConfig sc;
+		sc.use_opening = false;
+		sc.use_symmetries = false;
+		sc.constraints.max_simulations = max_simulations;
+		sc.final_selector.policy = "max_visit";
+		sc.device_config = { DeviceConfig() };
+		sc.device_config[0].batch_size = max_batch_size;
+		sc.search_config.max_batch_size = max_batch_size;
+		sc.search_config.tree_config.information_leak_threshold = information_leak_threshold;
+		sc.search_config.mcts_config.edge_selector_config.policy = "puct";
+		sc.search_config.mcts_config.edge_selector_config.init_to = init_to;
+		sc.search_config.mcts_config.edge_selector_config.exploration_constant = exploration_constant;
+		sc.search_config.tss_config.max_positions = solver_max_positions;
+		agref::g_game_config = gc;
+		agref::g_eval_fn = eval_fn;
+		agref::g_eval_ctx = ctx;
+		return new RefSelfplay(gc, sc, use_solver != 0);
+	}
+	void agref_sp_destroy(void *h)
+	{
+		delete static_cast<RefSelfplay*>(h);
+	}
+	void agref_sp_set_position(void *h, const int8_t *board, int sign_to_move)
+	{ // GAME_NOT_STARTED -> GAMEPLAY (GameGenerator.cpp:48-61), starting from an arbitrary position
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		for (int i = 0; i < sp->board.size(); i++)
+			sp->board[i] = static_cast<Sign>(board[i]);
+		sp->sign_to_move = static_cast<Sign>(sign_to_move);
+		sp->moves.clear();
+		sp->outcome = GameOutcome::UNKNOWN;
+		sp->tree.clear();
+		sp->search.getSolver().clear();
+		sp->prepare_search();
+	}
+	// one SELECT_SOLVE_EVALUATE + EXPAND_AND_BACKUP round; returns 0 = searching, 1 = a move was made, 2 = game over
+	int agref_sp_step(void *h)
+	{
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		const int max_simulations = sp->selfplay_config.constraints.max_simulations;
+		sp->search.select(sp->tree, max_simulations);
+		if (sp->use_solver)
+			sp->search.solve();
+		sp->search.scheduleToNN(sp->evaluator);
+		sp->evaluator.evaluateGraph();
+		sp->search.generateEdges(sp->tree);
+		sp->search.expand(sp->tree);
+		sp->search.backup(sp->tree);
+
+		const Value root_eval = sp->tree.getInfo( { }).getValue();
+		const int simulations = get_simulations_for_move(root_eval.draw_rate, max_simulations, 50);
+		if (sp->tree.getSimulationCount() > simulations or sp->tree.isRootProven())
+		{ // make_move (GameGenerator.cpp:145-173)
+			const Node root_node = sp->tree.getInfo( { });
+			std::unique_ptr<EdgeSelector> selector = EdgeSelector::create(sp->selfplay_config.final_selector);
+			const Move move = selector->select(&root_node)->getMove();
+			Board::putMove(sp->board, move);
+			sp->moves.push_back(move);
+			sp->last_move = move;
+			sp->sign_to_move = invertSign(move.sign);
+			sp->outcome = getOutcome(sp->game_config.rules, sp->board, move, sp->game_config.draw_after);
+			if (sp->outcome != GameOutcome::UNKNOWN)
+				return 2;
+			sp->prepare_search();
+			return 1;
+		}
+		return 0;
+	}
+	void agref_sp_root(void *h, int32_t *visits, float *priors, float *q, float *value3, int32_t *root_visits, int32_t *n_edges)
+	{
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		const int cells = sp->board.size();
+		std::memset(visits, 0, cells * sizeof(int32_t));
+		std::memset(priors, 0, cells * sizeof(float));
+		std::memset(q, 0, cells * sizeof(float));
+		const Node root = sp->tree.getInfo( { });
+		*root_visits = root.getVisits();
+		*n_edges = root.numberOfEdges();
+		value3[0] = root.getValue().win_rate;
+		value3[1] = root.getValue().draw_rate;
+		value3[2] = root.getValue().loss_rate();
+		if (root.numberOfEdges() == 0)
+			return;
+		for (const Edge *edge = root.begin(); edge < root.end(); edge++)
+		{
+			const Move m = edge->getMove();
+			const int idx = m.row * sp->board.cols() + m.col;
+			visits[idx] = edge->getVisits();
+			priors[idx] = edge->getPolicyPrior();
+			q[idx] = edge->getExpectation();
+		}
+	}
+	void agref_sp_board(void *h, int8_t *board, int32_t *sign_to_move, int32_t *outcome, int32_t *last_move)
+	{
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		for (int i = 0; i < sp->board.size(); i++)
+			board[i] = static_cast<int8_t>(sp->board[i]);
+		*sign_to_move = static_cast<int32_t>(sp->sign_to_move);
+		*outcome = static_cast<int32_t>(sp->outcome);
+		*last_move = sp->last_move.toShort();
+	}
+	void agref_sp_stats(void *h, uint64_t *out)
+	{
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		const SearchStats st = sp->search.getStats();
+		out[0] = st.nb_network_evaluations;
+		out[1] = st.nb_node_count;
+		out[2] = st.nb_duplicate_nodes;
+		out[3] = st.nb_information_leaks;
+		out[4] = st.nb_proven_states;
+		out[5] = st.nb_wasted_expansions;
+	}
+}

@@ -86,3 +86,70 @@ class RefOracle:
     def is_forbidden(self, size, board, row, col, sign):
         board = np.ascontiguousarray(board, np.int8)
         return bool(self.lib.agref_is_forbidden(size, size, _p(board), int(row), int(col), int(sign)))
+
+
+EVAL_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                           ctypes.POINTER(ctypes.c_float))
+
+
+class RefSelfplay:
+    """One game driven by the reference's own Tree / Search / NNEvaluator (oracle/ref_shim_search.cpp). `evaluate` is a
+    Python callable: features uint32 [n, cells] -> (policy [n, cells], value [n, 3], q [n, cells, 3] or None)."""
+
+    def __init__(self, rules, size, evaluate, max_batch_size=8, max_simulations=100, init_to="parent", exploration_constant=1.25,
+                 information_leak_threshold=0.01, use_solver=False, solver_max_positions=100, draw_after=0):
+        self.lib = ctypes.CDLL(REF_LIB)
+        self.size, self.cells = size, size * size
+        self.evaluations = 0
+
+        def callback(ctx, features, batch, rows, cols, policy, value, action_values, moves_left):
+            f = np.ctypeslib.as_array(features, shape=(batch, rows * cols)).copy()
+            p, v, q = evaluate(f)
+            self.evaluations += batch
+            np.ctypeslib.as_array(policy, shape=(batch, rows * cols))[:] = p
+            np.ctypeslib.as_array(value, shape=(batch, 3))[:] = v
+            av = np.ctypeslib.as_array(action_values, shape=(batch, rows * cols, 3))
+            av[:] = 0.0 if q is None else q
+            np.ctypeslib.as_array(moves_left, shape=(batch,))[:] = 0.0
+
+        self._cb = EVAL_FN(callback)
+        self.lib.agref_sp_create.restype = ctypes.c_void_p
+        self.lib.agref_sp_create.argtypes = [ctypes.c_int] * 6 + [ctypes.c_char_p, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                             EVAL_FN, ctypes.c_void_p]
+        self.h = ctypes.c_void_p(self.lib.agref_sp_create(rules, size, size, draw_after, max_batch_size, max_simulations, init_to.encode(),
+                                                          exploration_constant, information_leak_threshold, int(use_solver),
+                                                          solver_max_positions, self._cb, None))
+
+    def set_position(self, board, stm):
+        board = np.ascontiguousarray(board, np.int8)
+        self.lib.agref_sp_set_position(self.h, _p(board), int(stm))
+
+    def step(self):
+        return self.lib.agref_sp_step(self.h)
+
+    def root(self):
+        visits = np.zeros(self.cells, np.int32)
+        priors = np.zeros(self.cells, np.float32)
+        q = np.zeros(self.cells, np.float32)
+        value = np.zeros(3, np.float32)
+        rv, ne = ctypes.c_int32(0), ctypes.c_int32(0)
+        self.lib.agref_sp_root(self.h, _p(visits), _p(priors), _p(q), _p(value), ctypes.byref(rv), ctypes.byref(ne))
+        return visits, priors, q, value, rv.value
+
+    def board(self):
+        b = np.zeros(self.cells, np.int8)
+        stm, outcome, last = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        self.lib.agref_sp_board(self.h, _p(b), ctypes.byref(stm), ctypes.byref(outcome), ctypes.byref(last))
+        return b, stm.value, outcome.value, last.value
+
+    def stats(self):
+        out = np.zeros(6, np.uint64)
+        self.lib.agref_sp_stats(self.h, _p(out))
+        return dict(zip(["nb_network_evaluations", "nb_node_count", "nb_duplicate_nodes", "nb_information_leaks", "nb_proven_states",
+                         "nb_wasted_expansions"], out.tolist()))
+
+    def close(self):
+        if self.h:
+            self.lib.agref_sp_destroy(self.h)
+            self.h = None
