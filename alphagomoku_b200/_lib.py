@@ -28,7 +28,8 @@ class AgbStats(ctypes.Structure):
         ("nb_network_evaluations", ctypes.c_uint64), ("nb_node_count", ctypes.c_uint64), ("nb_duplicate_nodes", ctypes.c_uint64),
         ("nb_information_leaks", ctypes.c_uint64), ("nb_proven_states", ctypes.c_uint64), ("nb_wasted_expansions", ctypes.c_uint64),
         ("nb_moves_played", ctypes.c_uint64), ("nb_games_finished", ctypes.c_uint64), ("nb_kernel_launches", ctypes.c_uint64),
-        ("overflow_flags", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 6),
+        ("overflow_flags", ctypes.c_uint64), ("nn_kernel_ns", ctypes.c_uint64), ("nn_kernel_launches", ctypes.c_uint64),
+        ("nn_positions", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 3),
     ]
 
 
@@ -54,6 +55,7 @@ SYMBOLS = {
     "agb_weights_size": (ctypes.c_size_t, [_VP]),
     "agb_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "agb_forward_dev": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
+    "agb_evaluate": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "agb_selfplay_reset": (_I, [_VP, _VP, _VP]),
     "agb_step": (_I, [_VP, _I]),
     "agb_pop_finished": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I)]),

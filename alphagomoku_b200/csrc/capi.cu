@@ -146,6 +146,8 @@ extern "C"
 		for (void *p : ptrs)
 			if (p)
 				cudaFree(p);
+		for (cudaEvent_t ev : e->events)
+			cudaEventDestroy(ev);
 		if (e->stream)
 			cudaStreamDestroy(e->stream);
 		delete e;

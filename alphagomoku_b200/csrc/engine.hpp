@@ -19,6 +19,8 @@ struct AgbEngine
 		cudaStream_t stream = nullptr;
 		std::string error;
 		uint64_t launches = 0;
+		uint64_t nn_kernel_ns = 0, nn_kernel_launches = 0, nn_positions = 0; // device timing of K4 inside agb_step
+		std::vector<cudaEvent_t> events; // reusable event pool for that timing
 
 		// static tables
 		uint8_t *d_pattern = nullptr; // [1<<20]
@@ -53,6 +55,7 @@ namespace agb
 	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev);
 	int launch_add_undo(AgbEngine *e, const uint16_t *moves_dev, int n, bool undo);
 	int launch_encode(AgbEngine *e, int n, uint32_t *features_dev);
+	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse);
 	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n);
 	int launch_outcomes(AgbEngine *e, const int8_t *boards_dev, const uint16_t *moves_dev, int n, int8_t *out_dev);
 	// resnet.cu

@@ -346,6 +346,26 @@ namespace agb
 			dst[gid] = permute_direction_bits(src[static_cast<size_t>(b) * cells + sr * S + sc], mode);
 		}
 
+		// apply_symmetry on float planes with `channels` values per cell (policy: 1, action values: 3); inverse = undo `mode`
+		__global__ void symmetry_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, const int8_t *__restrict__ symmetry, int n, int S,
+				int channels, int inverse)
+		{
+			const int cells = S * S;
+			const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+			if (gid >= static_cast<long long>(n) * cells)
+				return;
+			const int b = static_cast<int>(gid / cells);
+			const int i = static_cast<int>(gid - static_cast<long long>(b) * cells);
+			const int r = i / S, c = i - r * S;
+			int mode = symmetry[b];
+			if (inverse)
+				mode = inverse_symmetry(mode);
+			int sr, sc;
+			symmetry_source(mode, S, r, c, sr, sc);
+			for (int k = 0; k < channels; k++)
+				dst[gid * channels + k] = src[(static_cast<size_t>(b) * cells + sr * S + sc) * channels + k];
+		}
+
 		// ---- getOutcome, one warp per (board, last move) ----------------------------------------------------------------
 		__global__ void __launch_bounds__(kWarpsPerBlock * 32) outcome_kernel(Tables tables, const int8_t *__restrict__ boards,
 				const uint16_t *__restrict__ moves, int n, int S, int rules, int draw_after, int8_t *__restrict__ outcomes, uint32_t *status)
@@ -414,6 +434,14 @@ namespace agb
 	{
 		const long long total = static_cast<long long>(n) * e->cells;
 		augment_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, e->stream>>>(src_dev, dst_dev, sym_dev, n, e->cfg.rows);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		return AGB_OK;
+	}
+	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse)
+	{
+		const long long total = static_cast<long long>(n) * e->cells;
+		symmetry_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, e->stream>>>(src_dev, dst_dev, sym_dev, n, e->cfg.rows, channels, inverse ? 1 : 0);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

@@ -758,6 +758,63 @@ extern "C"
 			return AGB_OK;
 		return agb::net_forward_dev(e, features_dev, n, policy_dev, value_dev, q_dev);
 	}
+	int agb_evaluate(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *symmetry_host, int n, float *policy_host,
+			float *value_host, float *q_host)
+	{
+		if (n < 0 or n > e->store.capacity)
+			return e->fail(AGB_EINVAL, "n exceeds max_boards");
+		if (boards_host == nullptr or sign_to_move_host == nullptr or policy_host == nullptr or value_host == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		if (n == 0)
+			return AGB_OK;
+		agb::NetWeights *net = e->net;
+		if (net == nullptr or not net->loaded)
+			return e->fail(AGB_ESTATE, "no weights loaded");
+		const size_t cells = e->cells;
+		const bool want_q = (q_host != nullptr and e->cfg.q_head);
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8, boards_host, n * cells, cudaMemcpyHostToDevice, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8b, sign_to_move_host, n, cudaMemcpyHostToDevice, e->stream));
+		int rc = agb::launch_set_boards(e, e->d_io8, e->d_io8b, n, e->d_features); // pack: K1 + K3
+		if (rc != AGB_OK)
+			return rc;
+		const uint32_t *features = e->d_features;
+		if (symmetry_host != nullptr)
+		{ // NNEvaluator::pack_to_network: features.augment(symmetry)
+			for (int i = 0; i < n; i++)
+				if (symmetry_host[i] < 0 or symmetry_host[i] > 7)
+					return e->fail(AGB_EINVAL, "symmetry must be in 0..7");
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8b, symmetry_host, n, cudaMemcpyHostToDevice, e->stream));
+			rc = agb::launch_augment(e, e->d_features, e->d_features2, e->d_io8b, n);
+			if (rc != AGB_OK)
+				return rc;
+			features = e->d_features2;
+		}
+		rc = agb::net_forward_dev(e, features, n, net->d_policy, net->d_value, net->d_q); // forward: K4
+		if (rc != AGB_OK)
+			return rc;
+		const float *policy = net->d_policy, *q = net->d_q;
+		if (symmetry_host != nullptr)
+		{ // unpack_from_network: inverse symmetry on policy and action values
+			float *tmp_policy = reinterpret_cast<float*>(e->d_features); // features are dead now: reuse as scratch
+			rc = agb::launch_symmetry_f32(e, net->d_policy, tmp_policy, e->d_io8b, n, 1, true);
+			if (rc != AGB_OK)
+				return rc;
+			policy = tmp_policy;
+			if (want_q)
+			{
+				rc = agb::launch_symmetry_f32(e, net->d_q, net->d_value_hidden, e->d_io8b, n, 3, true); // value_hidden [n][cells*4] is free again
+				if (rc != AGB_OK)
+					return rc;
+				q = net->d_value_hidden;
+			}
+		}
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(policy_host, policy, n * cells * 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(value_host, net->d_value, n * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+		if (want_q)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(q_host, q, n * cells * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		return AGB_OK;
+	}
 	int agb_forward(AgbEngine *e, const uint32_t *features_host, int n, float *policy_host, float *value_host, float *q_host)
 	{
 		if (n < 0 or n > e->store.capacity)

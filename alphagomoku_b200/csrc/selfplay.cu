@@ -1196,6 +1196,14 @@ extern "C"
 		const Params p = make_params(e);
 		const unsigned grid = static_cast<unsigned>((s->games + 3) / 4);
 		const int max_tasks = s->games * s->batch;
+		while (static_cast<int>(e->events.size()) < 2 * n_steps)
+		{
+			cudaEvent_t ev;
+			AGB_CUDA_CHECK(e, cudaEventCreate(&ev));
+			e->events.push_back(ev);
+		}
+		unsigned long long evals_before = 0;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&evals_before, s->stats + ST_EVALS, 8, cudaMemcpyDeviceToHost, e->stream));
 		for (int step = 0; step < n_steps; step++)
 		{
 			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->eval_count, 0, sizeof(int32_t), e->stream));
@@ -1205,9 +1213,11 @@ extern "C"
 			int rc = launch_set_boards_counted(e, s->task_boards, s->task_stm, s->eval_count, max_tasks, s->features);
 			if (rc != AGB_OK)
 				return rc;
+			AGB_CUDA_CHECK(e, cudaEventRecord(e->events[2 * step], e->stream));
 			rc = net_forward_dev_counted(e, s->features, s->eval_count, max_tasks, s->policy, s->value, s->q);
 			if (rc != AGB_OK)
 				return rc;
+			AGB_CUDA_CHECK(e, cudaEventRecord(e->events[2 * step + 1], e->stream));
 			expand_backup_kernel<<<grid, 128, 0, e->stream>>>(p);
 			make_move_kernel<<<grid, 128, 0, e->stream>>>(p);
 			e->launches += 2;
@@ -1215,7 +1225,17 @@ extern "C"
 		}
 		uint32_t status = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, 4, cudaMemcpyDeviceToHost, e->stream));
+ 		unsigned long long evals_after = 0;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&evals_after, s->stats + ST_EVALS, 8, cudaMemcpyDeviceToHost, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		for (int step = 0; step < n_steps; step++)
+		{ // device time of the network kernels (K4 + value head) of this call
+			float ms = 0.0f;
+			if (cudaEventElapsedTime(&ms, e->events[2 * step], e->events[2 * step + 1]) == cudaSuccess)
+				e->nn_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
+		}
+		e->nn_kernel_launches += n_steps;
+		e->nn_positions += evals_after - evals_before;
 		if (status != 0)
 			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status) + " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table)");
 		return AGB_OK;
@@ -1235,6 +1255,9 @@ extern "C"
 			return AGB_EINVAL;
 		*stats = AgbStats { };
 		stats->nb_kernel_launches = e->launches;
+		stats->nn_kernel_ns = e->nn_kernel_ns;
+		stats->nn_kernel_launches = e->nn_kernel_launches;
+		stats->nn_positions = e->nn_positions;
 		if (e->selfplay != nullptr)
 		{
 			unsigned long long h[16];

@@ -173,6 +173,18 @@ class Engine:
         self._check(self._lib.agb_forward(self._h, _ptr(features), n, _ptr(policy), _ptr(value), _ptr(q)))
         return policy, value, q
 
+    def evaluate(self, boards, sign_to_move, symmetry=None, want_q=False):
+        """NNEvaluator::evaluateGraph for n positions given as host boards: pack (K1+K3) -> forward (K4) -> unpack."""
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, self.cells)
+        stm = np.ascontiguousarray(sign_to_move, np.int8).reshape(-1)
+        sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8).reshape(-1)
+        n = boards.shape[0]
+        policy = np.zeros((n, self.cells), np.float32)
+        value = np.zeros((n, 3), np.float32)
+        q = np.zeros((n, self.cells, 3), np.float32) if want_q else None
+        self._check(self._lib.agb_evaluate(self._h, _ptr(boards), _ptr(stm), _ptr(sym), n, _ptr(policy), _ptr(value), _ptr(q)))
+        return policy, value, q
+
     # ---- lockstep self-play ------------------------------------------------------------------------------------------
     def selfplay_reset(self, boards=None, sign_to_move=None):
         b = None if boards is None else np.ascontiguousarray(boards, np.int8)

@@ -135,6 +135,12 @@ size_t agb_weights_size(const AgbEngine *engine); /* expected blob size for the 
  * q[n][cells][3] f32 or NULL (NetworkDataPack.cpp:112-129, 200-235) */
 int agb_forward(AgbEngine *engine, const uint32_t *features_host, int n, float *policy_host, float *value_host, float *q_host);
 int agb_forward_dev(AgbEngine *engine, const uint32_t *features_dev, int n, float *policy_dev, float *value_dev, float *q_dev);
+/* NNEvaluator drop-in (src/search/monte_carlo/NNEvaluator.cpp:147-181 evaluateGraph = pack_to_network -> forward ->
+ * unpack_from_network): host boards in, host policy/value(/q) out; K1 + K3 + K4 run back to back on the device.
+ * symmetry[n] (0..7, or NULL for identity) is applied to the features before and inverted on policy/q after the network,
+ * like NNEvaluator::pack_to_network / unpack_from_network (NNEvaluator.cpp:244-286). */
+int agb_evaluate(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *symmetry_host, int n,
+		float *policy_host, float *value_host, float *q_host);
 
 /* ---- lockstep self-play (GameGenerator::generate, src/selfplay/GameGenerator.cpp:46-121, over all games) ------- */
 /* start (or restart) all games from given positions: boards[games][cells], sign_to_move[games]; NULL = empty boards, cross to move */
@@ -157,7 +163,11 @@ typedef struct AgbStats
 	uint64_t nb_games_finished;
 	uint64_t nb_kernel_launches; /* kernels this engine launched since creation */
 	uint64_t overflow_flags; /* non-zero: a bounded device structure overflowed */
-	uint64_t reserved[6];
+	/* PerfEstimator-style device timing of the network kernel inside agb_step (networks/perf_stats.hpp:22-46) */
+	uint64_t nn_kernel_ns; /* total CUDA-event time of the network kernel launches issued by agb_step */
+	uint64_t nn_kernel_launches;
+	uint64_t nn_positions; /* positions those launches evaluated */
+	uint64_t reserved[3];
 } AgbStats;
 int agb_get_stats(AgbEngine *engine, AgbStats *stats);
 

@@ -98,8 +98,9 @@ class RefSelfplay:
     Python callable: features uint32 [n, cells] -> (policy [n, cells], value [n, 3], q [n, cells, 3] or None)."""
 
     def __init__(self, rules, size, evaluate, max_batch_size=8, max_simulations=100, init_to="parent", exploration_constant=1.25,
-                 information_leak_threshold=0.01, use_solver=False, solver_max_positions=100, draw_after=0):
-        self.lib = ctypes.CDLL(REF_LIB)
+                 information_leak_threshold=0.01, use_solver=False, solver_max_positions=100, draw_after=0, fast=False):
+        # fast=True: the reference's Release flags (-O3 -DNDEBUG), for timing only (its RNG is then seeded from the clock)
+        self.lib = ctypes.CDLL(REF_LIB_FAST if fast and os.path.exists(REF_LIB_FAST) else REF_LIB)
         self.size, self.cells = size, size * size
         self.evaluations = 0
 
