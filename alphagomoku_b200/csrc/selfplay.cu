@@ -17,6 +17,7 @@
 // reference's "not processed by solver" path: edges for all empty cells + check_terminal_conditions.
 #include "engine.hpp"
 #include "patterns_logic.cuh"
+#include "records.cuh"
 
 #include <cfloat>
 #include <cstring>
@@ -154,14 +155,24 @@ namespace agb
 			int32_t *opening_cursor = nullptr;
 			// last sample per game (dense), for parity checks and K8
 			int32_t *sample_visits = nullptr; // [games][cells]
-			float *sample_prior = nullptr, *sample_q = nullptr; // [games][cells]
+			float *sample_prior = nullptr, *sample_win = nullptr, *sample_draw = nullptr; // [games][cells]
+			uint16_t *sample_score = nullptr; // [games][cells]
+			// K8: format-201 records. Per game: [u32 sample count][samples...] grows ply by ply; finished games are appended to a
+			// global queue as complete GameDataStorage blobs
+			uint8_t *rec_buf = nullptr; // [games][rec_cap]
+			int32_t *rec_len = nullptr, *rec_samples = nullptr;
+			int rec_cap = 0;
+			uint8_t *fin_buf = nullptr;
+			unsigned long long *fin_used = nullptr; // bytes used in fin_buf
+			int32_t *fin_games = nullptr;
+			unsigned long long fin_cap = 0;
 			float *sample_root = nullptr; // [games][4] win, draw, (visits), (move)
 	};
 
 	namespace
 	{
 		enum : int { ST_EVALS = 0, ST_NODES = 1, ST_DUP = 2, ST_LEAKS = 3, ST_PROVEN = 4, ST_WASTED = 5, ST_MOVES = 6, ST_GAMES = 7, ST_OVERFLOW = 8 };
-		enum : uint32_t { OVF_NODES = 2, OVF_EDGES = 4, OVF_PATH = 8, OVF_TABLE = 16 };
+		enum : uint32_t { OVF_NODES = 2, OVF_EDGES = 4, OVF_PATH = 8, OVF_TABLE = 16, OVF_RECORD = 32, OVF_FINISHED = 64 };
 
 		struct Params
 		{
@@ -780,6 +791,33 @@ namespace agb
 				p.s.n_stored[g] = 0;
 		}
 
+		// A game that starts from a position has no move order for the stones already on the board; like Game::loadOpening
+		// (src/game/Game.cpp:58-63) the record lists them as moves: cross and circle stones in row-major order, interleaved.
+		__device__ int opening_moves(const int8_t *board, int cells, int S, uint16_t *moves)
+		{
+			int n = 0, ci = 0, oi = 0;
+			while (true)
+			{
+				while (ci < cells and board[ci] != CROSS)
+					ci++;
+				while (oi < cells and board[oi] != CIRCLE)
+					oi++;
+				if (ci >= cells and oi >= cells)
+					break;
+				if (ci < cells)
+				{
+					moves[n++] = static_cast<uint16_t>(CROSS | ((ci / S) << 2) | ((ci % S) << 9));
+					ci++;
+				}
+				if (oi < cells)
+				{
+					moves[n++] = static_cast<uint16_t>(CIRCLE | ((oi / S) << 2) | ((oi % S) << 9));
+					oi++;
+				}
+			}
+			return n;
+		}
+
 		// ---- per-ply driver: final move, record, game end, subtree reuse ------------------------------------------------------
 		__global__ void __launch_bounds__(128) make_move_kernel(const __grid_constant__ Params p)
 		{
@@ -828,7 +866,9 @@ namespace agb
 			{
 				p.s.sample_visits[static_cast<size_t>(g) * cells + i] = 0;
 				p.s.sample_prior[static_cast<size_t>(g) * cells + i] = 0.0f;
-				p.s.sample_q[static_cast<size_t>(g) * cells + i] = 0.0f;
+				p.s.sample_win[static_cast<size_t>(g) * cells + i] = 0.0f;
+				p.s.sample_draw[static_cast<size_t>(g) * cells + i] = 0.0f;
+				p.s.sample_score[static_cast<size_t>(g) * cells + i] = score::kDefault;
 			}
 			__syncwarp();
 			for (int i = lane; i < R.n_edges; i += 32)
@@ -837,7 +877,9 @@ namespace agb
 				const int cell = ((e.move >> 2) & 127) * S + ((e.move >> 9) & 127);
 				p.s.sample_visits[static_cast<size_t>(g) * cells + cell] = e.visits;
 				p.s.sample_prior[static_cast<size_t>(g) * cells + cell] = e.prior;
-				p.s.sample_q[static_cast<size_t>(g) * cells + cell] = expectation(e.win, e.draw);
+				p.s.sample_win[static_cast<size_t>(g) * cells + cell] = e.win;
+				p.s.sample_draw[static_cast<size_t>(g) * cells + cell] = e.draw;
+				p.s.sample_score[static_cast<size_t>(g) * cells + cell] = e.score;
 			}
 			if (lane == 0)
 			{
@@ -847,6 +889,24 @@ namespace agb
 				p.s.sample_root[g * 4 + 3] = static_cast<float>(chosen.move);
 				atomicAdd(p.s.stats + ST_MOVES, 1ull);
 			}
+			// game_data_storage.addSample(sample): quantise and append this ply (K8)
+			__syncwarp();
+			if (lane == 0)
+			{
+				uint8_t *rec = p.s.rec_buf + static_cast<size_t>(g) * p.s.rec_cap;
+				int len = p.s.rec_len[g];
+				if (len + static_cast<int>(records::max_sample_bytes(cells)) > p.s.rec_cap)
+					atomicOr(p.status, OVF_RECORD);
+				else
+				{
+					const size_t base = static_cast<size_t>(g) * cells;
+					len += static_cast<int>(records::serialize_sample_v201(rec + len, cells, p.s.root_board + base, p.s.sample_visits + base, p.s.sample_prior + base,
+							p.s.sample_win + base, p.s.sample_draw + base, p.s.sample_score + base, R.score, 0));
+					p.s.rec_len[g] = len;
+					p.s.rec_samples[g] += 1;
+				}
+			}
+			__syncwarp();
 			// game.makeMove
 			const int row = (chosen.move >> 2) & 127, col = (chosen.move >> 9) & 127, sign = chosen.move & 3;
 			const int cell = row * S + col;
@@ -882,6 +942,48 @@ namespace agb
 					p.s.outcome[g] = static_cast<int8_t>(outcome);
 					atomicAdd(p.s.stats + ST_GAMES, 1ull);
 				}
+				// GameDataStorage::serialize (GameDataStorage.cpp:217-251): u32 samples, samples, u32 moves + u16[], outcome, rows = cols = 0
+				// (GameGenerator default-constructs its storage, GameGenerator.hpp:39); games without samples are not recorded
+				const int n_samples = p.s.rec_samples[g];
+				if (n_samples > 0)
+				{
+					const int n_moves = p.s.n_moves[g];
+					const int body = p.s.rec_len[g];
+					const unsigned long long total = static_cast<unsigned long long>(body) + 4 + 2ull * n_moves + 12;
+					unsigned long long dst_off = 0;
+					if (lane == 0)
+						dst_off = atomicAdd(p.s.fin_used, total);
+					dst_off = __shfl_sync(kFullMask, dst_off, 0);
+					if (dst_off + total > p.s.fin_cap)
+					{
+						if (lane == 0)
+							atomicOr(p.status, OVF_FINISHED);
+					}
+					else
+					{
+						uint8_t *dst = p.s.fin_buf + dst_off;
+						const uint8_t *rec = p.s.rec_buf + static_cast<size_t>(g) * p.s.rec_cap;
+						for (int i = lane; i < body; i += 32)
+							dst[i] = (i < 4) ? static_cast<uint8_t>((static_cast<uint32_t>(n_samples) >> (8 * i)) & 0xFF) : rec[i];
+						for (int i = lane; i < n_moves; i += 32)
+						{
+							const uint16_t mv = p.s.moves[static_cast<size_t>(g) * cells + i];
+							dst[body + 4 + 2 * i] = static_cast<uint8_t>(mv & 0xFF);
+							dst[body + 4 + 2 * i + 1] = static_cast<uint8_t>(mv >> 8);
+						}
+						if (lane == 0)
+						{
+							size_t off = body;
+							records::put32(dst, off, static_cast<uint32_t>(n_moves));
+							off += 2 * static_cast<size_t>(n_moves);
+							records::put32(dst, off, static_cast<uint32_t>(outcome));
+							records::put32(dst, off, 0u);
+							records::put32(dst, off, 0u);
+							atomicAdd(p.s.fin_games, 1);
+						}
+					}
+				}
+				__syncwarp();
 				int8_t next_stm = CROSS;
 				const int8_t *src = nullptr;
 				if (p.s.n_openings > 0)
@@ -918,10 +1020,12 @@ namespace agb
 				{
 					p.s.root_hash[g] = h ^ p.s.zobrist[cells * 2 + next_stm - 1];
 					p.s.root_stm[g] = next_stm;
-					p.s.n_moves[g] = 0;
+					p.s.n_moves[g] = opening_moves(board, cells, S, p.s.moves + static_cast<size_t>(g) * cells);
 					p.s.root_node[g] = -1;
 					p.s.n_nodes[g] = 0;
 					p.s.n_edges[g] = 0;
+					p.s.rec_len[g] = 4;
+					p.s.rec_samples[g] = 0;
 				}
 				int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
 				for (int i = lane; i < p.s.table_size; i += 32)
@@ -1027,8 +1131,10 @@ namespace agb
 			p.s.n_nodes[g] = 0;
 			p.s.n_edges[g] = 0;
 			p.s.n_stored[g] = 0;
-			p.s.n_moves[g] = 0;
+			p.s.n_moves[g] = opening_moves(p.s.root_board + static_cast<size_t>(g) * cells, cells, p.s.S, p.s.moves + static_cast<size_t>(g) * cells);
 			p.s.outcome[g] = 0;
+			p.s.rec_len[g] = 4;
+			p.s.rec_samples[g] = 0;
 		}
 
 		uint64_t splitmix64(uint64_t &x)
@@ -1113,7 +1219,17 @@ namespace agb
 		alloc(&s->opening_cursor, 1);
 		alloc(&s->sample_visits, G * cells);
 		alloc(&s->sample_prior, G * cells);
-		alloc(&s->sample_q, G * cells);
+		alloc(&s->sample_win, G * cells);
+		alloc(&s->sample_draw, G * cells);
+		alloc(&s->sample_score, G * cells);
+		s->rec_cap = 4 + static_cast<int>(records::max_sample_bytes(static_cast<int>(cells))) * (static_cast<int>(cells) + 1);
+		alloc(&s->rec_buf, G * s->rec_cap);
+		alloc(&s->rec_len, G);
+		alloc(&s->rec_samples, G);
+		s->fin_cap = static_cast<unsigned long long>(G) * 65536ull + (1ull << 22);
+		alloc(&s->fin_buf, s->fin_cap);
+		alloc(&s->fin_used, 1);
+		alloc(&s->fin_games, 1);
 		alloc(&s->sample_root, G * 4);
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1124,6 +1240,8 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->zobrist, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->opening_cursor, 0, 4, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_used, 0, 8, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_games, 0, 4, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		return AGB_OK;
 	}
@@ -1134,8 +1252,8 @@ namespace agb
 			return;
 		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
-				s->value, s->q, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_q,
-				s->sample_root };
+				s->value, s->q, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
+				s->sample_root, s->sample_draw, s->sample_score, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
 			if (ptr)
 				cudaFree(ptr);
@@ -1237,17 +1355,35 @@ extern "C"
 		e->nn_kernel_launches += n_steps;
 		e->nn_positions += evals_after - evals_before;
 		if (status != 0)
-			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status) + " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table)");
+			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status) + " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table, 32 record, 64 finished queue)");
 		return AGB_OK;
 	}
 
-	int agb_pop_finished(AgbEngine *e, void *, size_t, size_t *used, int *n_games)
+	int agb_pop_finished(AgbEngine *e, void *records_host, size_t capacity, size_t *used, int *n_games)
 	{
-		if (used)
-			*used = 0;
-		if (n_games)
-			*n_games = 0;
-		return e->fail(AGB_ESTATE, "format-201 record writer (K8) is not built yet; see DESIGN.md");
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games");
+		if (used == nullptr or n_games == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		*used = 0;
+		*n_games = 0;
+		unsigned long long bytes = 0;
+		int32_t games = 0;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&bytes, s->fin_used, 8, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&games, s->fin_games, 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		if (bytes == 0)
+			return AGB_OK;
+		if (bytes > capacity or records_host == nullptr)
+			return e->fail(AGB_ENOMEM, "record buffer too small: need " + std::to_string(bytes) + " bytes");
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(records_host, s->fin_buf, bytes, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_used, 0, 8, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_games, 0, 4, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		*used = bytes;
+		*n_games = games;
+		return AGB_OK;
 	}
 	int agb_get_stats(AgbEngine *e, AgbStats *stats)
 	{

@@ -4,6 +4,9 @@
 // make_move / prepare_search (src/selfplay/GameGenerator.cpp:46-185) made synchronous and started from a given position;
 // `use_solver = 0` leaves out the Search::solve() call so that the tree kernels can be compared before the device solver
 // exists (tasks then take the "not processed by solver" path of UnifiedGenerator, EdgeGenerator.cpp:269-303).
+#include <alphagomoku/dataset/GameDataBuffer.hpp>
+#include <alphagomoku/dataset/GameDataStorage.hpp>
+#include <alphagomoku/dataset/data_packs.hpp>
 #include <alphagomoku/game/Board.hpp>
 #include <alphagomoku/game/rules.hpp>
 #include <alphagomoku/networks/AGNetwork.hpp>
@@ -16,6 +19,9 @@
 #include <alphagomoku/utils/configs.hpp>
 #include <alphagomoku/utils/misc.hpp>
 
+#include <minml/utils/serialization.hpp>
+
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -44,6 +50,7 @@ namespace
 			NNEvaluator evaluator;
 			GameOutcome outcome = GameOutcome::UNKNOWN;
 			Move last_move;
+			GameDataStorage game_data_storage; // default constructed like GameGenerator's (GameGenerator.hpp:39)
 
 			RefSelfplay(const GameConfig &gc, const SelfplayConfig &sc, bool solver) :
 					game_config(gc),
@@ -108,6 +115,30 @@ extern "C"
 			sp->board[i] = static_cast<Sign>(board[i]);
 		sp->sign_to_move = static_cast<Sign>(sign_to_move);
 		sp->moves.clear();
+		{ // stones already on the board become the opening moves of the record: cross / circle in row-major order, interleaved
+			const int cells = sp->board.size(), cols = sp->board.cols();
+			int ci = 0, oi = 0;
+			while (true)
+			{
+				while (ci < cells and sp->board[ci] != Sign::CROSS)
+					ci++;
+				while (oi < cells and sp->board[oi] != Sign::CIRCLE)
+					oi++;
+				if (ci >= cells and oi >= cells)
+					break;
+				if (ci < cells)
+				{
+					sp->moves.push_back(Move(ci / cols, ci % cols, Sign::CROSS));
+					ci++;
+				}
+				if (oi < cells)
+				{
+					sp->moves.push_back(Move(oi / cols, oi % cols, Sign::CIRCLE));
+					oi++;
+				}
+			}
+		}
+		sp->game_data_storage.clear();
 		sp->outcome = GameOutcome::UNKNOWN;
 		sp->tree.clear();
 		sp->search.getSolver().clear();
@@ -134,13 +165,19 @@ extern "C"
 			const Node root_node = sp->tree.getInfo( { });
 			std::unique_ptr<EdgeSelector> selector = EdgeSelector::create(sp->selfplay_config.final_selector);
 			const Move move = selector->select(&root_node)->getMove();
+			SearchDataPack sample(root_node, sp->board);
+			sp->game_data_storage.addSample(sample);
 			Board::putMove(sp->board, move);
 			sp->moves.push_back(move);
 			sp->last_move = move;
 			sp->sign_to_move = invertSign(move.sign);
 			sp->outcome = getOutcome(sp->game_config.rules, sp->board, move, sp->game_config.draw_after);
 			if (sp->outcome != GameOutcome::UNKNOWN)
+			{ // GameGenerator.cpp:104-112
+				sp->game_data_storage.setOutcome(sp->outcome);
+				sp->game_data_storage.addMoves(sp->moves);
 				return 2;
+			}
 			sp->prepare_search();
 			return 1;
 		}
@@ -189,5 +226,63 @@ extern "C"
 		out[3] = st.nb_information_leaks;
 		out[4] = st.nb_proven_states;
 		out[5] = st.nb_wasted_expansions;
+	}
+	// GameDataStorage::serialize of the game played so far (complete once agref_sp_step returned 2)
+	size_t agref_sp_record(void *h, uint8_t *out, size_t capacity)
+	{
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		SerializedObject so;
+		sp->game_data_storage.serialize(so);
+		if (so.size() <= capacity)
+			std::memcpy(out, so.data(), so.size());
+		return so.size();
+	}
+	// SearchDataPack -> SearchDataStorage_v201::loadFrom -> serialize for one ply given as dense per-cell arrays
+	size_t agref_serialize_sample_v201(int rows, int cols, const int8_t *board, const int32_t *visits, const float *prior, const float *win,
+			const float *draw, const uint16_t *scores, uint16_t minimax_score, uint16_t flags, uint8_t *out, size_t capacity)
+	{
+		SearchDataPack pack(rows, cols);
+		for (int i = 0; i < rows * cols; i++)
+		{
+			pack.board[i] = static_cast<Sign>(board[i]);
+			pack.visit_count[i] = visits[i];
+			pack.policy_prior[i] = prior[i];
+			pack.action_values[i] = Value(win[i], draw[i]);
+			pack.action_scores[i] = Score::from_short(scores[i]);
+		}
+		pack.minimax_score = Score::from_short(minimax_score);
+		pack.flags = BitMask1D<uint16_t>(flags);
+		SearchDataStorage_v201 storage;
+		storage.loadFrom(pack);
+		SerializedObject so;
+		storage.serialize(so);
+		if (so.size() <= capacity)
+			std::memcpy(out, so.data(), so.size());
+		return so.size();
+	}
+	// GameDataBuffer::load (GameDataBuffer.cpp:113-128) of a file written by our host writer; returns games, fills samples per game
+	int agref_buffer_load(const char *path, int32_t *samples_per_game, int32_t *moves_per_game, int32_t *outcomes, int capacity, int32_t *rows,
+			int32_t *cols, int32_t *rules)
+	{
+		GameDataBuffer buffer;
+		try
+		{
+			buffer.load(path);
+		}
+		catch (const std::exception &ex)
+		{
+			std::fprintf(stderr, "agref_buffer_load: %s\n", ex.what());
+			return -1;
+		}
+		*rows = buffer.getConfig().rows;
+		*cols = buffer.getConfig().cols;
+		*rules = static_cast<int32_t>(buffer.getConfig().rules);
+		for (int i = 0; i < buffer.numberOfGames() and i < capacity; i++)
+		{
+			samples_per_game[i] = buffer.getGameData(i).numberOfSamples();
+			moves_per_game[i] = buffer.getGameData(i).numberOfMoves();
+			outcomes[i] = static_cast<int32_t>(buffer.getGameData(i).getOutcome());
+		}
+		return buffer.numberOfGames();
 	}
 }

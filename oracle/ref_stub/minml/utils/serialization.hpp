@@ -35,12 +35,11 @@ class SerializedObject
 			save(&value, sizeof(T));
 		}
 		template<typename T>
-		T load(size_t &offset) const
-		{
+		T load(size_t offset) const
+		{ // does not advance: every reference call site adds sizeof(T) itself (e.g. SearchDataStorage.cpp:298-316)
 			static_assert(std::is_trivially_copyable<T>::value, "");
 			T result;
 			load(&result, offset, sizeof(T));
-			offset += sizeof(T);
 			return result;
 		}
 };

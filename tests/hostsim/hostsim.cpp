@@ -90,3 +90,10 @@ extern "C" void hostsim_augment(uint32_t *dst, const uint32_t *src, int S, int m
 			dst[r * S + c] = permute_direction_bits(src[sr * S + sc], mode);
 		}
 }
+
+#include "../../alphagomoku_b200/csrc/records.cuh"
+extern "C" size_t hostsim_serialize_sample_v201(int cells, const int8_t *board, const int32_t *visits, const float *prior, const float *win,
+		const float *draw, const uint16_t *scores, uint16_t minimax_score, uint16_t flags, uint8_t *out)
+{
+	return agb::records::serialize_sample_v201(out, cells, board, visits, prior, win, draw, scores, minimax_score, flags);
+}

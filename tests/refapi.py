@@ -150,6 +150,13 @@ class RefSelfplay:
         return dict(zip(["nb_network_evaluations", "nb_node_count", "nb_duplicate_nodes", "nb_information_leaks", "nb_proven_states",
                          "nb_wasted_expansions"], out.tolist()))
 
+    def record(self):
+        """GameDataStorage::serialize of the game (complete after step() returned 2)."""
+        self.lib.agref_sp_record.restype = ctypes.c_size_t
+        buf = np.zeros(1 << 20, np.uint8)
+        n = self.lib.agref_sp_record(self.h, _p(buf), ctypes.c_size_t(buf.size))
+        return bytes(buf[:n])
+
     def close(self):
         if self.h:
             self.lib.agref_sp_destroy(self.h)

@@ -160,3 +160,60 @@ def test_engine_fails_loudly_without_a_gpu():
     with pytest.raises(agb.AgbError) as err:
         agb.Engine(agb.GameConfig(), max_boards=4)
     assert err.value.code == -2
+
+
+def test_record_codecs_match_reference(ref, hostsim):
+    """K8 logic (records.cuh, compiled for the host) against SearchDataStorage_v201::loadFrom/serialize of the reference:
+    quantised bytes identical on random root statistics, incl. proven scores and empty / dense visit patterns."""
+    rng = np.random.default_rng(21)
+    hostsim.hostsim_serialize_sample_v201.restype = ctypes.c_size_t
+    ref.lib.agref_serialize_sample_v201.restype = ctypes.c_size_t
+    for size in (15, 20):
+        cells = size * size
+        for trial in range(200):
+            board = random_boards(rng, size, 1)[0]
+            empty = board == 0
+            visits = np.where(empty & (rng.random(cells) < rng.random()), rng.integers(0, 1 + int(rng.integers(1, 800)), cells), 0).astype(np.int32)
+            prior = np.where(empty, rng.random(cells) ** 3, 0).astype(np.float32)
+            prior /= max(prior.sum(), 1e-9) if trial % 7 else 1.0
+            win = np.where(empty, rng.random(cells), 0).astype(np.float32)
+            draw = np.where(empty, (1 - win) * rng.random(cells), 0).astype(np.float32)
+            scores = np.full(cells, (2 << 13) | 4000, np.uint16)
+            k = rng.random(cells)
+            scores[empty & (k < 0.05)] = (3 << 13) | (4000 - int(rng.integers(1, 70)))  # win in n
+            scores[empty & (k > 0.95)] = (0 << 13) | (4000 + int(rng.integers(1, 70)))  # loss in n
+            scores[empty & (k > 0.45) & (k < 0.5)] = (2 << 13) | (4000 + int(rng.integers(-1000, 1001)))  # unproven eval
+            if trial % 11 == 0:
+                visits[:] = 0
+            minimax = int(scores[rng.integers(cells)])
+            flags = int(rng.integers(0, 8))
+            mine = np.zeros(16 + 6 * cells, np.uint8)
+            theirs = np.zeros(16 + 6 * cells, np.uint8)
+            n1 = hostsim.hostsim_serialize_sample_v201(cells, P(board), P(visits), P(prior), P(win), P(draw), P(scores), minimax, flags, P(mine))
+            n2 = ref.lib.agref_serialize_sample_v201(size, size, P(board), P(visits), P(prior), P(win), P(draw), P(scores), minimax, flags, P(theirs),
+                                                     ctypes.c_size_t(theirs.size))
+            assert n1 == n2, (size, trial, n1, n2)
+            assert (mine[:n1] == theirs[:n2]).all(), (size, trial, np.nonzero(mine[:n1] != theirs[:n2])[0][:8])
+
+
+def test_game_data_buffer_file_loads_in_the_reference(ref, tmp_path):
+    """A format-201 file framed by alphagomoku_b200.dataset loads with the reference's GameDataBuffer::load."""
+    from alphagomoku_b200 import dataset
+    import struct
+    games = []
+    for g in range(3):
+        samples = b""
+        for s in range(g + 1):
+            samples += struct.pack("<HHHHHHI", 1, 2, 3, (2 << 13) | 4000, s, 0, 2) + bytes([0, 10, 20, 128, 30, 40]) + bytes([5, 1, 2, 128, 3, 4])
+        moves = [1 | (7 << 2) | (7 << 9), 2 | (7 << 2) | (8 << 9)]
+        games.append(struct.pack("<I", g + 1) + samples + struct.pack("<I", len(moves)) + struct.pack(f"<{len(moves)}H", *moves) + struct.pack("<iii", 2, 0, 0))
+    buf = dataset.GameDataBuffer(1, 15, 15)
+    buf.add_records(b"".join(games), 3)
+    path = str(tmp_path / "buffer.bin")
+    buf.save(path)
+    spg, mpg, out = np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(8, np.int32)
+    rows, cols, rules = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    n = ref.lib.agref_buffer_load(path.encode(), P(spg), P(mpg), P(out), 8, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(rules))
+    assert n == 3 and (rows.value, cols.value, rules.value) == (15, 15, 1)
+    assert spg[:3].tolist() == [1, 2, 3] and mpg[:3].tolist() == [2, 2, 2] and out[:3].tolist() == [2, 2, 2]
+    assert dataset.parse_record(games[2])["samples"][1]["move_number"] == 1

@@ -36,7 +36,8 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
     import refapi
     size, games = 15, 6
     blocks, filters = 2, 64
-    eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
+    draw_after = 14  # short games, so that game ends, restarts and finished-game records are exercised too
+    eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
                      games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
@@ -48,12 +49,13 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
     eng.selfplay_reset(boards, stm)
     refs = []
     for g in range(games):
-        r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=False)
+        r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=False, draw_after=draw_after)
         r.set_position(boards[g], stm[g])
         refs.append(r)
     active = [True] * games
     moves_checked = 0
-    for step in range(220):
+    ref_records = []
+    for step in range(400):
         eng.step(1)
         for g in range(games):
             if not active[g]:
@@ -62,6 +64,7 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
             rb, rstm, routcome, rlast = refs[g].board()
             if status == 2:
                 active[g] = False  # the device engine restarts the game; the reference instance stops here
+                ref_records.append(refs[g].record())
                 moves_checked += 1
                 continue
             db, dstm, _ = eng.get_board(g)
@@ -78,6 +81,13 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
             break
     st = eng.stats()
     assert st["overflow_flags"] == 0
+    # K8: every finished reference game must appear byte for byte among the device's format-201 records
+    from alphagomoku_b200 import dataset
+    blob, n_finished = eng.pop_finished()
+    device_records = dataset.split_records(blob, n_finished)
+    assert len(ref_records) >= 1
+    for rec in ref_records:
+        assert rec in device_records, dataset.parse_record(rec)["moves"]
     assert moves_checked >= 10
     assert st["nb_games_finished"] >= games - sum(active)
     for r in refs:
