@@ -49,8 +49,8 @@ namespace agb
 			ConvDesc layers[kMaxConvLayers];
 			int n_layers;
 			int S, P, F; // board size, row pitch (S + 2), filters
-			int n_stages, stage_bytes; // weight ring: stage_bytes = kc_per_stage * F * 16
-			int kc_per_stage; // 8-channel weight slices (F rows x 16 bytes) per stage, even
+			int n_stages, stage_bytes; // weight ring: stage_bytes = kc_per_stage * (F / 2) * 16 (each CTA of a pair holds half of C_out)
+			int kc_per_stage; // 8-channel weight slices ((F / 2) rows x 16 bytes) per stage, even
 			int buf_bytes; // one trunk image: (F / 8) * img_rows * 16
 			int img_rows, in_img_rows;
 			const uint8_t *w_images;
@@ -97,10 +97,59 @@ namespace agb
 			hi = __uint_as_float(w & 0xFFFF0000u);
 		}
 
-		__global__ void __launch_bounds__(kThreads, 1) resnet_board_kernel(const __grid_constant__ NetParams prm)
+		// Straight-line MMA schedule of one 3x3, F -> F convolution on a 15x15 board (the trunk and head convs: 40 of the
+		// 42 layers of a 20-block net). The issuing lane cannot hide latency, so everything that can be a compile-time constant
+		// is one: tap offsets (row pitch 17), K-slice offsets and the weight-ring geometry (32 KiB stages). Per MMA pair the lane
+		// executes two 64-bit adds and the two tcgen05.mma instructions.
+		template<int F>
+		__device__ __forceinline__ void issue_conv3x3_15(uint32_t tmem_base, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
+				uint32_t stage_step, uint64_t *w_full, uint64_t *peer_full, uint64_t *w_empty, int &stage, uint32_t &phase, int n_stages)
+		{
+			constexpr int P = 17;
+			constexpr int KC = F / 8; // 8-channel slices per tap
+			constexpr int TPS = 32768 / ((F / 2) * 16 * KC); // taps per 32 KiB stage: 2 (F = 128) or 8 (F = 64)
+#pragma unroll
+			for (int t0 = 0; t0 < 9; t0 += TPS)
+			{
+				mbar_wait(&w_full[stage], phase); // our half of the weights
+				mbar_wait_cluster(&peer_full[stage], phase); // the peer's half
+				tc_fence_after();
+				const uint64_t b_stage = b_desc0 + static_cast<uint32_t>(stage) * stage_step;
+				if (elect_one())
+				{
+#pragma unroll
+					for (int tt = 0; tt < TPS; tt++)
+					{
+						const int tap = t0 + tt;
+						if (tap < 9)
+						{
+							const int row0 = (tap / 3) * P + (tap % 3);
+#pragma unroll
+							for (int ks = 0; ks < KC / 2; ks++)
+							{
+								const uint64_t ad = a_desc0 + row0 + static_cast<uint32_t>(2 * ks) * a_kc_step;
+								const uint64_t bd = b_stage + (tt * KC + 2 * ks) * (F / 2);
+								mma_pair_bf16(tmem_base, ad, bd, idesc, (tap | ks) != 0);
+								mma_pair_bf16(tmem_base + F, ad + 128, bd, idesc, (tap | ks) != 0);
+							}
+						}
+					}
+					mma_pair_commit(&w_empty[stage], 3); // both CTAs may refill this stage once these MMAs have read it
+				}
+				__syncwarp();
+				if (++stage == n_stages)
+				{
+					stage = 0;
+					phase ^= 1;
+				}
+			}
+		}
+
+		template<int F>
+		__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) resnet_board_kernel(const __grid_constant__ NetParams prm)
 		{
 			extern __shared__ __align__(1024) uint8_t smem[];
-			const int S = prm.S, P = prm.P, F = prm.F;
+			const int S = prm.S, P = prm.P;
 			const int n_boards = prm.n_boards_dev ? *prm.n_boards_dev : prm.n_boards;
 			const int NS = prm.n_stages;
 			uint8_t *buf_x = smem;
@@ -109,9 +158,13 @@ namespace agb
 			float *partial = reinterpret_cast<float*>(stages + NS * prm.stage_bytes); // [2][3][256]
 			float *logits = partial + 2 * 3 * 256; // [256]
 			float *reduce = logits + 256; // [8]
-			uint64_t *bars = reinterpret_cast<uint64_t*>(reduce + 8);
-			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *img_ready = bars + 17;
-			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+			float *sbias2 = reduce + 8; // [2][128]
+			uint64_t *bars = reinterpret_cast<uint64_t*>(sbias2 + 256);
+			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *img_ready = bars + 17, *peer_full = bars + 18;
+			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+			// CTA pair: rank 0 (leader) issues the MMAs for both boards; each CTA loads half of every weight tile
+			const uint32_t rank = cluster_ctarank();
+			const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
 			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 			const uint32_t img_chunk_bytes = prm.img_rows * 16;
@@ -124,21 +177,23 @@ namespace agb
 				{
 					mbar_init(&w_full[s], 1);
 					mbar_init(&w_empty[s], 1);
+					mbar_init(&peer_full[s], 1);
 				}
 				mbar_init(acc_full, 1);
-				mbar_init(img_ready, kEpilogueThreads);
+				mbar_init(img_ready, 2 * kEpilogueThreads); // both CTAs' epilogue threads arrive on the leader's barrier
 				fence_mbar_init();
 			}
 			if (warp == 1)
 			{
-				tmem_alloc(tmem_slot, tmem_cols);
-				tmem_relinquish();
+				tmem_alloc_pair(tmem_slot, tmem_cols);
+				tmem_relinquish_pair();
 			}
 			// x image: the halo and the two pad columns stay zero for the whole kernel (only valid cells are ever written)
 			for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kThreads)
 				reinterpret_cast<uint4*>(buf_x)[i] = make_uint4(0, 0, 0, 0);
 			tc_fence_before();
 			__syncthreads();
+			cluster_sync(); // barriers of both CTAs are initialised before any remote arrive / multicast commit
 			tc_fence_after();
 			const uint32_t tmem_base = *tmem_slot;
 
@@ -148,17 +203,18 @@ namespace agb
 				{
 					int stage = 0;
 					uint32_t phase = 0;
-					for (int b = blockIdx.x; b < n_boards; b += gridDim.x)
+					for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
 							const int total_kc = L.n_taps * L.cin_chunks; // the layer's weights as a stream of 8-channel slices
 							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
-								const uint32_t bytes = min(prm.kc_per_stage, total_kc - kc0) * F * 16;
-								mbar_wait(&w_empty[stage], phase ^ 1);
+								const uint32_t bytes = min(prm.kc_per_stage, total_kc - kc0) * (F / 2) * 16;
+								mbar_wait_backoff(&w_empty[stage], phase ^ 1);
 								mbar_arrive_expect_tx(&w_full[stage], bytes);
-								bulk_g2s(stages + stage * prm.stage_bytes, prm.w_images + L.w_offset + static_cast<size_t>(kc0) * F * 16, bytes, &w_full[stage]);
+								bulk_g2s(stages + stage * prm.stage_bytes, prm.w_images + L.w_offset + (static_cast<size_t>(rank) * total_kc + kc0) * (F / 2) * 16, bytes,
+										&w_full[stage]);
 								if (++stage == NS)
 								{
 									stage = 0;
@@ -169,13 +225,13 @@ namespace agb
 				}
 			}
 			else if (warp == 1)
-			{ // ===== MMA issuer =====
-				if (lane == 0)
-				{
+			{ // ===== MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =====
+				if (rank == 0)
+				{ // the whole warp walks the (warp-uniform) schedule; one elected lane issues the MMAs and commits
 					int stage = 0;
 					uint32_t phase = 0, img_phase = 0;
-					const uint32_t idesc = idesc_bf16_f32(128, F);
-					for (int b = blockIdx.x; b < n_boards; b += gridDim.x)
+					const uint32_t idesc = idesc_bf16_f32(256, F); // M = 256: 128 positions of this CTA's board + 128 of the peer's
+					for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -183,33 +239,47 @@ namespace agb
 							const uint32_t a_lbo = (L.mode == MODE_STEM) ? in_chunk_bytes : img_chunk_bytes;
 							const uint32_t a_img = smem_u32((L.mode == MODE_STEM or L.mode == MODE_CONV2) ? buf_h : buf_x);
 							const int total_kc = L.n_taps * L.cin_chunks, cin_chunks = L.cin_chunks;
-							// descriptors are advanced by adding to their 14-bit start-address field (16-byte units); no field can carry
-							const uint64_t a_desc0 = smem_desc(a_img, a_lbo, 128), b_desc0 = smem_desc(smem_u32(stages), F * 16, 128);
-							const uint32_t a_kc_step = a_lbo >> 4, b_kc_step = F, stage_step = prm.stage_bytes >> 4;
-							mbar_wait(img_ready, img_phase & 1); // input image written, accumulators drained
+							// descriptors are advanced by adding to their 14-bit start-address field (16-byte units); no field can carry.
+							// The same shared-memory offsets are valid in both CTAs of the pair.
+							const uint64_t a_desc0 = smem_desc(a_img, a_lbo, 128), b_desc0 = smem_desc(smem_u32(stages), (F / 2) * 16, 128);
+							const uint32_t a_kc_step = a_lbo >> 4, b_kc_step = F / 2, stage_step = prm.stage_bytes >> 4;
+							mbar_wait_cluster(img_ready, img_phase & 1); // both input images written, both accumulators drained
 							img_phase++;
 							tc_fence_after();
-							if (prm.trace and b == 0)
-								prm.trace[4 * l + 0] = clock64();
-							int tap = 0, kin = 0, ky = 0, kx = 0; // position in the layer's stream of 8-channel weight slices
+							if (prm.trace and b0 == 0 and lane == 0)
+								prm.trace[6 * l + 0] = clock64();
+							int kin = 0, ky = 0, kx = 0; // position in the layer's stream of 8-channel weight slices
+							long long wait_own = 0, wait_peer = 0;
+							const bool fast = (S == 15 and L.radius == 1 and cin_chunks == F / 8 and prm.stage_bytes == 32768);
+							if (fast)
+								issue_conv3x3_15<F>(tmem_base, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, stage, phase, NS);
+							else
 							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
 								const int nkc = min(prm.kc_per_stage, total_kc - kc0);
-								mbar_wait(&w_full[stage], phase);
+								const long long tw0 = clock64();
+								mbar_wait(&w_full[stage], phase); // our half of the weights
+								const long long tw1 = clock64();
+								mbar_wait_cluster(&peer_full[stage], phase); // the peer's half
+								wait_own += tw1 - tw0;
+								wait_peer += clock64() - tw1;
 								tc_fence_after();
 								uint64_t bd = b_desc0 + stage * stage_step;
 								for (int j = 0; j < nkc; j += 2)
-								{ // one K=16 step: two 8-channel slices of one tap
+								{ // one K=16 step: two 8-channel slices of one tap, for both M-tiles of both boards
 									const uint64_t ad = a_desc0 + (ky * P + kx) + kin * a_kc_step;
 									const bool acc = (kc0 + j) != 0;
-									mma_bf16(tmem_base, ad, bd, idesc, acc);
-									mma_bf16(tmem_base + F, ad + 128, bd, idesc, acc);
+									if (elect_one())
+									{
+										mma_pair_bf16(tmem_base, ad, bd, idesc, acc);
+										mma_pair_bf16(tmem_base + F, ad + 128, bd, idesc, acc);
+									}
+									__syncwarp();
 									bd += 2 * b_kc_step;
 									kin += 2;
 									if (kin == cin_chunks)
 									{
 										kin = 0;
-										tap++;
 										if (++kx == KW)
 										{
 											kx = 0;
@@ -217,16 +287,44 @@ namespace agb
 										}
 									}
 								}
-								mma_commit(&w_empty[stage]); // stage may be refilled once these MMAs have read it
+								if (elect_one())
+									mma_pair_commit(&w_empty[stage], 3); // both CTAs may refill this stage once these MMAs have read it
+								__syncwarp();
 								if (++stage == NS)
 								{
 									stage = 0;
 									phase ^= 1;
 								}
 							}
-							if (prm.trace and b == 0)
-								prm.trace[4 * l + 1] = clock64();
-							mma_commit(acc_full);
+							if (prm.trace and b0 == 0 and lane == 0)
+							{
+								prm.trace[6 * l + 1] = clock64();
+								prm.trace[6 * l + 4] = wait_own;
+								prm.trace[6 * l + 5] = wait_peer;
+							}
+							if (elect_one())
+								mma_pair_commit(acc_full, 3);
+							__syncwarp();
+						}
+				}
+				else if (lane == 0)
+				{ // peer CTA: tell the leader when our half of each weight stage has landed
+					int stage = 0;
+					uint32_t phase = 0;
+					for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
+						for (int l = 0; l < prm.n_layers; l++)
+						{
+							const int total_kc = prm.layers[l].n_taps * prm.layers[l].cin_chunks;
+							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
+							{
+								mbar_wait_backoff(&w_full[stage], phase);
+								mbar_arrive_remote(&peer_full[stage], 0);
+								if (++stage == NS)
+								{
+									stage = 0;
+									phase ^= 1;
+								}
+							}
 						}
 				}
 			}
@@ -237,15 +335,17 @@ namespace agb
 				const int half = (warp - 2) >> 2; // which half of the output channels
 				const int cells = S * S;
 				uint32_t acc_phase = 0;
-				for (int b = blockIdx.x; b < n_boards; b += gridDim.x)
+				for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
 				{
+					const int b = b0 + rank; // this CTA's board
+					const bool live = b < n_boards; // an odd batch leaves the last peer without a board: it still runs every barrier
 					// ---- prologue: feature words -> bf16 stem image (32 channels, halo 2) in the h buffer ----
 					for (uint32_t i = et; i < 4 * in_chunk_bytes / 16; i += kEpilogueThreads)
 						reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
 					named_barrier_epilogue();
 					for (int cell = et; cell < cells; cell += kEpilogueThreads)
 					{
-						const uint32_t f = prm.features[static_cast<size_t>(b) * cells + cell];
+						const uint32_t f = live ? prm.features[static_cast<size_t>(b) * cells + cell] : 0u;
 						const int y = cell / S, x = cell - y * S;
 						const uint32_t idx = (y + 2) * P + x + 2;
 #pragma unroll
@@ -262,52 +362,72 @@ namespace agb
 					}
 					fence_proxy_async();
 					tc_fence_before();
-					mbar_arrive(img_ready);
+					if (rank == 0)
+						mbar_arrive(img_ready);
+					else
+						mbar_arrive_remote(img_ready, 0);
 
 					for (int l = 0; l < prm.n_layers; l++)
 					{
 						const ConvDesc &L = prm.layers[l];
-						mbar_wait(acc_full, acc_phase & 1);
+						// this layer's bias goes to shared memory while its MMAs are still running
+						// (double buffered by layer parity: slower warps may still be reading the previous layer's copy)
+						float *sbias = sbias2 + (l & 1) * 128;
+						if (et < F)
+							sbias[et] = __ldg(prm.bias + L.bias_offset + et);
+						named_barrier_epilogue();
+						mbar_wait_backoff(acc_full, acc_phase & 1, 32);
 						acc_phase++;
 						tc_fence_after();
 						if (prm.trace and b == 0 and et == 0)
-							prm.trace[4 * l + 2] = clock64();
+							prm.trace[6 * l + 2] = clock64();
 						if (L.mode == MODE_STEM)
 						{ // the stem image is dead now: give the h buffer its zero halo back
 							for (uint32_t i = et; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kEpilogueThreads)
 								reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
 						}
 						uint8_t *out_img = (L.mode == MODE_CONV1) ? buf_h : buf_x;
-						const float *bias = prm.bias + L.bias_offset;
 						float head[2][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
+						constexpr int HC = F / 2; // output channels handled by this warp (its half), as HC/16 TMEM loads of 16 columns
 						for (int tile = 0; tile < 2; tile++)
 						{
 							const int p = tile * 128 + quadrant * 32 + lane;
 							const int y = p / P, x = p - y * P;
 							const bool valid = (y < S) and (x < S);
 							const uint32_t out_idx = p + P + 1;
-							for (int cb = 0; cb < F / 2; cb += 16)
+							// all TMEM loads of this tile are issued back to back and waited for once
+							uint32_t v[HC];
+#pragma unroll
+							for (int cb = 0; cb < HC; cb += 16)
+								tmem_ld16(tmem_base + ((quadrant * 32u) << 16) + tile * F + half * HC + cb, *reinterpret_cast<uint32_t (*)[16]>(&v[cb]));
+							uint4 res[HC / 8];
+							if (L.mode == MODE_CONV2)
+							{ // residual operand: x is updated in place
+#pragma unroll
+								for (int h8 = 0; h8 < HC / 8; h8++)
+									res[h8] = *reinterpret_cast<const uint4*>(buf_x + ((half * HC) / 8 + h8) * img_chunk_bytes + out_idx * 16);
+							}
+							tmem_ld_wait();
+#pragma unroll
+							for (int cb = 0; cb < HC; cb += 16)
 							{
-								const int c0 = half * (F / 2) + cb;
-								uint32_t v[16];
-								tmem_ld16(tmem_base + ((quadrant * 32u) << 16) + tile * F + c0, v);
-								tmem_ld_wait();
+								const int c0 = half * HC + cb;
 								float a[16];
 #pragma unroll
 								for (int j = 0; j < 16; j += 4)
 								{
-									const float4 bj = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-									a[j] = __uint_as_float(v[j]) + bj.x;
-									a[j + 1] = __uint_as_float(v[j + 1]) + bj.y;
-									a[j + 2] = __uint_as_float(v[j + 2]) + bj.z;
-									a[j + 3] = __uint_as_float(v[j + 3]) + bj.w;
+									const float4 bj = *reinterpret_cast<const float4*>(sbias + c0 + j);
+									a[j] = __uint_as_float(v[cb + j]) + bj.x;
+									a[j + 1] = __uint_as_float(v[cb + j + 1]) + bj.y;
+									a[j + 2] = __uint_as_float(v[cb + j + 2]) + bj.z;
+									a[j + 3] = __uint_as_float(v[cb + j + 3]) + bj.w;
 								}
 								if (L.mode == MODE_CONV2)
-								{ // residual: x is updated in place
+								{
 #pragma unroll
 									for (int h8 = 0; h8 < 2; h8++)
 									{
-										const uint4 r = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16);
+										const uint4 r = res[cb / 8 + h8];
 										float lo, hi;
 										unpack_bf16(r.x, lo, hi); a[8 * h8 + 0] += lo; a[8 * h8 + 1] += hi;
 										unpack_bf16(r.y, lo, hi); a[8 * h8 + 2] += lo; a[8 * h8 + 3] += hi;
@@ -387,7 +507,7 @@ namespace agb
 							for (int w = 0; w < 8; w++)
 								s += reduce[w];
 							const int p = et, y = p / P, x = p - y * P;
-							if (y < S and x < S)
+							if (live and y < S and x < S)
 								prm.policy[static_cast<size_t>(b) * cells + y * S + x] = e / s;
 							named_barrier_epilogue();
 						}
@@ -398,7 +518,7 @@ namespace agb
 									partial[(half * 3 + k) * 256 + tile * 128 + quadrant * 32 + lane] = head[tile][k];
 							named_barrier_epilogue();
 							const int p = et, y = p / P, x = p - y * P;
-							if (y < S and x < S and prm.q != nullptr)
+							if (live and y < S and x < S and prm.q != nullptr)
 							{
 								float z[3];
 								for (int k = 0; k < 3; k++)
@@ -440,23 +560,28 @@ namespace agb
 								o.y = fmaxf(s4[1] + __ldg(prm.value_w + 4 * F + 1), 0.f);
 								o.z = fmaxf(s4[2] + __ldg(prm.value_w + 4 * F + 2), 0.f);
 								o.w = fmaxf(s4[3] + __ldg(prm.value_w + 4 * F + 3), 0.f);
-								*reinterpret_cast<float4*>(prm.value_hidden + (static_cast<size_t>(b) * cells + cell) * 4) = o;
+								if (live)
+									*reinterpret_cast<float4*>(prm.value_hidden + (static_cast<size_t>(b) * cells + cell) * 4) = o;
 							}
 						}
 						if (prm.trace and b == 0 and et == 0)
-							prm.trace[4 * l + 3] = clock64();
+							prm.trace[6 * l + 3] = clock64();
 						if (l + 1 < prm.n_layers)
 						{ // hand the image (and the drained accumulators) to the MMA warp
 							fence_proxy_async();
-							mbar_arrive(img_ready);
+							if (rank == 0)
+								mbar_arrive(img_ready);
+							else
+								mbar_arrive_remote(img_ready, 0);
 						}
 					}
 				}
 			}
 			tc_fence_before();
 			__syncthreads();
+			cluster_sync(); // the peer may still be reading TMEM / receiving our remote arrivals
 			if (warp == 1)
-				tmem_dealloc(tmem_base, tmem_cols);
+				tmem_dealloc_pair(tmem_base, tmem_cols);
 		}
 
 		// ---- value head: dense(4*cells -> D) + ReLU, dense(D -> 3), softmax (createValueHead, blocks.cpp:112-117) --------
@@ -523,7 +648,7 @@ namespace agb
 				n += f * 9 * f + f + 3 * f + 3;
 			return n;
 		}
-		// fp32 W[F][k][k][cin] -> bf16 tap images [tap][cin/8][F][8]
+		// fp32 W[F][k][k][cin] -> bf16 tap images [half][tap][cin/8][F/2][8]
 		void append_conv_image(std::vector<uint16_t> &img, const float *w, int F, int k, int cin)
 		{
 			const auto to_bf16 = [](float x)
@@ -533,11 +658,13 @@ namespace agb
 				const uint32_t rounded = u + 0x7FFFu + ((u >> 16) & 1u); // round to nearest even
 				return static_cast<uint16_t>(rounded >> 16);
 			};
-			for (int tap = 0; tap < k * k; tap++)
-				for (int kc = 0; kc < cin / 8; kc++)
-					for (int co = 0; co < F; co++)
-						for (int e = 0; e < 8; e++)
-							img.push_back(to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]));
+			// half-major: CTA `half` of a pair streams [tap][cin/8][F/2 rows][8] for output channels half*F/2 ..
+			for (int half = 0; half < 2; half++)
+				for (int tap = 0; tap < k * k; tap++)
+					for (int kc = 0; kc < cin / 8; kc++)
+						for (int co = half * (F / 2); co < (half + 1) * (F / 2); co++)
+							for (int e = 0; e < 8; e++)
+								img.push_back(to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]));
 		}
 	}
 
@@ -586,7 +713,7 @@ namespace agb
 		{ // weight ring geometry (tunable: AGB_NET_STAGE_KB / AGB_NET_STAGES)
 			const char *kb = getenv("AGB_NET_STAGE_KB"), *ns = getenv("AGB_NET_STAGES");
 			p.stage_bytes = (kb ? atoi(kb) : 32) * 1024; // measured best on B200 (profiles/r01_k4_weight_ring.txt)
-			p.kc_per_stage = p.stage_bytes / (F * 16);
+			p.kc_per_stage = p.stage_bytes / ((F / 2) * 16);
 			p.n_stages = ns ? atoi(ns) : ((F == 128) ? 2 : 4);
 			if (p.kc_per_stage < 2 or p.kc_per_stage % 2 != 0 or p.n_stages < 2 or p.n_stages > kMaxStages)
 				return e->fail(AGB_EINVAL, "bad weight ring geometry");
@@ -672,8 +799,11 @@ namespace agb
 		p.q_w1 = c.q_head ? n->d_small + q_w1_off : nullptr;
 		p.value_hidden = n->d_value_hidden;
 		n->dense_width = D;
-		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (2 * 3 * 256 + 256 + 8) * 4 + 20 * 8;
-		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
+		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (2 * 3 * 256 + 256 + 8 + 256) * 4 + 20 * 8;
+		if (F == 128)
+			AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
+		else
+			AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
 		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cells * 4 + D) * 4));
 		n->loaded = true;
 		return AGB_OK;
@@ -693,24 +823,29 @@ namespace agb
 		static long long *d_trace = nullptr;
 		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
 		if (trace and d_trace == nullptr)
-			cudaMalloc(&d_trace, kMaxConvLayers * 4 * sizeof(long long));
+			cudaMalloc(&d_trace, kMaxConvLayers * 6 * sizeof(long long));
 		p.trace = trace ? d_trace : nullptr;
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
-		const int grid = n_boards < sms ? n_boards : sms;
-		resnet_board_kernel<<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
+		const int pairs = std::min((n_boards + 1) / 2, sms / 2);
+		const int grid = 2 * pairs; // clusters of two CTAs, one board each
+		if (p.F == 128)
+			resnet_board_kernel<128><<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
+		else
+			resnet_board_kernel<64><<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		if (trace)
 		{
-			std::vector<long long> h(kMaxConvLayers * 4);
+			std::vector<long long> h(kMaxConvLayers * 6);
 			cudaStreamSynchronize(e->stream);
 			cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
 			FILE *f = fopen(getenv("AGB_NET_TRACE"), "w");
 			if (f)
 			{
 				for (int l = 0; l < p.n_layers; l++)
-					fprintf(f, "%d %lld %lld %lld %lld\n", l, h[4 * l] - h[0], h[4 * l + 1] - h[0], h[4 * l + 2] - h[0], h[4 * l + 3] - h[0]);
+					fprintf(f, "%d %lld %lld %lld %lld  wait_own=%lld wait_peer=%lld\n", l, h[6 * l] - h[0], h[6 * l + 1] - h[0], h[6 * l + 2] - h[0], h[6 * l + 3] - h[0],
+							h[6 * l + 4], h[6 * l + 5]);
 				fclose(f);
 			}
 		}

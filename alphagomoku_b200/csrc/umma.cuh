@@ -49,6 +49,12 @@ namespace agb
 			{
 			}
 		}
+		// for roles that wait a long time next to the MMA-issuing lane: back off so the spin does not take issue slots from it
+		__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns = 64)
+		{
+			while (not mbar_try_wait(bar, parity))
+				__nanosleep(ns);
+		}
 		// generic-proxy shared-memory writes -> visible to the async proxy (TMA / tensor core reads)
 		__device__ __forceinline__ void fence_proxy_async()
 		{
@@ -121,6 +127,71 @@ namespace agb
 		__device__ __forceinline__ void tmem_ld_wait()
 		{
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+		}
+	}
+}
+
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster share one MMA. Each CTA supplies 128 rows of A and half of
+// the rows of B from its own shared memory (same offsets in both), the leader CTA issues, and each CTA finds its 128 rows
+// of D in its own TMEM. Validated on hardware by tools/umma_probe2.cu (64 cycles per M=256,N=128,K=16 instruction).
+namespace agb
+{
+	namespace umma
+	{
+		// one lane of a converged warp (elect.sync); used to issue single-thread instructions from warp-uniform code so that
+		// descriptors stay in uniform registers
+		__device__ __forceinline__ bool elect_one()
+		{
+			uint32_t pred = 0;
+			asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+			return pred != 0;
+		}
+		__device__ __forceinline__ uint32_t cluster_ctarank()
+		{
+			uint32_t r;
+			asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+			return r;
+		}
+		__device__ __forceinline__ void cluster_sync()
+		{
+			asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+		}
+		__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_result, uint32_t columns)
+		{
+			asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_result)), "r"(columns) : "memory");
+		}
+		__device__ __forceinline__ void tmem_relinquish_pair()
+		{
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+		}
+		__device__ __forceinline__ void tmem_dealloc_pair(uint32_t tmem_addr, uint32_t columns)
+		{
+			asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_addr), "r"(columns) : "memory");
+		}
+		__device__ __forceinline__ void mma_pair_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+		{
+			asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+					:: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)) : "memory");
+		}
+		// arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once the issued MMAs have completed
+		__device__ __forceinline__ void mma_pair_commit(uint64_t *bar, uint16_t cta_mask)
+		{
+			asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+					:: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+		}
+		// arrive (release, cluster scope) on the mbarrier that sits at the same offset as `bar` in CTA `target_rank` of the cluster
+		__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t target_rank)
+		{
+			asm volatile("{\n\t.reg .b32 raddr;\n\tmapa.shared::cluster.u32 raddr, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t}"
+					:: "r"(smem_u32(bar)), "r"(target_rank) : "memory");
+		}
+		// wait with cluster-scope acquire: pairs with remote arrivals from the peer CTA
+		__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+		{
+			uint32_t ok = 0;
+			while (not ok)
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+						: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 		}
 	}
 }
