@@ -91,6 +91,12 @@ namespace agb
 			const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
 			return *reinterpret_cast<const uint32_t*>(&v);
 		}
+		__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
+		{ // cvt.rn.relu.bf16x2.f32: max(x, 0) folded into the rounding conversion
+			uint32_t r;
+			asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+			return r;
+		}
 		__device__ __forceinline__ void unpack_bf16(uint32_t w, float &lo, float &hi)
 		{
 			lo = __uint_as_float(w << 16);
@@ -180,7 +186,7 @@ namespace agb
 					mbar_init(&peer_full[s], 1);
 				}
 				mbar_init(acc_full, 1);
-				mbar_init(img_ready, 2 * kEpilogueThreads); // both CTAs' epilogue threads arrive on the leader's barrier
+				mbar_init(img_ready, 2 * (kEpilogueThreads / 32)); // one arrival per epilogue warp of both CTAs, on the leader's barrier
 				fence_mbar_init();
 			}
 			if (warp == 1)
@@ -362,10 +368,14 @@ namespace agb
 					}
 					fence_proxy_async();
 					tc_fence_before();
-					if (rank == 0)
-						mbar_arrive(img_ready);
-					else
-						mbar_arrive_remote(img_ready, 0);
+					__syncwarp(); // the lane that arrives publishes the whole warp's writes
+					if (lane == 0)
+					{
+						if (rank == 0)
+							mbar_arrive(img_ready);
+						else
+							mbar_arrive_remote(img_ready, 0);
+					}
 
 					for (int l = 0; l < prm.n_layers; l++)
 					{
@@ -448,14 +458,11 @@ namespace agb
 								}
 								else
 								{
-#pragma unroll
-									for (int j = 0; j < 16; j++)
-										a[j] = fmaxf(a[j], 0.0f);
 									if (L.mode == MODE_POLICY)
 									{
 #pragma unroll
 										for (int j = 0; j < 16; j++)
-											head[tile][0] += a[j] * __ldg(prm.policy_w1 + c0 + j);
+											head[tile][0] += fmaxf(a[j], 0.0f) * __ldg(prm.policy_w1 + c0 + j);
 									}
 									else if (valid)
 									{
@@ -463,10 +470,10 @@ namespace agb
 										for (int h8 = 0; h8 < 2; h8++)
 										{
 											uint4 o;
-											o.x = pack_bf16(a[8 * h8 + 0], a[8 * h8 + 1]);
-											o.y = pack_bf16(a[8 * h8 + 2], a[8 * h8 + 3]);
-											o.z = pack_bf16(a[8 * h8 + 4], a[8 * h8 + 5]);
-											o.w = pack_bf16(a[8 * h8 + 6], a[8 * h8 + 7]);
+											o.x = pack_bf16_relu(a[8 * h8 + 0], a[8 * h8 + 1]);
+											o.y = pack_bf16_relu(a[8 * h8 + 2], a[8 * h8 + 3]);
+											o.z = pack_bf16_relu(a[8 * h8 + 4], a[8 * h8 + 5]);
+											o.w = pack_bf16_relu(a[8 * h8 + 6], a[8 * h8 + 7]);
 											*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
 										}
 									}
@@ -569,10 +576,14 @@ namespace agb
 						if (l + 1 < prm.n_layers)
 						{ // hand the image (and the drained accumulators) to the MMA warp
 							fence_proxy_async();
-							if (rank == 0)
-								mbar_arrive(img_ready);
-							else
-								mbar_arrive_remote(img_ready, 0);
+							__syncwarp();
+							if (lane == 0)
+							{
+								if (rank == 0)
+									mbar_arrive(img_ready);
+								else
+									mbar_arrive_remote(img_ready, 0);
+							}
 						}
 					}
 				}
