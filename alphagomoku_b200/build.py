@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
-SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu"]
+SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-rdc=false",

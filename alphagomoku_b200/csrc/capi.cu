@@ -117,6 +117,9 @@ extern "C"
 		int rc = agb::build_tables(e);
 		if (rc != AGB_OK)
 			return bail(rc);
+		rc = agb::solver_create(e);
+		if (rc != AGB_OK)
+			return bail(rc);
 		if (config->blocks > 0)
 		{
 			rc = agb::net_create(e);
@@ -142,7 +145,7 @@ extern "C"
 		agb::net_destroy(e);
 		agb::BoardStore &s = e->store;
 		void *ptrs[] = { s.board, s.sign_to_move, s.lines, s.ptypes, s.threats, s.forbidden, s.hist_count, s.hist_cells, e->d_features, e->d_features2,
-				e->d_io8, e->d_io8b, e->d_io16, e->d_status, e->d_pattern, e->d_threat };
+				e->d_io8, e->d_io8b, e->d_io16, e->d_status, e->d_pattern, e->d_threat, e->d_def_table };
 		for (void *p : ptrs)
 			if (p)
 				cudaFree(p);

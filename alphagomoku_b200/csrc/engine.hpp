@@ -25,6 +25,7 @@ struct AgbEngine
 		// static tables
 		uint8_t *d_pattern = nullptr; // [1<<20]
 		uint8_t *d_threat = nullptr; // [4096]
+		uint16_t *d_def_table = nullptr; // [15][256][2] defensive move masks (solver_logic.cuh)
 		agb::Tables tables { };
 
 		// pattern store
@@ -48,6 +49,19 @@ struct AgbEngine
 
 namespace agb
 {
+	// per-slot outputs of the static solver (K5)
+	struct SolverOutputs
+	{
+			uint16_t *moves; // [slots][pitch] Move::toShort, in action-list order
+			uint16_t *scores; // [slots][pitch]
+			int32_t *n_actions;
+			uint16_t *score; // position score
+			uint8_t *must_defend;
+			int pitch;
+	};
+	// solver.cu
+	int solver_create(AgbEngine *e);
+	int launch_solve_static(AgbEngine *e, const int *n_dev, int max_n, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count);
 	// tables.cu
 	int build_tables(AgbEngine *e);
 	// patterns.cu

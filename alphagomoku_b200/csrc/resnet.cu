@@ -64,6 +64,7 @@ namespace agb
 			float *q; // [n][S*S][3] or null
 			int n_boards;
 			const int *n_boards_dev; // if set, the batch size is read from device memory
+			const int *gather; // if set, board i of this launch lives in slot gather[i] of the feature / output arrays
 			long long *trace; // optional [n_layers][4] clock64 stamps of CTA 0's first board (AGB_NET_TRACE)
 	};
 
@@ -343,8 +344,9 @@ namespace agb
 				uint32_t acc_phase = 0;
 				for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
 				{
-					const int b = b0 + rank; // this CTA's board
-					const bool live = b < n_boards; // an odd batch leaves the last peer without a board: it still runs every barrier
+					const int bi = b0 + rank; // this CTA's board in the launch
+					const bool live = bi < n_boards;
+					const int b = (live and prm.gather != nullptr) ? prm.gather[bi] : bi; // its slot in the feature / output arrays // an odd batch leaves the last peer without a board: it still runs every barrier
 					// ---- prologue: feature words -> bf16 stem image (32 channels, halo 2) in the h buffer ----
 					for (uint32_t i = et; i < 4 * in_chunk_bytes / 16; i += kEpilogueThreads)
 						reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
@@ -389,7 +391,7 @@ namespace agb
 						mbar_wait_backoff(acc_full, acc_phase & 1, 32);
 						acc_phase++;
 						tc_fence_after();
-						if (prm.trace and b == 0 and et == 0)
+						if (prm.trace and bi == 0 and et == 0)
 							prm.trace[6 * l + 2] = clock64();
 						if (L.mode == MODE_STEM)
 						{ // the stem image is dead now: give the h buffer its zero halo back
@@ -571,7 +573,7 @@ namespace agb
 									*reinterpret_cast<float4*>(prm.value_hidden + (static_cast<size_t>(b) * cells + cell) * 4) = o;
 							}
 						}
-						if (prm.trace and b == 0 and et == 0)
+						if (prm.trace and bi == 0 and et == 0)
 							prm.trace[6 * l + 3] = clock64();
 						if (l + 1 < prm.n_layers)
 						{ // hand the image (and the drained accumulators) to the MMA warp
@@ -598,14 +600,16 @@ namespace agb
 		// ---- value head: dense(4*cells -> D) + ReLU, dense(D -> 3), softmax (createValueHead, blocks.cpp:112-117) --------
 		// one CTA per board, D threads; 0.02 % of the network's FLOPs
 		__global__ void value_head_kernel(const float *__restrict__ hidden, const float *__restrict__ wd1, const float *__restrict__ bd1,
-				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D, const int *__restrict__ n_dev)
+				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D, const int *__restrict__ n_dev,
+				const int *__restrict__ gather)
 		{
 			if (n_dev != nullptr)
 				n = *n_dev;
 			extern __shared__ float sh[]; // [in_dim] + [D]
 			float *sx = sh, *sd = sh + in_dim;
-			for (int b = blockIdx.x; b < n; b += gridDim.x)
+			for (int bi = blockIdx.x; bi < n; bi += gridDim.x)
 			{
+				const int b = gather ? gather[bi] : bi;
 				for (int i = threadIdx.x; i < in_dim; i += blockDim.x)
 					sx[i] = hidden[static_cast<size_t>(b) * in_dim + i];
 				__syncthreads();
@@ -820,7 +824,8 @@ namespace agb
 		return AGB_OK;
 	}
 
-	int net_forward_impl(AgbEngine *e, const uint32_t *features_dev, int n_boards, const int *n_dev, float *policy_dev, float *value_dev, float *q_dev)
+	int net_forward_impl(AgbEngine *e, const uint32_t *features_dev, int n_boards, const int *n_dev, const int *gather_dev, float *policy_dev, float *value_dev,
+			float *q_dev)
 	{
 		NetWeights *n = e->net;
 		if (n == nullptr or not n->loaded)
@@ -831,6 +836,7 @@ namespace agb
 		p.q = e->cfg.q_head ? q_dev : nullptr;
 		p.n_boards = n_boards;
 		p.n_boards_dev = n_dev;
+		p.gather = gather_dev;
 		static long long *d_trace = nullptr;
 		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
 		if (trace and d_trace == nullptr)
@@ -862,7 +868,7 @@ namespace agb
 		}
 		const int cells = e->cells, D = n->dense_width;
 		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, e->stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
-				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev);
+				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev, gather_dev);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
@@ -873,12 +879,12 @@ namespace agb
 {
 	int net_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n_boards, float *policy_dev, float *value_dev, float *q_dev)
 	{
-		return net_forward_impl(e, features_dev, n_boards, nullptr, policy_dev, value_dev, q_dev);
+		return net_forward_impl(e, features_dev, n_boards, nullptr, nullptr, policy_dev, value_dev, q_dev);
 	}
-	int net_forward_dev_counted(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, int max_boards, float *policy_dev, float *value_dev,
-			float *q_dev)
+	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
+			float *value_dev, float *q_dev)
 	{
-		return net_forward_impl(e, features_dev, max_boards, count_dev, policy_dev, value_dev, q_dev);
+		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev);
 	}
 }
 

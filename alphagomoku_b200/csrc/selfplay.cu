@@ -109,7 +109,7 @@ namespace agb
 			int8_t stm;
 			uint8_t stored; // task is part of the batch
 			uint8_t proven_edge; // reached a proven edge: no solver / NN / edge generation
-			uint8_t pad;
+			uint8_t sticky; // solver flags of this task slot; never cleared, like the reference's reused SearchTask (bit0 static, bit1 recursive)
 			float win, draw, moves_left;
 			uint16_t score;
 			uint16_t pad2;
@@ -143,7 +143,10 @@ namespace agb
 			// evaluation batch
 			int8_t *task_boards = nullptr; // [games*batch][cells] compact (K1 input)
 			int8_t *task_stm = nullptr;
-			int32_t *eval_count = nullptr; // device counter
+			int32_t *eval_count = nullptr; // device counter: slots of the current batch (all leaf positions)
+			uint8_t *slot_is_root = nullptr; // [games*batch]
+			int32_t *nn_list = nullptr, *nn_count = nullptr; // slots that go to the network when the solver is on
+			SolverOutputs solver_out { };
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
 			uint64_t *zobrist = nullptr; // [cells][2] + [2]
@@ -181,6 +184,7 @@ namespace agb
 				int max_simulations, init_to;
 				float exploration_constant, leak_threshold;
 				int q_head;
+				int solver_mode; // 0: terminal checks in K7, 1: K5 static solver on every leaf
 				Tables tables;
 				BoardStore store;
 				uint32_t *status;
@@ -507,6 +511,7 @@ namespace agb
 					slot = atomicAdd(p.s.eval_count, 1);
 					task.nn_slot = slot;
 					p.s.task_stm[slot] = task.stm;
+					p.s.slot_is_root[slot] = (task.path_len == 0) ? 1 : 0;
 				}
 				slot = __shfl_sync(kFullMask, slot, 0);
 				for (int i = lane; i < cells; i += 32)
@@ -558,7 +563,7 @@ namespace agb
 				const int stm = task.stm;
 				const size_t cbase = static_cast<size_t>(slot) * kCellPitch;
 				int n_nodes = p.s.n_nodes[g], n_edges = p.s.n_edges[g];
-				if (lane == 0)
+				if (lane == 0 and p.solver_mode == 0)
 				{ // NNEvaluator::unpack_from_network: value always, moves left only if the score is unproven
 					task.win = p.s.value[slot * 3 + 0];
 					task.draw = p.s.value[slot * 3 + 1];
@@ -573,13 +578,18 @@ namespace agb
 					stones += (p.store.board[cbase + i] != NONE);
 				for (int o = 16; o > 0; o >>= 1)
 					stones += __shfl_xor_sync(kFullMask, stones, o);
-				const bool draw_now = (stones + 1) >= p.draw_after;
-				int count = 0, wins = 0, draws = 0, losses = 0;
+				int count = 0;
+				uint16_t tscore = score::kDefault;
+				bool must_defend = false;
 				if (n_edges + (cells - stones) > p.s.max_edges)
 				{
 					atomicOr(p.status, OVF_EDGES);
 					continue;
 				}
+				if (p.solver_mode == 0)
+				{
+				const bool draw_now = (stones + 1) >= p.draw_after;
+				int wins = 0, draws = 0, losses = 0;
 				for (int i0 = 0; i0 < cells; i0 += 32)
 				{
 					const int i = i0 + lane;
@@ -632,7 +642,6 @@ namespace agb
 				}
 				__syncwarp();
 				// position score from the terminal checks (EdgeGenerator.cpp:163-178)
-				uint16_t tscore = score::kDefault;
 				if (wins > 0)
 					tscore = score::make(score::WIN, -1);
 				else if (draws > 0)
@@ -644,6 +653,68 @@ namespace agb
 					task.score = tscore;
 					task.win = (score::pv(tscore) == score::WIN) ? 1.0f : 0.0f;
 					task.draw = (score::pv(tscore) == score::DRAW) ? 1.0f : 0.0f;
+				}
+				}
+				else
+				{ // processed by the solver (K5): AlphaBetaSearch::solve outputs (AlphaBetaSearch.cpp:114-135), then what the network
+				  // adds (NNEvaluator.cpp:263-286), then UnifiedGenerator::generate without terminal checks (EdgeGenerator.cpp:269-303)
+					tscore = p.s.solver_out.score[slot];
+					must_defend = p.s.solver_out.must_defend[slot] != 0;
+					count = p.s.solver_out.n_actions[slot];
+					const bool proven = score::is_proven(tscore);
+					const bool went_to_nn = (task.path_len == 0) or not proven;
+					if (lane == 0)
+					{
+						task.score = tscore;
+						if (proven)
+						{ // Score::convertToValue, distance as moves left
+							task.win = (score::pv(tscore) == score::WIN) ? 1.0f : 0.0f;
+							task.draw = (score::pv(tscore) == score::DRAW) ? 1.0f : 0.0f;
+							task.moves_left = static_cast<float>(score::distance(tscore));
+						}
+						if (went_to_nn)
+						{
+							task.win = p.s.value[slot * 3 + 0];
+							task.draw = p.s.value[slot * 3 + 1];
+							if (not proven)
+								task.moves_left = 0.0f;
+							atomicAdd(p.s.stats + ST_EVALS, 1ull);
+						}
+						task.sticky |= 1; // node_counter <= 1: statically solved
+						if (proven)
+							task.sticky |= 2; // (sic) a proven result is flagged as recursively solved
+					}
+					const uint16_t *am = p.s.solver_out.moves + static_cast<size_t>(slot) * p.s.solver_out.pitch;
+					const uint16_t *as = p.s.solver_out.scores + static_cast<size_t>(slot) * p.s.solver_out.pitch;
+					for (int i = lane; i < count; i += 32)
+					{
+						EdgeD e;
+						const uint16_t mv = am[i];
+						const int cell = ((mv >> 2) & 127) * S + ((mv >> 9) & 127);
+						e.move = mv;
+						e.score = as[i];
+						e.visits = 0;
+						e.vloss_flag = 0;
+						e.pad = 0;
+						e.prior = went_to_nn ? p.s.policy[static_cast<size_t>(slot) * cells + cell] : 0.0f;
+						e.win = 0.0f;
+						e.draw = 0.0f;
+						if (went_to_nn)
+						{ // the network's action values replace the solver's for the whole board (NNEvaluator.cpp:279)
+							if (p.q_head)
+							{
+								e.win = p.s.q[(static_cast<size_t>(slot) * cells + cell) * 3 + 0];
+								e.draw = p.s.q[(static_cast<size_t>(slot) * cells + cell) * 3 + 1];
+							}
+						}
+						else if (score::is_proven(e.score))
+						{
+							e.win = (score::pv(e.score) == score::WIN) ? 1.0f : 0.0f;
+							e.draw = (score::pv(e.score) == score::DRAW) ? 1.0f : 0.0f;
+						}
+						edges[n_edges + i] = e;
+					}
+					__syncwarp();
 				}
 				// prune_weak_moves (proven position, not the root): keep the best-scoring edges in their order
 				const bool is_root_task = (task.path_len == 0);
@@ -676,7 +747,7 @@ namespace agb
 					count = kept;
 				}
 				// renormalize_policy: sequential float sum in edge order (EdgeGenerator.cpp:23-40)
-				if (lane == 0)
+				if (lane == 0 and count > 0)
 				{
 					float sum = 0.0f;
 					for (int i = 0; i < count; i++)
@@ -696,6 +767,8 @@ namespace agb
 				}
 				__syncwarp();
 				// Tree::expand
+				if (count == 0)
+					continue; // ExpandOutcome::SKIPPED_EXPANSION
 				const int existing = table_seek(p, g, task.hash, task.bits, stm, lane);
 				if (existing < 0)
 				{
@@ -718,8 +791,10 @@ namespace agb
 					node.hash = task.hash;
 					node_update_value(node, task.win, task.draw);
 					node.moves_left += (task.moves_left - node.moves_left) / node.visits;
-					if (count + stones == cells)
+					if (must_defend or count + stones == cells)
 						node.flags |= 2; // fully expanded
+					if (p.solver_mode != 0)
+						node.flags |= static_cast<uint8_t>(((task.sticky & 3) << 2) | (must_defend ? 16 : 0)); // Node::setAdditionaFlags
 					if (is_root_task)
 						node.flags |= 1;
 					update_node_score(node, edges, lane);
@@ -901,7 +976,7 @@ namespace agb
 				{
 					const size_t base = static_cast<size_t>(g) * cells;
 					len += static_cast<int>(records::serialize_sample_v201(rec + len, cells, p.s.root_board + base, p.s.sample_visits + base, p.s.sample_prior + base,
-							p.s.sample_win + base, p.s.sample_draw + base, p.s.sample_score + base, R.score, 0));
+							p.s.sample_win + base, p.s.sample_draw + base, p.s.sample_score + base, R.score, static_cast<uint16_t>((R.flags >> 2) & 7)));
 					p.s.rec_len[g] = len;
 					p.s.rec_samples[g] += 1;
 				}
@@ -1155,6 +1230,7 @@ namespace agb
 			p.exploration_constant = e->cfg.exploration_constant;
 			p.leak_threshold = e->cfg.information_leak_threshold;
 			p.q_head = e->cfg.q_head;
+			p.solver_mode = e->cfg.solver_max_positions > 0 ? 1 : 0;
 			p.tables = e->tables;
 			p.store = e->store;
 			p.status = e->d_status;
@@ -1162,14 +1238,18 @@ namespace agb
 		}
 	}
 
-	int net_forward_dev_counted(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, int max_boards, float *policy_dev, float *value_dev,
-			float *q_dev);
+	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
+			float *value_dev, float *q_dev);
 
 	int selfplay_create(AgbEngine *e)
 	{
 		const AgbConfig &c = e->cfg;
 		if (c.blocks <= 0)
 			return e->fail(AGB_EINVAL, "self-play needs a network (blocks > 0)");
+		if (c.max_children > 0 and c.max_children < e->cells)
+			return e->fail(AGB_EINVAL, "max_children below the board size (policy pruning of unproven positions) is not on the device yet: use 0 (unlimited, the reference default)");
+		if (c.solver_max_positions > 1)
+			return e->fail(AGB_EINVAL, "solver_max_positions > 1 (recursive alpha-beta with the 4 Mi-entry table) is not on the device yet: use 0 (off) or 1 (static solver)");
 		if (c.max_batch_size <= 0 or c.games * c.max_batch_size > c.max_boards)
 			return e->fail(AGB_EINVAL, "games * max_batch_size must fit in max_boards");
 		SelfplayState *s = new SelfplayState();
@@ -1210,6 +1290,15 @@ namespace agb
 		alloc(&s->task_boards, T * cells);
 		alloc(&s->task_stm, T);
 		alloc(&s->eval_count, 1);
+		alloc(&s->slot_is_root, T);
+		alloc(&s->nn_list, T);
+		alloc(&s->nn_count, 1);
+		s->solver_out.pitch = static_cast<int>(cells);
+		alloc(&s->solver_out.moves, T * cells);
+		alloc(&s->solver_out.scores, T * cells);
+		alloc(&s->solver_out.n_actions, T);
+		alloc(&s->solver_out.score, T);
+		alloc(&s->solver_out.must_defend, T);
 		alloc(&s->features, T * cells);
 		alloc(&s->policy, T * cells);
 		alloc(&s->value, T * 3);
@@ -1231,6 +1320,8 @@ namespace agb
 		alloc(&s->fin_used, 1);
 		alloc(&s->fin_games, 1);
 		alloc(&s->sample_root, G * 4);
+		if (ok)
+			ok = cudaMemset(s->tasks, 0, T * sizeof(TaskD)) == cudaSuccess; // sticky per-slot flags start cleared
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
 		std::vector<uint64_t> keys(cells * 2 + 2);
@@ -1253,7 +1344,8 @@ namespace agb
 		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
 				s->value, s->q, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
-				s->sample_root, s->sample_draw, s->sample_score, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
+				s->sample_root, s->sample_draw, s->sample_score, s->slot_is_root, s->nn_list, s->nn_count, s->solver_out.moves, s->solver_out.scores,
+				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
 			if (ptr)
 				cudaFree(ptr);
@@ -1332,7 +1424,15 @@ extern "C"
 			if (rc != AGB_OK)
 				return rc;
 			AGB_CUDA_CHECK(e, cudaEventRecord(e->events[2 * step], e->stream));
-			rc = net_forward_dev_counted(e, s->features, s->eval_count, max_tasks, s->policy, s->value, s->q);
+			if (p.solver_mode != 0)
+			{ // K5 on every leaf; only unproven positions (and roots) go on to the network
+				AGB_CUDA_CHECK(e, cudaMemsetAsync(s->nn_count, 0, sizeof(int32_t), e->stream));
+				rc = launch_solve_static(e, s->eval_count, max_tasks, s->solver_out, s->slot_is_root, s->nn_list, s->nn_count);
+				if (rc != AGB_OK)
+					return rc;
+			}
+			rc = net_forward_dev_gather(e, s->features, p.solver_mode != 0 ? s->nn_count : s->eval_count, p.solver_mode != 0 ? s->nn_list : nullptr, max_tasks,
+					s->policy, s->value, s->q);
 			if (rc != AGB_OK)
 				return rc;
 			AGB_CUDA_CHECK(e, cudaEventRecord(e->events[2 * step + 1], e->stream));
@@ -1431,7 +1531,15 @@ extern "C"
 		if (root_visits)
 			*root_visits = 0;
 		if (root < 0)
+		{ // no root yet: a default-constructed Node (Node.hpp), i.e. Value() whose loss rate is 1
+			if (root_value3_host)
+			{
+				root_value3_host[0] = 0.0f;
+				root_value3_host[1] = 0.0f;
+				root_value3_host[2] = 1.0f;
+			}
 			return AGB_OK;
+		}
 		NodeD node;
 		AGB_CUDA_CHECK(e, cudaMemcpy(&node, s->nodes + static_cast<size_t>(game) * s->max_nodes + root, sizeof(NodeD), cudaMemcpyDeviceToHost));
 		std::vector<EdgeD> edges(node.n_edges);

@@ -15,6 +15,7 @@
 #include <alphagomoku/search/monte_carlo/NNEvaluator.hpp>
 #include <alphagomoku/search/monte_carlo/Search.hpp>
 #include <alphagomoku/search/monte_carlo/Tree.hpp>
+#include <alphagomoku/search/alpha_beta/AlphaBetaSearch.hpp>
 #include <alphagomoku/selfplay/NetworkLoader.hpp>
 #include <alphagomoku/utils/configs.hpp>
 #include <alphagomoku/utils/misc.hpp>
@@ -284,5 +285,42 @@ extern "C"
 			outcomes[i] = static_cast<int32_t>(buffer.getGameData(i).getOutcome());
 		}
 		return buffer.numberOfGames();
+	}
+	// AlphaBetaSearch::solve (AlphaBetaSearch.cpp:77-156) on one position with a node limit; outputs the task's edge list (in
+	// order), their scores, the position score and flags (bit0 must_defend, bit1 statically solved, bit2 recursively solved)
+	int agref_solve(int rules, int rows, int cols, int draw_after, const int8_t *board, int sign_to_move, int max_nodes, uint16_t *moves,
+			uint16_t *scores, uint16_t *result_score, int32_t *flags)
+	{
+		static std::unique_ptr<AlphaBetaSearch> solver;
+		static GameConfig solver_config;
+		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
+		if (draw_after > 0)
+			gc.draw_after = draw_after;
+		if (solver == nullptr or solver_config.rules != gc.rules or solver_config.rows != gc.rows or solver_config.draw_after != gc.draw_after)
+		{
+			solver = std::make_unique<AlphaBetaSearch>(gc);
+			solver_config = gc;
+		}
+		matrix<Sign> b(rows, cols);
+		for (int i = 0; i < rows * cols; i++)
+			b[i] = static_cast<Sign>(board[i]);
+		SearchTask task(gc);
+		task.set(b, static_cast<Sign>(sign_to_move));
+		solver->clear();
+		solver->setDepthLimit(100);
+		solver->setNodeLimit(max_nodes);
+		solver->setTimeLimit(1.0e30);
+		solver->solve(task);
+		int n = 0;
+		for (const Edge &e : task.getEdges())
+		{
+			const Move m = e.getMove();
+			moves[n] = m.toShort();
+			scores[n] = Score::to_short(task.getActionScores().at(m.row, m.col));
+			n++;
+		}
+		*result_score = Score::to_short(task.getScore());
+		*flags = static_cast<int>(task.mustDefend()) | (static_cast<int>(task.wasStaticallySolved()) << 1) | (static_cast<int>(task.wasRecursivelySolved()) << 2);
+		return n;
 	}
 }

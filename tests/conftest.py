@@ -27,6 +27,18 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def ref_fast(ref):
+    """The same reference sources with the reference's Release flags (-O3 -DNDEBUG): for inputs on which its debug asserts abort."""
+    import refapi
+    if not os.path.exists(refapi.REF_LIB_FAST):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", os.path.join(ROOT, "oracle", "_ref", "libagref_fast.so")])
+        else:
+            pytest.skip("oracle/_ref/libagref_fast.so not built and /root/reference absent")
+    return refapi.RefOracle(fast=True)
+
+
+@pytest.fixture(scope="session")
 def hostsim(tmp_path_factory):
     """Host-compiled kernel logic (tests/hostsim): the per-cell device functions run on the CPU for logic checks."""
     import ctypes

@@ -97,3 +97,62 @@ extern "C" size_t hostsim_serialize_sample_v201(int cells, const int8_t *board, 
 {
 	return agb::records::serialize_sample_v201(out, cells, board, visits, prior, win, draw, scores, minimax_score, flags);
 }
+
+#include "../../alphagomoku_b200/csrc/solver_logic.cuh"
+// sequential model of "K1 state -> K5 static solve" for one position (the device runs the same functions, one thread per task)
+extern "C" void hostsim_defensive_table(int rules, uint16_t *table)
+{
+	agb::solver::build::defensive_table(rules, table);
+}
+extern "C" uint32_t hostsim_defensive_mask(const uint16_t *table, int rules, uint32_t window13, int defender, int threat)
+{
+	return agb::solver::defensive_mask(table, rules, window13, defender, threat);
+}
+extern "C" int hostsim_solve_static(int rules, int S, int draw_after, const int8_t *board, int stm, const uint8_t *pattern_table, const uint8_t *threat_table,
+		const uint16_t *def_table, uint16_t *moves, uint16_t *scores, uint16_t *result_score, int32_t *flags)
+{
+	using namespace agb::solver;
+	const int cells = S * S;
+	uint64_t lines[kMaxLines];
+	for (int l = 0; l < line_count(S); l++)
+		lines[l] = build_line(board, S, l);
+	std::vector<uint32_t> ptypes(cells, 0);
+	std::vector<uint8_t> threats(cells, 0), forbidden(cells, 0);
+	std::vector<int32_t> hist_count(2 * kHistTypes, 0);
+	std::vector<uint16_t> hist_cells(2 * kHistTypes * cells, 0);
+	Tables tables { pattern_table, threat_table };
+	int stones = 0;
+	for (int r = 0; r < S; r++)
+		for (int c = 0; c < S; c++)
+		{
+			const int idx = r * S + c;
+			stones += (board[idx] != NONE);
+			if (board[idx] != NONE)
+				continue;
+			ptypes[idx] = classify_cell(lines, pattern_table, r, c, S);
+			threats[idx] = threat_of_cell(ptypes[idx], threat_table);
+			for (int colour = 0; colour < 2; colour++)
+			{
+				const int t = (threats[idx] >> (4 * colour)) & 15;
+				if (t != TT_NONE)
+					hist_cells[(colour * kHistTypes + t) * cells + hist_count[colour * kHistTypes + t]++] = mk_loc(r, c);
+			}
+			if (rules == RULE_RENJU)
+			{
+				const int tc = threats[idx] & 15;
+				if (tc == TT_OVERLINE or tc == TT_FORK_4x4)
+					forbidden[idx] = 1;
+				else if (tc == TT_FORK_3x3)
+				{
+					Overlay ov;
+					forbidden[idx] = is_forbidden_raw(board, S, r, c, tables, ov);
+				}
+			}
+		}
+	View v { S, cells, rules, stm, stones, draw_after > 0 ? draw_after : cells, cells, board, lines, ptypes.data(), threats.data(), forbidden.data(),
+			hist_count.data(), hist_cells.data(), pattern_table, def_table };
+	const Result res = solve_static(v, moves, scores);
+	*result_score = res.score;
+	*flags = static_cast<int>(res.must_defend) | (static_cast<int>(res.has_initiative) << 3);
+	return res.n_actions;
+}

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, random_boards
+from refapi import _p
 
 P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
 
@@ -217,3 +218,83 @@ def test_game_data_buffer_file_loads_in_the_reference(ref, tmp_path):
     assert n == 3 and (rows.value, cols.value, rules.value) == (15, 15, 1)
     assert spg[:3].tolist() == [1, 2, 3] and mpg[:3].tolist() == [2, 2, 2] and out[:3].tolist() == [2, 2, 2]
     assert dataset.parse_record(games[2])["samples"][1]["move_number"] == 1
+
+
+# ---- K5: static solver (MoveGenerator in OPTIMAL mode + static evaluation) ------------------------------------------------------
+def _solver_tables(hostsim, rules):
+    pattern = np.zeros(1 << 20, np.uint8)
+    threat = np.zeros(4096, np.uint8)
+    deftab = np.zeros(15 * 256 * 2, np.uint16)
+    hostsim.hostsim_pattern_table(rules, _p(pattern))
+    hostsim.hostsim_threat_table(rules, _p(threat))
+    hostsim.hostsim_defensive_table(rules, _p(deftab))
+    return pattern, threat, deftab
+
+
+def _solve_both(ref, hostsim, tables, rules, size, board, stm, draw_after=0):
+    cells = size * size
+    out = []
+    for which in range(2):
+        moves, scores = np.zeros(cells, np.uint16), np.zeros(cells, np.uint16)
+        result, flags = np.zeros(1, np.uint16), np.zeros(1, np.int32)
+        if which == 0:
+            n = ref.lib.agref_solve(rules, size, size, draw_after, _p(board), int(stm), 1, _p(moves), _p(scores), _p(result), _p(flags))
+        else:
+            n = hostsim.hostsim_solve_static(rules, size, draw_after, _p(board), int(stm), _p(tables[0]), _p(tables[1]), _p(tables[2]), _p(moves),
+                                             _p(scores), _p(result), _p(flags))
+        out.append((moves[:n].copy(), scores[:n].copy(), int(result[0]), int(flags[0]) & 1))
+    return out
+
+
+@pytest.mark.parametrize("rules", [0, 1, 2, 3, 4])
+def test_defensive_move_table_matches_reference(ref, hostsim, rules):
+    """DefensiveMoveTable::getMoves (DefensiveMoveTable.cpp:393-477) against solver_logic.cuh's table + lookup on random 13-cell
+    windows whose centre is empty, for every threat type the table serves."""
+    rng = np.random.default_rng(900 + rules)
+    _, _, deftab = _solver_tables(hostsim, rules)
+    hostsim.hostsim_defensive_mask.restype = ctypes.c_uint32
+    ref.lib.agref_defensive_moves.restype = ctypes.c_uint16
+    checked = 0
+    for _ in range(6000):
+        cellsv = rng.choice(4, size=13, p=[0.45, 0.25, 0.25, 0.05])
+        cellsv[6] = 0
+        window = int(sum(int(v) << (2 * i) for i, v in enumerate(cellsv)))
+        for defender in (1, 2):
+            for threat in (3, 4, 5, 6, 7):  # OPEN_3, HALF_OPEN_4, OPEN_4, DOUBLE_4, FIVE
+                a = ref.lib.agref_defensive_moves(rules, window, defender, threat)
+                b = hostsim.hostsim_defensive_mask(_p(deftab), rules, window, defender, threat)
+                assert a == b, (rules, hex(window), defender, threat, bin(a), bin(b))
+                checked += 1
+    assert checked == 60000
+
+
+@pytest.mark.parametrize("rules,size", [(0, 15), (1, 15), (3, 20), (4, 15), (0, 12)])
+def test_static_solver_matches_reference(ref, hostsim, rules, size):
+    """AlphaBetaSearch::solve with a node limit of 1 (AlphaBetaSearch.cpp:77-156 -> MoveGenerator.cpp, static evaluation) against the
+    host-compiled K5 logic: same action list in the same order, same action scores, same position score and must-defend flag."""
+    rng = np.random.default_rng(1000 + 10 * rules + size)
+    tables = _solver_tables(hostsim, rules)
+    boards = random_boards(rng, size, 300, max_fill=0.5)
+    for i, board in enumerate(boards):
+        stm = 1 if (np.count_nonzero(board) % 2 == 0) else 2
+        if i % 5 == 0:
+            stm = 3 - stm
+        a, b = _solve_both(ref, hostsim, tables, rules, size, board, stm)
+        assert np.array_equal(a[0], b[0]), (i, a[0], b[0])
+        assert np.array_equal(a[1], b[1]), i
+        assert a[2:] == b[2:], (i, a[2:], b[2:])
+
+
+def test_static_solver_renju_matches_reference_up_to_order(ref_fast, hostsim):
+    """RENJU: the reference's isForbidden() re-runs add/undo on its calculator and so reorders its threat lists mid-generation; the device
+    lists keep K1's order. Scores, flags and the SET of (move, score) must still agree. Uses the reference's Release build: on random
+    (unreachable) positions its debug build aborts in MoveGenerator.cpp:999."""
+    ref = ref_fast
+    rng = np.random.default_rng(1234)
+    tables = _solver_tables(hostsim, 2)
+    boards = random_boards(rng, 15, 300, max_fill=0.5)
+    for i, board in enumerate(boards):
+        stm = 1 if (np.count_nonzero(board) % 2 == 0) else 2
+        a, b = _solve_both(ref, hostsim, tables, 2, 15, board, stm)
+        assert a[2:] == b[2:], (i, a[2:], b[2:])
+        assert sorted(zip(a[0].tolist(), a[1].tolist())) == sorted(zip(b[0].tolist(), b[1].tolist())), i

@@ -28,17 +28,20 @@ def _openings(rng, size, n):
     return boards, stm
 
 
-@pytest.mark.parametrize("rules,q_head,init_to,batch,sims", [(0, False, "parent", 4, 60), (1, True, "q_head", 8, 80), (2, False, "parent", 3, 50),
-                                                          (0, False, "loss", 1, 55)])
-def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, batch, sims):
+@pytest.mark.parametrize("rules,q_head,init_to,batch,sims,solver", [
+    (0, False, "parent", 4, 60, 0), (1, True, "q_head", 8, 80, 0), (2, False, "parent", 3, 50, 0), (0, False, "loss", 1, 55, 0),
+    # K5 on: Search::solve with tss max_positions = 1 (static solver) on every leaf, proven leaves skip the network
+    (0, False, "parent", 4, 60, 1), (1, True, "q_head", 8, 80, 1), (4, False, "parent", 5, 70, 1), (3, True, "q_head", 2, 55, 1)])
+def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, batch, sims, solver):
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import refapi
     size, games = 15, 6
     blocks, filters = 2, 64
-    draw_after = 14  # short games, so that game ends, restarts and finished-game records are exercised too
+    # short games, so that game ends, restarts and finished-game records are exercised too (longer with the solver, so that real threats appear)
+    draw_after = 14 if solver == 0 else 28
     eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
-                     games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024)
+                     games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
     def evaluate(features):
@@ -49,13 +52,14 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
     eng.selfplay_reset(boards, stm)
     refs = []
     for g in range(games):
-        r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=False, draw_after=draw_after)
+        r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=solver > 0,
+                                solver_max_positions=max(solver, 1), draw_after=draw_after)
         r.set_position(boards[g], stm[g])
         refs.append(r)
     active = [True] * games
     moves_checked = 0
     ref_records = []
-    for step in range(400):
+    for step in range(400 if solver == 0 else 1200):
         eng.step(1)
         for g in range(games):
             if not active[g]:
