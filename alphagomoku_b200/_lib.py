@@ -19,7 +19,8 @@ class AgbConfig(ctypes.Structure):
         ("exploration_constant", ctypes.c_float), ("information_leak_threshold", ctypes.c_float),
         ("policy_expansion_threshold", ctypes.c_float), ("max_children", ctypes.c_int32),
         ("solver_max_positions", ctypes.c_int32), ("use_symmetries", ctypes.c_int32),
-        ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("reserved", ctypes.c_int32 * 7),
+        ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("solver_table_entries", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 6),
     ]
 
 
@@ -57,6 +58,7 @@ SYMBOLS = {
     "agb_forward_dev": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "agb_evaluate": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "agb_selfplay_reset": (_I, [_VP, _VP, _VP]),
+    "agb_set_solver_keys": (_I, [_VP, _VP, ctypes.c_size_t]),
     "agb_step": (_I, [_VP, _I]),
     "agb_pop_finished": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I)]),
     "agb_get_stats": (_I, [_VP, ctypes.POINTER(AgbStats)]),

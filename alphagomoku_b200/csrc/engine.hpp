@@ -49,7 +49,7 @@ struct AgbEngine
 
 namespace agb
 {
-	// per-slot outputs of the static solver (K5)
+	// per-slot outputs of the solver (K5)
 	struct SolverOutputs
 	{
 			uint16_t *moves; // [slots][pitch] Move::toShort, in action-list order
@@ -57,11 +57,32 @@ namespace agb
 			int32_t *n_actions;
 			uint16_t *score; // position score
 			uint8_t *must_defend;
+			int32_t *nodes; // positions visited by the search (1: solved statically)
 			int pitch;
+	};
+	// per-game memory of the solver: transposition table, action stack, frames, and the slots of the current batch in task order
+	struct SolverState
+	{
+			static constexpr int kFrameBytes = 24;
+			int games = 0, batch = 0;
+			size_t table_entries = 0; // per game, power of two
+			uint64_t *table = nullptr; // [games][table_entries][2]
+			uint64_t *keys = nullptr; // [key sets][2 * cells][2] Zobrist words (low, high) per (cell, colour)
+			size_t keys_stride = 0; // words between the key sets of consecutive games (0: all games share one set)
+			int32_t *generation = nullptr; // [games] SharedHashTable::m_base_generation
+			int32_t *game_slots = nullptr; // [games][batch]
+			int32_t *game_slot_count = nullptr; // [games]
+			uint16_t *stack_moves = nullptr, *stack_scores = nullptr; // [games][stack_capacity]
+			int stack_capacity = 0;
+			void *frames = nullptr; // [games][kMaxFrames] solver::Frame
+			const uint16_t *def_table = nullptr;
 	};
 	// solver.cu
 	int solver_create(AgbEngine *e);
-	int launch_solve_static(AgbEngine *e, const int *n_dev, int max_n, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count);
+	int solver_state_create(AgbEngine *e, int games, int batch, SolverState *st);
+	int solver_state_reset(AgbEngine *e, SolverState *st);
+	void solver_state_destroy(SolverState *st);
+	int launch_solve_games(AgbEngine *e, const SolverState &st, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count);
 	// tables.cu
 	int build_tables(AgbEngine *e);
 	// patterns.cu

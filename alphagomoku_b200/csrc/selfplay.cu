@@ -147,6 +147,7 @@ namespace agb
 			uint8_t *slot_is_root = nullptr; // [games*batch]
 			int32_t *nn_list = nullptr, *nn_count = nullptr; // slots that go to the network when the solver is on
 			SolverOutputs solver_out { };
+			SolverState solver { }; // per-game search memory (solver.cu)
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
 			uint64_t *zobrist = nullptr; // [cells][2] + [2]
@@ -500,6 +501,7 @@ namespace agb
 			if (lane == 0)
 				p.s.n_stored[g] = stored;
 			// evaluation batch: every stored task that is a root or not proven goes to the network (Search::scheduleToNN)
+			int n_slots = 0;
 			for (int t = 0; t < stored; t++)
 			{
 				TaskD &task = tasks[t];
@@ -512,7 +514,10 @@ namespace agb
 					task.nn_slot = slot;
 					p.s.task_stm[slot] = task.stm;
 					p.s.slot_is_root[slot] = (task.path_len == 0) ? 1 : 0;
+					if (p.solver_mode != 0)
+						p.s.solver.game_slots[static_cast<size_t>(g) * p.s.batch + n_slots] = slot; // the solver walks them in task order
 				}
+				n_slots++;
 				slot = __shfl_sync(kFullMask, slot, 0);
 				for (int i = lane; i < cells; i += 32)
 				{
@@ -520,6 +525,8 @@ namespace agb
 					p.s.task_boards[static_cast<size_t>(slot) * cells + i] = static_cast<int8_t>(((cross >> (i & 63)) & 1) | (((circle >> (i & 63)) & 1) << 1));
 				}
 			}
+			if (lane == 0 and p.solver_mode != 0)
+				p.s.solver.game_slot_count[g] = n_slots;
 		}
 
 		// ---- K7: edge generation + expand + backup ------------------------------------------------------------------------
@@ -680,7 +687,8 @@ namespace agb
 								task.moves_left = 0.0f;
 							atomicAdd(p.s.stats + ST_EVALS, 1ull);
 						}
-						task.sticky |= 1; // node_counter <= 1: statically solved
+						if (p.s.solver_out.nodes[slot] <= 1)
+							task.sticky |= 1; // node_counter <= 1: statically solved
 						if (proven)
 							task.sticky |= 2; // (sic) a proven result is flagged as recursively solved
 					}
@@ -1101,12 +1109,17 @@ namespace agb
 					p.s.n_edges[g] = 0;
 					p.s.rec_len[g] = 4;
 					p.s.rec_samples[g] = 0;
+					if (p.solver_mode != 0)
+						p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64;
 				}
 				int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
 				for (int i = lane; i < p.s.table_size; i += 32)
 					table[i] = -1;
 				return;
 			}
+			// prepare_search -> Search::setBoard: the solver's table enters a new generation
+			if (lane == 0 and p.solver_mode != 0)
+				p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64;
 			// prepare_search -> Tree::setBoard -> NodeCache::cleanup: keep every node whose position can still occur
 			const int n_nodes = p.s.n_nodes[g];
 			int32_t *remap = p.s.remap + static_cast<size_t>(g) * p.s.max_nodes;
@@ -1210,6 +1223,8 @@ namespace agb
 			p.s.outcome[g] = 0;
 			p.s.rec_len[g] = 4;
 			p.s.rec_samples[g] = 0;
+			if (p.solver_mode != 0)
+				p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64; // prepare_search -> Search::setBoard -> increaseGeneration
 		}
 
 		uint64_t splitmix64(uint64_t &x)
@@ -1248,8 +1263,6 @@ namespace agb
 			return e->fail(AGB_EINVAL, "self-play needs a network (blocks > 0)");
 		if (c.max_children > 0 and c.max_children < e->cells)
 			return e->fail(AGB_EINVAL, "max_children below the board size (policy pruning of unproven positions) is not on the device yet: use 0 (unlimited, the reference default)");
-		if (c.solver_max_positions > 1)
-			return e->fail(AGB_EINVAL, "solver_max_positions > 1 (recursive alpha-beta with the 4 Mi-entry table) is not on the device yet: use 0 (off) or 1 (static solver)");
 		if (c.max_batch_size <= 0 or c.games * c.max_batch_size > c.max_boards)
 			return e->fail(AGB_EINVAL, "games * max_batch_size must fit in max_boards");
 		SelfplayState *s = new SelfplayState();
@@ -1299,6 +1312,7 @@ namespace agb
 		alloc(&s->solver_out.n_actions, T);
 		alloc(&s->solver_out.score, T);
 		alloc(&s->solver_out.must_defend, T);
+		alloc(&s->solver_out.nodes, T);
 		alloc(&s->features, T * cells);
 		alloc(&s->policy, T * cells);
 		alloc(&s->value, T * 3);
@@ -1324,6 +1338,12 @@ namespace agb
 			ok = cudaMemset(s->tasks, 0, T * sizeof(TaskD)) == cudaSuccess; // sticky per-slot flags start cleared
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
+		if (c.solver_max_positions > 0)
+		{
+			const int rc = solver_state_create(e, c.games, c.max_batch_size, &s->solver);
+			if (rc != AGB_OK)
+				return rc;
+		}
 		std::vector<uint64_t> keys(cells * 2 + 2);
 		uint64_t seed = c.seed ^ 0xA5A5A5A55A5A5A5Aull;
 		for (auto &k : keys)
@@ -1345,10 +1365,11 @@ namespace agb
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
 				s->value, s->q, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
 				s->sample_root, s->sample_draw, s->sample_score, s->slot_is_root, s->nn_list, s->nn_count, s->solver_out.moves, s->solver_out.scores,
-				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
+				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->solver_out.nodes, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
 			if (ptr)
 				cudaFree(ptr);
+		solver_state_destroy(&s->solver);
 		delete s;
 		e->selfplay = nullptr;
 	}
@@ -1388,10 +1409,39 @@ extern "C"
 		}
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
+		if (e->cfg.solver_max_positions > 0)
+		{
+			const int rc = solver_state_reset(e, &s->solver);
+			if (rc != AGB_OK)
+				return rc;
+		}
 		const Params p = make_params(e);
 		reset_games_kernel<<<static_cast<unsigned>((G + 127) / 128), 128, 0, e->stream>>>(p);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		return AGB_OK;
+	}
+
+	int agb_set_solver_keys(AgbEngine *e, const uint64_t *keys_host, size_t n_words)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or s->solver.keys == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games or without the solver");
+		const size_t per_set = static_cast<size_t>(s->cells) * 4;
+		if (keys_host == nullptr or (n_words != per_set and n_words != per_set * s->games))
+			return e->fail(AGB_EINVAL, "expected 2 x 64-bit words for each of 2 * rows * cols (cell, colour) pairs, once or once per game");
+		if (n_words != per_set)
+		{ // one key set per game, like one AlphaBetaSearch per GameGenerator in the reference
+			uint64_t *fresh = nullptr;
+			AGB_CUDA_CHECK(e, cudaMalloc(&fresh, n_words * sizeof(uint64_t)));
+			cudaFree(s->solver.keys);
+			s->solver.keys = fresh;
+			s->solver.keys_stride = per_set;
+		}
+		else
+			s->solver.keys_stride = 0;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->solver.keys, keys_host, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		return AGB_OK;
 	}
@@ -1427,7 +1477,7 @@ extern "C"
 			if (p.solver_mode != 0)
 			{ // K5 on every leaf; only unproven positions (and roots) go on to the network
 				AGB_CUDA_CHECK(e, cudaMemsetAsync(s->nn_count, 0, sizeof(int32_t), e->stream));
-				rc = launch_solve_static(e, s->eval_count, max_tasks, s->solver_out, s->slot_is_root, s->nn_list, s->nn_count);
+				rc = launch_solve_games(e, s->solver, s->solver_out, s->slot_is_root, s->nn_list, s->nn_count);
 				if (rc != AGB_OK)
 					return rc;
 			}

@@ -1,9 +1,14 @@
-// K5, static layer: one thread per leaf position runs the reference's staged move generator + static evaluation on the K1
-// state of its slot (solver_logic.cuh), i.e. AlphaBetaSearch::solve with TSSConfig::max_positions = 1
-// (src/search/alpha_beta/AlphaBetaSearch.cpp:77-156). Positions that are not proven (or are tree roots) are appended to the
-// network batch (Search::scheduleToNN, src/search/monte_carlo/Search.cpp:184-198).
+// K5: the per-leaf solver of the lockstep engine. One warp owns one game and its lane 0 solves that game's leaf positions of
+// the current batch one after another, in task order, on top of the K1 state of their slots: staged move generation, static
+// evaluation and (max_positions > 1) the alpha-beta threat-space search with the game's transposition table
+// (solver_logic.cuh, solver_search.cuh). Replaces Search::solve -> AlphaBetaSearch::solve
+// (src/search/monte_carlo/Search.cpp:160-183, src/search/alpha_beta/AlphaBetaSearch.cpp:77-156) and, for the positions that
+// stay unproven or are tree roots, Search::scheduleToNN (Search.cpp:184-198).
+//
+// The positions of one game must be solved in order because they share the table (what task i stores, task i+1 may read);
+// games are independent, so the parallelism is one warp per game with all of the sequential logic in lane 0.
 #include "engine.hpp"
-#include "solver_logic.cuh"
+#include "solver_search.cuh"
 
 #include <vector>
 
@@ -11,27 +16,71 @@ namespace agb
 {
 	namespace
 	{
-		__global__ void __launch_bounds__(128) solve_static_kernel(BoardStore store, Tables tables, const uint16_t *__restrict__ def_table, const int *__restrict__ n_dev,
-				int S, int rules, int draw_after, SolverOutputs out, const uint8_t *__restrict__ slot_is_root, int *__restrict__ nn_list, int *__restrict__ nn_count)
+		constexpr int kSolverWarpsPerBlock = 4;
+
+		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int games, int S, int rules,
+				int draw_after, int max_nodes, SolverOutputs out, const uint8_t *__restrict__ slot_is_root, int *__restrict__ nn_list, int *__restrict__ nn_count,
+				uint32_t *__restrict__ status)
 		{
-			const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-			if (slot >= *n_dev)
+			const int g = blockIdx.x * kSolverWarpsPerBlock + (threadIdx.x >> 5);
+			if (g >= games or (threadIdx.x & 31) != 0)
 				return;
 			const int cells = S * S;
-			const size_t cbase = static_cast<size_t>(slot) * kCellPitch;
-			int stones = 0;
-			for (int i = 0; i < cells; i++)
-				stones += (store.board[cbase + i] != NONE);
-			solver::View v { S, cells, rules, store.sign_to_move[slot], stones, draw_after, kCellPitch, store.board + cbase,
-					store.lines + static_cast<size_t>(slot) * kLinePitch, store.ptypes + cbase, store.threats + cbase, store.forbidden + cbase,
-					store.hist_count + static_cast<size_t>(slot) * 2 * kHistTypes, store.hist_cells + static_cast<size_t>(slot) * 2 * kHistTypes * kCellPitch,
-					tables.pattern, def_table };
-			const solver::Result res = solver::solve_static(v, out.moves + static_cast<size_t>(slot) * out.pitch, out.scores + static_cast<size_t>(slot) * out.pitch);
-			out.n_actions[slot] = res.n_actions;
-			out.score[slot] = res.score;
-			out.must_defend[slot] = res.must_defend ? 1 : 0;
-			if (slot_is_root[slot] or not solver::sc_is_proven(res.score))
-				nn_list[atomicAdd(nn_count, 1)] = slot;
+			const int n_slots = st.game_slot_count[g];
+			solver::HashTable tt { st.table + static_cast<size_t>(g) * st.table_entries * 2, st.table_entries / 4 - 1, st.generation[g], st.keys + static_cast<size_t>(g) * st.keys_stride };
+			solver::SearchMemory mem { st.stack_moves + static_cast<size_t>(g) * st.stack_capacity, st.stack_scores + static_cast<size_t>(g) * st.stack_capacity,
+					st.stack_capacity, reinterpret_cast<solver::Frame*>(st.frames) + static_cast<size_t>(g) * solver::kMaxFrames };
+			for (int k = 0; k < n_slots; k++)
+			{
+				const int slot = st.game_slots[static_cast<size_t>(g) * st.batch + k];
+				const size_t cbase = static_cast<size_t>(slot) * kCellPitch;
+				int stones = 0;
+				for (int i = 0; i < cells; i++)
+					stones += (store.board[cbase + i] != NONE);
+				solver::DynState d;
+				d.board = store.board + cbase;
+				d.lines = store.lines + static_cast<size_t>(slot) * kLinePitch;
+				d.ptypes = store.ptypes + cbase;
+				d.threats = store.threats + cbase;
+				d.hist_count = store.hist_count + static_cast<size_t>(slot) * 2 * kHistTypes;
+				d.hist_cells = store.hist_cells + static_cast<size_t>(slot) * 2 * kHistTypes * kCellPitch;
+				d.threat_table = tables.threat;
+				d.v = solver::View { S, cells, rules, store.sign_to_move[slot], stones, draw_after, kCellPitch, d.board, d.lines, d.ptypes, d.threats,
+						store.forbidden + cbase, d.hist_count, d.hist_cells, tables.pattern, st.def_table, &d };
+				solver::encode_forbidden_pass(d);
+				const solver::SearchOutput res = solver::solve_position(d, tt, mem, max_nodes, 100);
+				uint16_t *om = out.moves + static_cast<size_t>(slot) * out.pitch;
+				uint16_t *os = out.scores + static_cast<size_t>(slot) * out.pitch;
+				for (int i = 0; i < res.n_actions; i++)
+				{
+					om[i] = mem.stack_moves[i];
+					os[i] = mem.stack_scores[i];
+				}
+				out.n_actions[slot] = res.n_actions;
+				out.score[slot] = res.score;
+				out.must_defend[slot] = res.must_defend ? 1 : 0;
+				out.nodes[slot] = res.node_counter;
+				if (res.overflow)
+					atomicOr(status, res.overflow << 8); // bits 8..11, see AgbStats::overflow_flags
+				if (slot_is_root[slot] or not solver::sc_is_proven(res.score))
+					nn_list[atomicAdd(nn_count, 1)] = slot;
+			}
+		}
+		__global__ void clear_tables_kernel(uint64_t *table, size_t n_entries)
+		{
+			for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_entries; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+			{
+				table[2 * i] = 0;
+				table[2 * i + 1] = solver::kEmptyEntryData;
+			}
+		}
+		uint64_t splitmix64(uint64_t &x)
+		{
+			x += 0x9E3779B97F4A7C15ull;
+			uint64_t z = x;
+			z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+			z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+			return z ^ (z >> 31);
 		}
 	}
 
@@ -44,11 +93,63 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		return AGB_OK;
 	}
-	int launch_solve_static(AgbEngine *e, const int *n_dev, int max_n, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count)
+	// per-game search memory; called by selfplay_create when the solver is on
+	int solver_state_create(AgbEngine *e, int games, int batch, SolverState *st)
+	{
+		static_assert(sizeof(solver::Frame) == SolverState::kFrameBytes, "frame size");
+		const AgbConfig &c = e->cfg;
+		size_t entries = c.solver_table_entries > 0 ? static_cast<size_t>(c.solver_table_entries) : 65536;
+		if (entries < 4 or (entries & (entries - 1)) != 0)
+			return e->fail(AGB_EINVAL, "solver_table_entries must be a power of two >= 4 (entries of the per-game transposition table)");
+		st->games = games;
+		st->batch = batch;
+		st->table_entries = entries;
+		st->stack_capacity = e->cells + 64 * 128; // the root list plus room for the deepest lines of a 100-node search
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->table, static_cast<size_t>(games) * entries * 16));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->keys, static_cast<size_t>(e->cells) * 4 * sizeof(uint64_t)));
+		st->keys_stride = 0;
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->generation, games * sizeof(int32_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->game_slots, static_cast<size_t>(games) * batch * sizeof(int32_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->game_slot_count, games * sizeof(int32_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->stack_moves, static_cast<size_t>(games) * st->stack_capacity * sizeof(uint16_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->stack_scores, static_cast<size_t>(games) * st->stack_capacity * sizeof(uint16_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->frames, static_cast<size_t>(games) * solver::kMaxFrames * sizeof(solver::Frame)));
+		AGB_CUDA_CHECK(e, cudaMemset(st->generation, 0, games * sizeof(int32_t)));
+		AGB_CUDA_CHECK(e, cudaMemset(st->game_slot_count, 0, games * sizeof(int32_t)));
+		st->def_table = e->d_def_table;
+		// hash keys: any fixed random words do (they only decide the bucket mapping); agb_set_solver_keys replaces them
+		std::vector<uint64_t> keys(static_cast<size_t>(e->cells) * 4);
+		uint64_t x = c.seed ^ 0x5EEDFACE0C0FFEEull;
+		for (uint64_t &k : keys)
+			k = splitmix64(x);
+		AGB_CUDA_CHECK(e, cudaMemcpy(st->keys, keys.data(), keys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+		return solver_state_reset(e, st);
+	}
+	int solver_state_reset(AgbEngine *e, SolverState *st)
+	{ // AlphaBetaSearch::clear + a fresh generation counter
+		clear_tables_kernel<<<148 * 8, 256, 0, e->stream>>>(st->table, static_cast<size_t>(st->games) * st->table_entries);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(st->generation, 0, st->games * sizeof(int32_t), e->stream));
+		return AGB_OK;
+	}
+	void solver_state_destroy(SolverState *st)
+	{
+		cudaFree(st->table);
+		cudaFree(st->keys);
+		cudaFree(st->generation);
+		cudaFree(st->game_slots);
+		cudaFree(st->game_slot_count);
+		cudaFree(st->stack_moves);
+		cudaFree(st->stack_scores);
+		cudaFree(st->frames);
+		*st = SolverState { };
+	}
+	int launch_solve_games(AgbEngine *e, const SolverState &st, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count)
 	{
 		const int draw_after = e->cfg.draw_after > 0 ? e->cfg.draw_after : e->cells;
-		solve_static_kernel<<<(max_n + 127) / 128, 128, 0, e->stream>>>(e->store, e->tables, e->d_def_table, n_dev, e->cfg.rows, e->cfg.rules, draw_after, out,
-				slot_is_root, nn_list, nn_count);
+		solve_games_kernel<<<(st.games + kSolverWarpsPerBlock - 1) / kSolverWarpsPerBlock, kSolverWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, st,
+				st.games, e->cfg.rows, e->cfg.rules, draw_after, e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

@@ -211,6 +211,9 @@ namespace agb
 		}
 
 		// ---- view of one analysed position ---------------------------------------------------------------------------------------
+		struct DynState;
+		AGB_HD inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c); // solver_search.cuh: live state, reference side effects
+		enum : int { GEN_BASIC = 0, GEN_THREATS = 1, GEN_OPTIMAL = 2, GEN_REDUCED = 3, GEN_LEGAL = 4 }; // MoveGeneratorMode (MoveGenerator.hpp)
 		struct View
 		{
 				int S, cells, rules, stm, stones, draw_after, pitch; // pitch: cells per list in hist_cells
@@ -223,6 +226,7 @@ namespace agb
 				const uint16_t *hist_cells; // [2][10][pitch]
 				const uint8_t *pattern_table;
 				const uint16_t *def_table;
+				DynState *dyn = nullptr; // set when the position is searched in place (forbidden moves are then evaluated on the live state)
 
 				AGB_HD int own() const { return stm; }
 				AGB_HD int opp() const { return 3 - stm; }
@@ -256,7 +260,12 @@ namespace agb
 					return 0;
 				}
 				AGB_HD bool anything_forbidden_for(int sign) const { return rules == RULE_RENJU and sign == CROSS; }
-				AGB_HD bool is_forbidden(int sign, int r, int c) const { return anything_forbidden_for(sign) and forbidden[r * S + c] != 0; }
+				AGB_HD bool is_forbidden(int sign, int r, int c) const
+				{
+					if (dyn != nullptr)
+						return dyn_is_forbidden(dyn, sign, r, c);
+					return anything_forbidden_for(sign) and forbidden[r * S + c] != 0;
+				}
 				AGB_HD bool has_any_four(int sign) const
 				{
 					return count(sign, TT_HALF_OPEN_4) > 0 or count(sign, TT_FORK_4x3) > 0 or count(sign, TT_FORK_4x4) > 0 or count(sign, TT_OPEN_4) > 0;
@@ -339,6 +348,23 @@ namespace agb
 				uint16_t *scores;
 				Result out;
 				uint32_t added[kMaxSize]; // bitmask of cells already in the list (MoveGenerator::moves)
+				// MoveGenerator::temporary_list: a copy of a threat list taken before a loop that may call is_forbidden(), which re-plays
+				// moves on the calculator and so may reorder the original list (MoveGenerator.cpp:1181-1185)
+				static constexpr int kTempCapacity = 96;
+				uint16_t temp[kTempCapacity];
+				int temp_size = 0;
+				bool temp_overflow = false;
+				AGB_HD void copy_list(int sign, int tt)
+				{
+					temp_size = v.count(sign, tt);
+					if (temp_size > kTempCapacity)
+					{
+						temp_size = kTempCapacity;
+						temp_overflow = true;
+					}
+					for (int i = 0; i < temp_size; i++)
+						temp[i] = v.item(sign, tt, i);
+				}
 
 				AGB_HD MoveGenerator(const View &view, uint16_t *m, uint16_t *s) : v(view), moves(m), scores(s)
 				{
@@ -541,10 +567,10 @@ namespace agb
 					int hidden = 0;
 					if (v.anything_forbidden_for(v.own()))
 					{
-						const int n = v.count(v.own(), TT_FORK_3x3);
-						for (int i = 0; i < n; i++)
+						copy_list(v.own(), TT_FORK_3x3);
+						for (int i = 0; i < temp_size; i++)
 						{
-							const uint16_t loc = v.item(v.own(), TT_FORK_3x3, i);
+							const uint16_t loc = temp[i];
 							if (v.group_contains(v.own(), loc_row(loc), loc_col(loc), PT_HALF_OPEN_4) and not v.is_forbidden(v.own(), loc_row(loc), loc_col(loc)))
 							{
 								add_move(loc, prior, false);
@@ -666,10 +692,10 @@ namespace agb
 					int threats = 0;
 					if (v.anything_forbidden_for(v.own()))
 					{
-						const int n = v.count(v.own(), TT_FORK_3x3);
-						for (int i = 0; i < n; i++)
+						copy_list(v.own(), TT_FORK_3x3);
+						for (int i = 0; i < temp_size; i++)
 						{
-							const uint16_t loc = v.item(v.own(), TT_FORK_3x3, i);
+							const uint16_t loc = temp[i];
 							if (v.group_contains(v.own(), loc_row(loc), loc_col(loc), PT_OPEN_4) and not v.is_forbidden(v.own(), loc_row(loc), loc_col(loc)))
 							{
 								threats++;
@@ -686,10 +712,10 @@ namespace agb
 					}
 					if (v.anything_forbidden_for(v.opp()))
 					{ // renju, white to move: a four whose only answer is a forbidden point for black
-						const int n = v.count(v.own(), TT_HALF_OPEN_4);
-						for (int i = 0; i < n; i++)
+						copy_list(v.own(), TT_HALF_OPEN_4);
+						for (int i = 0; i < temp_size; i++)
 						{
-							const uint16_t loc = v.item(v.own(), TT_HALF_OPEN_4, i);
+							const uint16_t loc = temp[i];
 							const int r = loc_row(loc), c = loc_col(loc);
 							const int dir = v.direction_of(v.own(), r, c, PT_HALF_OPEN_4);
 							bool winning = false;
@@ -781,20 +807,20 @@ namespace agb
 					}
 					else
 					{
-						const int n_open4 = v.count(v.opp(), TT_OPEN_4);
-						for (int i = 0; i < n_open4; i++)
+						copy_list(v.opp(), TT_OPEN_4);
+						for (int i = 0; i < temp_size; i++)
 						{
 							out.must_defend = true;
-							const uint16_t loc = v.item(v.opp(), TT_OPEN_4, i);
+							const uint16_t loc = temp[i];
 							const int dir = v.direction_of(v.opp(), loc_row(loc), loc_col(loc), PT_OPEN_4);
 							add_all(get_defensive_moves(loc, dir));
 						}
 						if (v.anything_forbidden_for(v.opp()))
 						{
-							const int n = v.count(v.opp(), TT_FORK_3x3);
-							for (int i = 0; i < n; i++)
+							copy_list(v.opp(), TT_FORK_3x3);
+							for (int i = 0; i < temp_size; i++)
 							{
-								const uint16_t loc = v.item(v.opp(), TT_FORK_3x3, i);
+								const uint16_t loc = temp[i];
 								const int r = loc_row(loc), c = loc_col(loc);
 								if (v.group_contains(v.opp(), r, c, PT_OPEN_4) and not v.is_forbidden(v.opp(), r, c))
 								{
@@ -805,11 +831,11 @@ namespace agb
 						}
 						if (not v.anything_forbidden_for(v.opp()))
 						{
-							const int n = v.count(v.opp(), TT_FORK_4x4);
-							for (int i = 0; i < n; i++)
+							copy_list(v.opp(), TT_FORK_4x4);
+							for (int i = 0; i < temp_size; i++)
 							{
 								out.must_defend = true;
-								const uint16_t loc = v.item(v.opp(), TT_FORK_4x4, i);
+								const uint16_t loc = temp[i];
 								for (int dir = 0; dir < 4; dir++)
 								{
 									const int pt = v.ptype_at(v.opp(), loc_row(loc), loc_col(loc), dir);
@@ -856,14 +882,23 @@ namespace agb
 						out.must_defend = true;
 						out.baseline = loss_in(6);
 					}
+					// the reference walks the LIVE lists here and dereferences its iterator again for every get_defensive_moves() call, while
+					// the pattern group was read once at the top of the iteration; is_forbidden() inside may have reordered the list in between
 					for (int i = 0; i < n43; i++)
 					{
 						const uint16_t loc = v.item(v.opp(), TT_FORK_4x3, i);
 						const int r = loc_row(loc), c = loc_col(loc);
+						int group[4];
 						for (int dir = 0; dir < 4; dir++)
-							if (v.ptype_at(v.opp(), r, c, dir) == PT_OPEN_3)
-								add_all(get_defensive_moves(loc, dir), sc_eval(0));
-						const LocList<7> four_defence = get_defensive_moves(loc, v.direction_of(v.opp(), r, c, PT_HALF_OPEN_4));
+							group[dir] = v.ptype_at(v.opp(), r, c, dir);
+						for (int dir = 0; dir < 4; dir++)
+							if (group[dir] == PT_OPEN_3)
+								add_all(get_defensive_moves(v.item(v.opp(), TT_FORK_4x3, i), dir), sc_eval(0));
+						int four_dir = 0;
+						for (int dir = 3; dir >= 0; dir--)
+							if (group[dir] == PT_HALF_OPEN_4)
+								four_dir = dir;
+						const LocList<7> four_defence = get_defensive_moves(v.item(v.opp(), TT_FORK_4x3, i), four_dir);
 						add_all(four_defence, sc_eval(0));
 						for (int k = 0; k < four_defence.size; k++)
 						{
@@ -885,9 +920,12 @@ namespace agb
 					{
 						const uint16_t loc = v.item(v.opp(), TT_FORK_3x3, i);
 						const int r = loc_row(loc), c = loc_col(loc);
+						int group[4];
 						for (int dir = 0; dir < 4; dir++)
-							if (v.ptype_at(v.opp(), r, c, dir) == PT_OPEN_3)
-								add_all(get_defensive_moves(loc, dir), sc_eval(0));
+							group[dir] = v.ptype_at(v.opp(), r, c, dir);
+						for (int dir = 0; dir < 4; dir++)
+							if (group[dir] == PT_OPEN_3)
+								add_all(get_defensive_moves(v.item(v.opp(), TT_FORK_3x3, i), dir), sc_eval(0));
 						add_list(v.own(), TT_FORK_3x3, sc_eval(13));
 						add_list(v.own(), TT_OPEN_3, sc_eval(1));
 						uint32_t mask[kMaxSize];
@@ -917,16 +955,17 @@ namespace agb
 				{ // MoveGenerator.cpp:995-1010
 					add_list(v.own(), TT_OVERLINE, loss_in(1), true);
 					add_list(v.own(), TT_FORK_4x4, loss_in(1), true);
-					const int n = v.count(v.own(), TT_FORK_3x3);
-					for (int i = 0; i < n; i++)
+					copy_list(v.own(), TT_FORK_3x3);
+					for (int i = 0; i < temp_size; i++)
 					{
-						const uint16_t loc = v.item(v.own(), TT_FORK_3x3, i);
+						const uint16_t loc = temp[i];
 						if (v.is_forbidden(CROSS, loc_row(loc), loc_col(loc)))
 							add_move(loc, loss_in(1), true);
 					}
 				}
-				// MoveGenerator::generate in OPTIMAL mode (MoveGenerator.cpp:159-223)
-				AGB_HD void generate_optimal()
+				AGB_HD void generate_optimal() { generate(GEN_OPTIMAL); }
+				// MoveGenerator::generate in THREATS or OPTIMAL mode (MoveGenerator.cpp:159-223)
+				AGB_HD void generate(int mode)
 				{
 					const int distance_to_draw = v.draw_after - v.stones;
 					if (distance_to_draw <= 0)
@@ -950,7 +989,7 @@ namespace agb
 						stop = defend_loss_in_6(score);
 					if (not stop and distance_to_draw >= 3)
 						add_own_half_open_fours();
-					if (not stop)
+					if (not stop and mode >= GEN_OPTIMAL)
 					{
 						if (distance_to_draw >= 6)
 						{
@@ -970,7 +1009,7 @@ namespace agb
 					}
 					if (v.anything_forbidden_for(v.own()))
 						mark_forbidden_moves();
-					out.is_fully_expanded = true; // must_defend or mode >= OPTIMAL
+					out.is_fully_expanded = out.must_defend or mode >= GEN_OPTIMAL;
 					out.score = stop ? score : kScoreDefault;
 				}
 		};

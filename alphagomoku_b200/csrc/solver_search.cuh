@@ -1,0 +1,633 @@
+// K5 (search layer): the reference's alpha-beta threat-space search on top of the static layer, as host+device code.
+//
+// Reference: AlphaBetaSearch::solve / recursive_solve / evaluate (src/search/alpha_beta/AlphaBetaSearch.cpp:77-156, 185-339,
+// 345-365), ActionList / ActionStack (include/alphagomoku/search/alpha_beta/ActionList.hpp:262-420), SharedHashTable
+// (include/alphagomoku/search/alpha_beta/SharedHashTable.hpp:27-220), FastZobristHashing (ZobristHashing.hpp:111-127),
+// PatternCalculator::addMove / undoMove / update_around (src/patterns/PatternCalculator.cpp:68-106, 278-366) and
+// PatternCalculator::isForbidden / is_3x3_forbidden (PatternCalculator.hpp:173-189, PatternCalculator.cpp:213-244).
+//
+// One thread owns one game: it solves that game's leaf positions one after another (they share the game's transposition
+// table, so the order is part of the result). The recursion of the reference is unrolled into an explicit frame stack;
+// the position is updated in place with the same incremental update as K2, which also keeps the ORDER of the threat lists
+// identical to the reference's (swap-with-last removal, append on change, visiting order of update_around).
+#pragma once
+#include "solver_logic.cuh"
+
+namespace agb
+{
+	namespace solver
+	{
+		// ---- mutable position ----------------------------------------------------------------------------------------------------
+		struct DynState
+		{
+				View v; // read side (same memory); stm / stones follow add and undo
+				int8_t *board;
+				uint64_t *lines;
+				uint32_t *ptypes;
+				uint8_t *threats;
+				int32_t *hist_count;
+				uint16_t *hist_cells;
+				const uint8_t *threat_table;
+				// MoveGenerator::forbidden_moves_cache: results of isForbidden within one generate() call
+				uint16_t cache_loc[48];
+				uint8_t cache_val[48];
+				int cache_size = 0;
+				uint32_t overflow = 0; // 1: forbidden-move recursion too deep, 2: forbidden cache full
+		};
+
+		AGB_HD inline void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
+		{ // ThreatHistogram::remove (ThreatHistogram.hpp:74-91)
+			if (type == TT_NONE)
+				return;
+			int32_t &count = d.hist_count[colour * kHistTypes + type];
+			uint16_t *list = d.hist_cells + (colour * kHistTypes + type) * d.v.pitch;
+			for (int i = 0; i < count; i++)
+				if (list[i] == loc)
+				{
+					list[i] = list[count - 1];
+					count--;
+					return;
+				}
+		}
+		AGB_HD inline void dyn_hist_add(DynState &d, int colour, int type, uint16_t loc)
+		{
+			if (type == TT_NONE)
+				return;
+			int32_t &count = d.hist_count[colour * kHistTypes + type];
+			d.hist_cells[(colour * kHistTypes + type) * d.v.pitch + count] = loc;
+			count++;
+		}
+		AGB_HD inline void dyn_update_neighbours(DynState &d, int r, int c, const uint64_t *line4, const int *pos4)
+		{ // the 40 cells at distance 1..5 in the visiting order of update_around (PatternCalculator.cpp:320-330)
+			const int S = d.v.S;
+			for (int off = -5; off <= 5; off++)
+				if (off != 0)
+					for (int dir = 0; dir < 4; dir++)
+					{
+						const int nr = r + off * dir_row_step(dir), nc = c + off * dir_col_step(dir);
+						if (nr < 0 or nr >= S or nc < 0 or nc >= S)
+							continue;
+						const int ncell = nr * S + nc;
+						if (d.board[ncell] != NONE)
+							continue;
+						const uint32_t window = static_cast<uint32_t>(line4[dir] >> (2 * (pos4[dir] + off) + 2)) & 0x3FFFFFu;
+						const uint32_t byte = d.v.pattern_table[narrow_window(window)];
+						const uint32_t p = (d.ptypes[ncell] & ~(0xFFu << (8 * dir))) | (byte << (8 * dir));
+						const uint8_t old_t = d.threats[ncell];
+						const uint8_t new_t = threat_of_cell(p, d.threat_table);
+						d.ptypes[ncell] = p;
+						d.threats[ncell] = new_t;
+						if (old_t != new_t)
+						{
+							const uint16_t loc = mk_loc(nr, nc);
+							if ((old_t & 15) != (new_t & 15))
+							{
+								dyn_hist_remove(d, 0, old_t & 15, loc);
+								dyn_hist_add(d, 0, new_t & 15, loc);
+							}
+							if ((old_t >> 4) != (new_t >> 4))
+							{
+								dyn_hist_remove(d, 1, old_t >> 4, loc);
+								dyn_hist_add(d, 1, new_t >> 4, loc);
+							}
+						}
+					}
+		}
+		AGB_HD inline void dyn_add_move(DynState &d, int r, int c, int sign)
+		{ // PatternCalculator::addMove (PatternCalculator.cpp:68-86)
+			const int S = d.v.S;
+			uint64_t line4[4];
+			int pos4[4];
+			for (int dir = 0; dir < 4; dir++)
+			{
+				const int li = line_index(dir, r, c, S);
+				pos4[dir] = pos_in_line(dir, r, c, S);
+				d.lines[li] |= static_cast<uint64_t>(sign) << (12 + 2 * pos4[dir]);
+				line4[dir] = d.lines[li];
+			}
+			const int centre = r * S + c;
+			d.board[centre] = static_cast<int8_t>(sign);
+			const uint8_t old_t = d.threats[centre];
+			dyn_hist_remove(d, 0, old_t & 15, mk_loc(r, c));
+			dyn_hist_remove(d, 1, old_t >> 4, mk_loc(r, c));
+			d.ptypes[centre] = 0;
+			d.threats[centre] = 0;
+			dyn_update_neighbours(d, r, c, line4, pos4);
+			d.v.stm = 3 - d.v.stm;
+			d.v.stones++;
+		}
+		AGB_HD inline void dyn_undo_move(DynState &d, int r, int c, int sign)
+		{ // PatternCalculator::undoMove (PatternCalculator.cpp:87-106)
+			(void) sign;
+			const int S = d.v.S;
+			uint64_t line4[4];
+			int pos4[4];
+			for (int dir = 0; dir < 4; dir++)
+			{
+				const int li = line_index(dir, r, c, S);
+				pos4[dir] = pos_in_line(dir, r, c, S);
+				d.lines[li] &= ~(3ull << (12 + 2 * pos4[dir]));
+				line4[dir] = d.lines[li];
+			}
+			const int centre = r * S + c;
+			d.board[centre] = NONE;
+			uint32_t p = 0;
+			for (int dir = 0; dir < 4; dir++)
+				p |= static_cast<uint32_t>(d.v.pattern_table[narrow_window(static_cast<uint32_t>(line4[dir] >> (2 * pos4[dir] + 2)) & 0x3FFFFFu)]) << (8 * dir);
+			const uint8_t new_t = threat_of_cell(p, d.threat_table);
+			d.ptypes[centre] = p;
+			d.threats[centre] = new_t;
+			dyn_hist_add(d, 0, new_t & 15, mk_loc(r, c));
+			dyn_hist_add(d, 1, new_t >> 4, mk_loc(r, c));
+			dyn_update_neighbours(d, r, c, line4, pos4);
+			d.v.stm = 3 - d.v.stm;
+			d.v.stones--;
+		}
+
+		// ---- renju forbidden moves on the live state (with the reference's side effect on the list order) ---------------------------
+		constexpr int kMaxForbiddenDepth = 8;
+		AGB_HD inline bool dyn_calc_is_forbidden(DynState &d, int r, int c, int depth);
+		AGB_HD inline bool dyn_raw_straight_four(const DynState &d, int r, int c, int dir)
+		{ // RawPatternCalculator::isStraightFourAt on the raw board
+			Overlay none;
+			return makes_straight_four(raw_window(d.board, d.v.S, r, c, dir, none));
+		}
+		AGB_HD inline bool dyn_is_3x3_forbidden(DynState &d, int r, int c, int depth)
+		{ // PatternCalculator::is_3x3_forbidden (PatternCalculator.cpp:213-244)
+			if (depth >= kMaxForbiddenDepth)
+			{
+				d.overflow |= 1u;
+				return true;
+			}
+			const int S = d.v.S;
+			int open3_count = 0;
+			for (int dir = 0; dir < 4; dir++)
+				if (d.v.ptype_at(CROSS, r, c, dir) == PT_OPEN_3)
+				{
+					const uint32_t promotions = open_three_promotions(normal_window(d.lines, dir, r, c, S));
+					d.board[r * S + c] = CROSS;
+					for (int i = -5; i <= 5; i++)
+						if ((promotions >> (i + 5)) & 1u)
+						{
+							const int pr = r + i * dir_row_step(dir), pc = c + i * dir_col_step(dir);
+							if (pr < 0 or pr >= S or pc < 0 or pc >= S)
+								continue;
+							if (d.board[pr * S + pc] == NONE and dyn_raw_straight_four(d, pr, pc, dir))
+							{
+								d.board[r * S + c] = NONE;
+								const int stm = d.v.stm;
+								dyn_add_move(d, r, c, CROSS);
+								const bool forbidden = dyn_calc_is_forbidden(d, pr, pc, depth + 1);
+								dyn_undo_move(d, r, c, CROSS);
+								d.v.stm = stm;
+								d.board[r * S + c] = CROSS;
+								if (not forbidden)
+								{
+									open3_count++;
+									break;
+								}
+							}
+						}
+					d.board[r * S + c] = NONE;
+				}
+			return open3_count >= 2;
+		}
+		AGB_HD inline bool dyn_calc_is_forbidden(DynState &d, int r, int c, int depth)
+		{ // PatternCalculator::isForbidden(CROSS, r, c) (PatternCalculator.hpp:173-189)
+			if (d.v.rules != RULE_RENJU)
+				return false;
+			if (d.board[r * d.v.S + c] != NONE)
+				return false;
+			const int t = d.threats[r * d.v.S + c] & 15;
+			if (t == TT_OVERLINE or t == TT_FORK_4x4)
+				return true;
+			if (t == TT_FORK_3x3)
+				return dyn_is_3x3_forbidden(d, r, c, depth);
+			return false;
+		}
+		AGB_HD inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c)
+		{ // MoveGenerator::is_forbidden (MoveGenerator.cpp:1167-1180): cached per generate() call
+			if (not (d->v.rules == RULE_RENJU and sign == CROSS))
+				return false;
+			const uint16_t loc = mk_loc(r, c);
+			for (int i = 0; i < d->cache_size; i++)
+				if (d->cache_loc[i] == loc)
+					return d->cache_val[i] != 0;
+			const bool result = dyn_calc_is_forbidden(*d, r, c, 0);
+			if (d->cache_size < 48)
+			{
+				d->cache_loc[d->cache_size] = loc;
+				d->cache_val[d->cache_size] = result ? 1 : 0;
+				d->cache_size++;
+			}
+			else
+				d->overflow |= 2u;
+			return result;
+		}
+
+		// NNInputFeatures::encode (NNInputFeatures.cpp:104-110) asks isForbidden for every cell before the search starts; only its side
+		// effect on the list order matters here (the feature words themselves come from K3)
+		AGB_HD inline void encode_forbidden_pass(DynState &d)
+		{
+			if (d.v.rules != RULE_RENJU or d.v.stm != CROSS)
+				return;
+			const int n = d.v.count(CROSS, TT_FORK_3x3);
+			if (n == 0)
+				return; // nothing would be added or undone
+			for (int r = 0; r < d.v.S; r++)
+				for (int c = 0; c < d.v.S; c++)
+					if ((d.threats[r * d.v.S + c] & 15) == TT_FORK_3x3)
+						dyn_calc_is_forbidden(d, r, c, 0);
+		}
+
+		// ---- transposition table (one per game) --------------------------------------------------------------------------------------
+		enum : int { BOUND_NONE = 0, BOUND_LOWER = 1, BOUND_UPPER = 2, BOUND_EXACT = 3 };
+		struct HashTable
+		{
+				uint64_t *entries; // [size][2]: upper key word, packed data (SharedTableData)
+				uint64_t bucket_mask; // buckets of 4 entries
+				int generation; // SharedHashTable::m_base_generation
+				const uint64_t *keys; // [2 * cells][2]: low, high word per (cell, colour)
+		};
+		constexpr uint64_t kKeyMask = 0xFFFF000000000000ull;
+		constexpr uint64_t kEmptyEntryData = static_cast<uint64_t>(kScoreDefault) << 16; // SharedTableData(): bound NONE, depth 0, Score(), Move()
+		AGB_HD inline uint64_t tt_pack(int bound, int depth, uint16_t score, uint16_t move)
+		{
+			return static_cast<uint64_t>(bound) | (static_cast<uint64_t>(depth) << 8) | (static_cast<uint64_t>(score) << 16) | (static_cast<uint64_t>(move) << 32);
+		}
+		AGB_HD inline int tt_bound(uint64_t e) { return static_cast<int>(e & 3ull); }
+		AGB_HD inline int tt_generation(uint64_t e) { return static_cast<int>((e >> 2) & 63ull); }
+		AGB_HD inline int tt_depth(uint64_t e) { return static_cast<int>((e >> 8) & 255ull); }
+		AGB_HD inline uint16_t tt_score(uint64_t e) { return static_cast<uint16_t>((e >> 16) & 65535ull); }
+		AGB_HD inline uint16_t tt_move(uint64_t e) { return static_cast<uint16_t>((e >> 32) & 65535ull); }
+		AGB_HD inline void tt_clear(uint64_t *entries, size_t n_entries)
+		{
+			for (size_t i = 0; i < n_entries; i++)
+			{
+				entries[2 * i] = 0;
+				entries[2 * i + 1] = kEmptyEntryData;
+			}
+		}
+		AGB_HD inline uint64_t tt_seek(const HashTable &t, uint64_t lo, uint64_t hi)
+		{
+			const uint64_t *bucket = t.entries + 8 * (lo & t.bucket_mask);
+			for (int i = 0; i < 4; i++)
+				if (bucket[2 * i] == hi and (bucket[2 * i + 1] & kKeyMask) == (lo & kKeyMask))
+					return bucket[2 * i + 1];
+			return kEmptyEntryData;
+		}
+		AGB_HD inline void tt_insert(HashTable &t, uint64_t lo, uint64_t hi, uint64_t value)
+		{
+			value &= ~(kKeyMask | 0xFCull);
+			value |= static_cast<uint64_t>(t.generation) << 2;
+			value |= lo & kKeyMask;
+			uint64_t *bucket = t.entries + 8 * (lo & t.bucket_mask);
+			if (sc_is_proven(tt_score(value)) or tt_bound(value) == BOUND_EXACT)
+				for (int i = 0; i < 4; i++)
+					if (bucket[2 * i] == hi and (bucket[2 * i + 1] & kKeyMask) == (lo & kKeyMask))
+					{
+						bucket[2 * i] = hi;
+						bucket[2 * i + 1] = value;
+						return;
+					}
+			int idx = 0, best = 0;
+			for (int i = 0; i < 4; i++)
+			{
+				const int val = tt_depth(bucket[2 * i + 1]) - (t.generation - tt_generation(bucket[2 * i + 1]));
+				if (i == 0 or val < best)
+				{
+					best = val;
+					idx = i;
+				}
+			}
+			bucket[2 * idx] = hi;
+			bucket[2 * idx + 1] = value;
+		}
+
+		// ---- Score arithmetic of the search (search/Score.hpp) -----------------------------------------------------------------------
+		constexpr uint16_t kScoreMinusInf = 0x0000, kScorePlusInf = 0xFFFF;
+		AGB_HD inline int sc_pv(uint16_t s) { return (s >> 13) & 3; }
+		AGB_HD inline int sc_ev(uint16_t s) { return static_cast<int>(s & 8191) - 4000; }
+		AGB_HD inline bool sc_finite(uint16_t s) { return s != kScoreMinusInf and s != kScorePlusInf; }
+		AGB_HD inline bool sc_is_loss(uint16_t s) { return sc_pv(s) == PV_LOSS and sc_finite(s); }
+		AGB_HD inline int sc_distance(uint16_t s)
+		{
+			switch (sc_pv(s))
+			{
+				case PV_LOSS:
+				case PV_DRAW:
+					return sc_ev(s);
+				case PV_WIN:
+					return -sc_ev(s);
+				default:
+					return 0;
+			}
+		}
+		AGB_HD inline uint16_t sc_negate(uint16_t s)
+		{
+			switch (sc_pv(s))
+			{
+				case PV_LOSS:
+					return sc_finite(s) ? mk_score(PV_WIN, -sc_ev(s)) : kScorePlusInf;
+				case PV_DRAW:
+					return mk_score(PV_DRAW, sc_ev(s));
+				case PV_WIN:
+					return sc_finite(s) ? mk_score(PV_LOSS, -sc_ev(s)) : kScoreMinusInf;
+				default:
+					return mk_score(PV_UNKNOWN, -sc_ev(s));
+			}
+		}
+		AGB_HD inline uint16_t sc_invert(uint16_t s, int delta)
+		{ // invert_up (delta +1) / invert_down (delta -1)
+			switch (sc_pv(s))
+			{
+				case PV_LOSS:
+					return sc_finite(s) ? win_in(sc_distance(s) + delta) : sc_negate(s);
+				case PV_DRAW:
+					return draw_in(sc_distance(s) + delta);
+				case PV_WIN:
+					return sc_finite(s) ? loss_in(sc_distance(s) + delta) : sc_negate(s);
+				default:
+					return sc_negate(s);
+			}
+		}
+
+		// ---- the search --------------------------------------------------------------------------------------------------------------
+		constexpr int kMaxFrames = 104; // depth limit 100 (Search::solve sets it) + root
+		struct Frame
+		{
+				int32_t list_begin; // offset of this node's actions on the action stack
+				int16_t list_size;
+				int16_t index; // action being searched
+				int16_t depth_remaining;
+				uint16_t alpha, beta, original_alpha, best_score, best_move;
+				uint16_t move; // move made to descend from this node
+				uint8_t is_fully_expanded;
+				uint8_t pad;
+		};
+		struct SearchMemory
+		{ // scratch of one game (global memory on the device)
+				uint16_t *stack_moves, *stack_scores; // ActionStack
+				int stack_capacity;
+				Frame *frames; // [kMaxFrames]
+		};
+		struct SearchOutput
+		{
+				uint16_t score = kScoreDefault;
+				int n_actions = 0; // root actions are left at the bottom of the action stack, in their final order
+				bool must_defend = false;
+				int node_counter = 0;
+				uint32_t overflow = 0; // 4: action stack full, 8: frame stack full (plus DynState's bits)
+		};
+
+		AGB_HD inline void hash_toggle(const HashTable &t, uint64_t &lo, uint64_t &hi, int S, uint16_t move)
+		{ // FastZobristHashing::updateHash
+			const int row = (move >> 2) & 127, col = (move >> 9) & 127, sign = move & 3;
+			const uint64_t *k = t.keys + 2 * (2 * (row * S + col) + sign - 1);
+			lo ^= k[0];
+			hi ^= k[1];
+		}
+		AGB_HD inline void hash_of_board(const HashTable &t, const DynState &d, uint64_t &lo, uint64_t &hi)
+		{ // FastZobristHashing::getHash
+			lo = 0;
+			hi = 0;
+			for (int i = 0; i < d.v.cells; i++)
+				if (d.board[i] == CROSS or d.board[i] == CIRCLE)
+				{
+					const uint64_t *k = t.keys + 2 * (2 * i + d.board[i] - 1);
+					lo ^= k[0];
+					hi ^= k[1];
+				}
+		}
+
+		// AlphaBetaSearch::solve (AlphaBetaSearch.cpp:77-156) without the time limit; `max_depth` is Search::solve's 100
+		AGB_HD inline SearchOutput solve_position(DynState &d, HashTable &tt, SearchMemory &mem, int max_nodes, int max_depth)
+		{
+			SearchOutput out;
+			uint64_t key_lo, key_hi;
+			hash_of_board(tt, d, key_lo, key_hi);
+			int stack_offset = 0, stack_max_offset = 0; // ActionStack::m_offset / m_max_offset
+			int root_size = 0;
+			bool root_fully_expanded = false;
+			uint16_t result = kScoreDefault;
+			Frame *frames = mem.frames;
+
+			for (int depth = 0; depth <= max_depth; depth += 4)
+			{
+				const int max_offset_before = stack_max_offset;
+				// ---- recursive_solve(depth, min_value, max_value, root actions), unrolled -------------------------------------------
+				int top = 0;
+				frames[0].list_begin = 0;
+				frames[0].list_size = static_cast<int16_t>(root_size);
+				frames[0].depth_remaining = static_cast<int16_t>(depth);
+				frames[0].alpha = kScoreMinusInf;
+				frames[0].beta = kScorePlusInf;
+				frames[0].is_fully_expanded = root_fully_expanded ? 1 : 0;
+				bool entering = true;
+				uint16_t returned = kScoreDefault;
+				while (top >= 0)
+				{
+					Frame &f = frames[top];
+					if (entering)
+					{ // AlphaBetaSearch.cpp:197-245
+						entering = false;
+						f.best_move = 0; // Move()
+						bool done = false;
+						const uint64_t entry = tt_seek(tt, key_lo, key_hi);
+						if (tt_bound(entry) != BOUND_NONE)
+						{
+							f.best_move = tt_move(entry);
+							if (top > 0)
+							{
+								const uint16_t s = tt_score(entry);
+								const int b = tt_bound(entry);
+								if (sc_is_proven(s))
+								{
+									returned = s;
+									done = true;
+								}
+								else if (tt_depth(entry) >= f.depth_remaining
+										and (b == BOUND_EXACT or (b == BOUND_LOWER and s >= f.beta) or (b == BOUND_UPPER and s <= f.alpha)))
+								{
+									returned = s;
+									done = true;
+								}
+							}
+						}
+						if (not done)
+						{
+							out.node_counter++;
+							if (f.list_size == 0)
+							{
+								if (stack_offset + d.v.cells > mem.stack_capacity)
+								{
+									out.overflow |= 4u;
+									returned = kScoreDefault;
+									done = true;
+								}
+								else
+								{
+									d.cache_size = 0;
+									MoveGenerator gen(d.v, mem.stack_moves + f.list_begin, mem.stack_scores + f.list_begin);
+									gen.generate(top == 0 ? GEN_OPTIMAL : GEN_THREATS);
+									f.list_size = static_cast<int16_t>(gen.out.n_actions);
+									f.is_fully_expanded = gen.out.is_fully_expanded ? 1 : 0;
+									stack_offset += gen.out.n_actions;
+									if (stack_offset > stack_max_offset)
+										stack_max_offset = stack_offset;
+									if (top == 0)
+									{
+										root_size = gen.out.n_actions;
+										root_fully_expanded = gen.out.is_fully_expanded;
+										out.must_defend = gen.out.must_defend;
+									}
+									if (sc_is_proven(gen.out.score))
+									{
+										returned = gen.out.score;
+										done = true;
+									}
+								}
+							}
+						}
+						if (not done and f.depth_remaining <= 0)
+						{
+							returned = static_evaluation(d.v);
+							done = true;
+						}
+						if (done)
+						{ // return from this call: the child's list dies (ActionList::~ActionList)
+							if (top > 0)
+								stack_offset -= f.list_size;
+							top--;
+							continue;
+						}
+						f.original_alpha = f.alpha;
+						f.best_score = kScoreMinusInf;
+						f.index = 0;
+					}
+					else
+					{ // back from the child of action f.index (AlphaBetaSearch.cpp:293-310)
+						const int i = f.index;
+						mem.stack_scores[f.list_begin + i] = sc_invert(returned, +1);
+						const uint16_t mv = f.move;
+						dyn_undo_move(d, (mv >> 2) & 127, (mv >> 9) & 127, mv & 3);
+						hash_toggle(tt, key_lo, key_hi, d.v.S, mv);
+						// rest of the loop body for this action
+						const uint16_t s = mem.stack_scores[f.list_begin + i];
+						if (s > f.best_score)
+							f.best_score = s;
+						if (s > f.alpha)
+						{
+							f.alpha = s;
+							f.best_move = mem.stack_moves[f.list_begin + i];
+						}
+						if (s >= f.beta or sc_is_win(s))
+							f.index = f.list_size; // break
+						else
+							f.index++;
+					}
+
+					// the action loop (AlphaBetaSearch.cpp:262-316)
+					uint16_t *am = mem.stack_moves + f.list_begin;
+					uint16_t *as = mem.stack_scores + f.list_begin;
+					bool descended = false;
+					while (f.index < f.list_size)
+					{
+						const int i = f.index;
+						bool ordered = false;
+						if (i == 0)
+						{ // is_move_legal(best_move) -> moveCloserToFront(best_move, 0)
+							const uint16_t bm = f.best_move;
+							const int br = (bm >> 2) & 127, bc = (bm >> 9) & 127;
+							if ((bm & 3) == d.v.stm and br < d.v.S and bc < d.v.S and d.board[br * d.v.S + bc] == NONE)
+							{
+								ordered = true;
+								for (int j = 0; j < f.list_size; j++)
+									if (am[j] == bm)
+									{
+										const uint16_t tm = am[0], ts = as[0];
+										am[0] = am[j];
+										as[0] = as[j];
+										am[j] = tm;
+										as[j] = ts;
+										break;
+									}
+							}
+						}
+						if (not ordered)
+						{ // selection step: first maximum of the remaining actions
+							int idx = i;
+							for (int j = i + 1; j < f.list_size; j++)
+								if (as[idx] < as[j])
+									idx = j;
+							const uint16_t tm = am[i], ts = as[i];
+							am[i] = am[idx];
+							as[i] = as[idx];
+							am[idx] = tm;
+							as[idx] = ts;
+						}
+						if (sc_pv(as[i]) == PV_UNKNOWN and out.node_counter < max_nodes)
+						{ // descend
+							if (top + 1 >= kMaxFrames)
+							{
+								out.overflow |= 8u;
+							}
+							else
+							{
+								const uint16_t mv = am[i];
+								hash_toggle(tt, key_lo, key_hi, d.v.S, mv);
+								Frame &child = frames[top + 1];
+								child.list_begin = stack_offset;
+								child.list_size = 0;
+								child.depth_remaining = static_cast<int16_t>(f.depth_remaining - 1);
+								child.alpha = sc_invert(f.beta, -1);
+								child.beta = sc_invert(f.alpha, -1);
+								child.is_fully_expanded = 0;
+								f.move = mv;
+								dyn_add_move(d, (mv >> 2) & 127, (mv >> 9) & 127, mv & 3);
+								top++;
+								entering = true;
+								descended = true;
+								break;
+							}
+						}
+						const uint16_t s = as[i];
+						if (s > f.best_score)
+							f.best_score = s;
+						if (s > f.alpha)
+						{
+							f.alpha = s;
+							f.best_move = am[i];
+						}
+						if (s >= f.beta or sc_is_win(s))
+							break;
+						f.index++;
+					}
+					if (descended)
+						continue;
+
+					// after the loop (AlphaBetaSearch.cpp:317-339)
+					if (f.list_size == 0 or (sc_is_loss(f.best_score) and not f.is_fully_expanded))
+						f.best_score = static_evaluation(d.v);
+					int bound;
+					if (f.best_score <= f.original_alpha)
+						bound = BOUND_UPPER;
+					else
+						bound = (f.best_score >= f.beta) ? BOUND_LOWER : BOUND_EXACT;
+					tt_insert(tt, key_lo, key_hi, tt_pack(bound, f.depth_remaining, f.best_score, f.best_move));
+					returned = f.best_score;
+					if (top > 0)
+						stack_offset -= f.list_size;
+					top--;
+				}
+				result = returned;
+				if (root_size == 0 or sc_is_proven(result) or out.node_counter >= max_nodes or stack_max_offset == max_offset_before)
+					break;
+			}
+			out.score = result;
+			out.n_actions = root_size;
+			out.overflow |= d.overflow;
+			return out;
+		}
+	}
+}

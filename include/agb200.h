@@ -77,11 +77,13 @@ typedef struct AgbConfig
 	float information_leak_threshold; /* TreeConfig (0.01) */
 	float policy_expansion_threshold; /* MCTSConfig (1e-4) */
 	int32_t max_children; /* MCTSConfig::max_children; <= 0 means unlimited */
-	int32_t solver_max_positions; /* TSSConfig::max_positions */
+	int32_t solver_max_positions; /* TSSConfig::max_positions: 0 = no solver, 1 = static move generator + evaluation, n = alpha-beta search of n positions */
 	int32_t use_symmetries; /* SelfplayConfig::use_symmetries */
 	uint64_t seed; /* base seed; per-game streams are keyed by (seed, global game id) */
 	int32_t first_game_id; /* global id of this engine's game 0 (rank * games when sharded) */
-	int32_t reserved[7];
+	int32_t solver_table_entries; /* entries of each game's solver transposition table (power of two; 0 = 65536; the reference uses 4 Mi,
+	                                 AlphaBetaSearch.cpp:55) */
+	int32_t reserved[6];
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -145,6 +147,12 @@ int agb_evaluate(AgbEngine *engine, const int8_t *boards_host, const int8_t *sig
 /* ---- lockstep self-play (GameGenerator::generate, src/selfplay/GameGenerator.cpp:46-121, over all games) ------- */
 /* start (or restart) all games from given positions: boards[games][cells], sign_to_move[games]; NULL = empty boards, cross to move */
 int agb_selfplay_reset(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host);
+/* replace the Zobrist words of the solver's transposition tables: keys[2 * rows * cols][2] = (low, high) 64-bit word of
+ * (cell, CROSS) then (cell, CIRCLE), i.e. FastZobristHashing::m_keys (include/alphagomoku/search/ZobristHashing.hpp:111-127).
+ * The words only decide which bucket a position maps to; parity tests pass the reference's own so that bucket replacement
+ * (SharedHashTable::insert, SharedHashTable.hpp:160-181) sees the same collisions. n_words = 4 * rows * cols for one set shared by all
+ * games, or games times that for one set per game (the reference has one per GameGenerator). Call before agb_selfplay_reset. */
+int agb_set_solver_keys(AgbEngine *engine, const uint64_t *keys_host, size_t n_words);
 /* advance every game by n_steps lockstep iterations of select -> solve/encode -> evaluate -> expand -> backup (-> move) */
 int agb_step(AgbEngine *engine, int n_steps);
 /* pop finished-game records (GameDataStorage::serialize, src/dataset/GameDataStorage.cpp:217-251, format 201) */

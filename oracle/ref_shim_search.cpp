@@ -4,6 +4,17 @@
 // make_move / prepare_search (src/selfplay/GameGenerator.cpp:46-185) made synchronous and started from a given position;
 // `use_solver = 0` leaves out the Search::solve() call so that the tree kernels can be compared before the device solver
 // exists (tasks then take the "not processed by solver" path of UnifiedGenerator, EdgeGenerator.cpp:269-303).
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+// the solver's hash keys are private to AlphaBetaSearch; tests need them to give the device table the same bucket mapping
+#define private public
+#include <alphagomoku/search/alpha_beta/AlphaBetaSearch.hpp>
+#undef private
 #include <alphagomoku/dataset/GameDataBuffer.hpp>
 #include <alphagomoku/dataset/GameDataStorage.hpp>
 #include <alphagomoku/dataset/data_packs.hpp>
@@ -286,41 +297,105 @@ extern "C"
 		}
 		return buffer.numberOfGames();
 	}
-	// AlphaBetaSearch::solve (AlphaBetaSearch.cpp:77-156) on one position with a node limit; outputs the task's edge list (in
-	// order), their scores, the position score and flags (bit0 must_defend, bit1 statically solved, bit2 recursively solved)
-	int agref_solve(int rules, int rows, int cols, int draw_after, const int8_t *board, int sign_to_move, int max_nodes, uint16_t *moves,
-			uint16_t *scores, uint16_t *result_score, int32_t *flags)
+	// ---- AlphaBetaSearch as a persistent object: transposition table and generation survive between calls -------------------------
+	namespace
 	{
-		static std::unique_ptr<AlphaBetaSearch> solver;
-		static GameConfig solver_config;
+		void export_keys(const AlphaBetaSearch &solver, int rows, int cols, uint64_t *keys)
+		{ // [2 * cells][2]: low and high word of FastZobristHashing's key of (cell, CROSS) then (cell, CIRCLE)
+			for (int r = 0; r < rows; r++)
+				for (int c = 0; c < cols; c++)
+					for (int s = 1; s <= 2; s++)
+					{
+						HashKey128 k;
+						solver.shared_table.getHashFunction().updateHash(k, Move(r, c, static_cast<Sign>(s)));
+						keys[2 * (2 * (r * cols + c) + s - 1) + 0] = k.getLow();
+						keys[2 * (2 * (r * cols + c) + s - 1) + 1] = k.getHigh();
+					}
+		}
+		int run_solver(AlphaBetaSearch &solver, const GameConfig &gc, const int8_t *board, int sign_to_move, int max_nodes, uint16_t *moves, uint16_t *scores,
+				uint16_t *result_score, int32_t *flags)
+		{
+			matrix<Sign> b(gc.rows, gc.cols);
+			for (int i = 0; i < gc.rows * gc.cols; i++)
+				b[i] = static_cast<Sign>(board[i]);
+			SearchTask task(gc);
+			task.set(b, static_cast<Sign>(sign_to_move));
+			solver.setDepthLimit(100); // Search::solve (Search.cpp:160-169)
+			solver.setNodeLimit(max_nodes);
+			solver.setTimeLimit(std::numeric_limits<double>::max());
+			const int nodes = solver.solve(task);
+			int n = 0;
+			for (const Edge &e : task.getEdges())
+			{
+				const Move m = e.getMove();
+				moves[n] = m.toShort();
+				scores[n] = Score::to_short(task.getActionScores().at(m.row, m.col));
+				n++;
+			}
+			*result_score = Score::to_short(task.getScore());
+			*flags = static_cast<int>(task.mustDefend()) | (static_cast<int>(task.wasStaticallySolved()) << 1) | (static_cast<int>(task.wasRecursivelySolved()) << 2)
+					| (nodes << 8);
+			return n;
+		}
+		struct RefSolver
+		{
+				GameConfig gc;
+				AlphaBetaSearch solver;
+				RefSolver(const GameConfig &cfg) :
+						gc(cfg),
+						solver(cfg)
+				{
+				}
+		};
+	}
+	void* agref_solver_create(int rules, int rows, int cols, int draw_after)
+	{
 		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
 		if (draw_after > 0)
 			gc.draw_after = draw_after;
-		if (solver == nullptr or solver_config.rules != gc.rules or solver_config.rows != gc.rows or solver_config.draw_after != gc.draw_after)
-		{
-			solver = std::make_unique<AlphaBetaSearch>(gc);
-			solver_config = gc;
-		}
-		matrix<Sign> b(rows, cols);
-		for (int i = 0; i < rows * cols; i++)
-			b[i] = static_cast<Sign>(board[i]);
-		SearchTask task(gc);
-		task.set(b, static_cast<Sign>(sign_to_move));
-		solver->clear();
-		solver->setDepthLimit(100);
-		solver->setNodeLimit(max_nodes);
-		solver->setTimeLimit(1.0e30);
-		solver->solve(task);
-		int n = 0;
-		for (const Edge &e : task.getEdges())
-		{
-			const Move m = e.getMove();
-			moves[n] = m.toShort();
-			scores[n] = Score::to_short(task.getActionScores().at(m.row, m.col));
-			n++;
-		}
-		*result_score = Score::to_short(task.getScore());
-		*flags = static_cast<int>(task.mustDefend()) | (static_cast<int>(task.wasStaticallySolved()) << 1) | (static_cast<int>(task.wasRecursivelySolved()) << 2);
-		return n;
+		return new RefSolver(gc);
+	}
+	void agref_solver_destroy(void *h)
+	{
+		delete static_cast<RefSolver*>(h);
+	}
+	void agref_solver_keys(void *h, uint64_t *keys)
+	{
+		RefSolver *s = static_cast<RefSolver*>(h);
+		export_keys(s->solver, s->gc.rows, s->gc.cols, keys);
+	}
+	void agref_solver_next_generation(void *h)
+	{
+		static_cast<RefSolver*>(h)->solver.increaseGeneration();
+	}
+	void agref_solver_clear(void *h)
+	{
+		static_cast<RefSolver*>(h)->solver.clear();
+	}
+	// flags: bit0 must_defend, bit1 statically solved, bit2 recursively solved, bits 8.. node count
+	int agref_solver_solve(void *h, const int8_t *board, int sign_to_move, int max_nodes, uint16_t *moves, uint16_t *scores, uint16_t *result_score,
+			int32_t *flags)
+	{
+		RefSolver *s = static_cast<RefSolver*>(h);
+		return run_solver(s->solver, s->gc, board, sign_to_move, max_nodes, moves, scores, result_score, flags);
+	}
+	void agref_sp_solver_keys(void *h, uint64_t *keys)
+	{
+		RefSelfplay *sp = static_cast<RefSelfplay*>(h);
+		export_keys(sp->search.getSolver(), sp->game_config.rows, sp->game_config.cols, keys);
+	}
+	// AlphaBetaSearch::solve (AlphaBetaSearch.cpp:77-156) on one position with a node limit and a cleared table; outputs the task's edge
+	// list (in order), their scores, the position score and flags (as above)
+	int agref_solve(int rules, int rows, int cols, int draw_after, const int8_t *board, int sign_to_move, int max_nodes, uint16_t *moves,
+			uint16_t *scores, uint16_t *result_score, int32_t *flags)
+	{
+		static std::unique_ptr<RefSolver> solver;
+		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
+		if (draw_after > 0)
+			gc.draw_after = draw_after;
+		if (solver == nullptr or solver->gc.rules != gc.rules or solver->gc.rows != gc.rows or solver->gc.draw_after != gc.draw_after)
+			solver = std::make_unique<RefSolver>(gc);
+		solver->solver.clear();
+		return run_solver(solver->solver, solver->gc, board, sign_to_move, max_nodes, moves, scores, result_score, flags);
 	}
 }

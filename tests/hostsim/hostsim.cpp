@@ -98,7 +98,7 @@ extern "C" size_t hostsim_serialize_sample_v201(int cells, const int8_t *board, 
 	return agb::records::serialize_sample_v201(out, cells, board, visits, prior, win, draw, scores, minimax_score, flags);
 }
 
-#include "../../alphagomoku_b200/csrc/solver_logic.cuh"
+#include "../../alphagomoku_b200/csrc/solver_search.cuh"
 // sequential model of "K1 state -> K5 static solve" for one position (the device runs the same functions, one thread per task)
 extern "C" void hostsim_defensive_table(int rules, uint16_t *table)
 {
@@ -155,4 +155,106 @@ extern "C" int hostsim_solve_static(int rules, int S, int draw_after, const int8
 	*result_score = res.score;
 	*flags = static_cast<int>(res.must_defend) | (static_cast<int>(res.has_initiative) << 3);
 	return res.n_actions;
+}
+
+// sequential model of one game's solver: K1 state -> K5 search (solve_position) with a persistent transposition table
+struct HostSolver
+{
+		int rules, S, draw_after;
+		std::vector<uint8_t> pattern_table, threat_table;
+		std::vector<uint16_t> def_table;
+		std::vector<uint64_t> keys, table;
+		int generation = 0;
+		std::vector<uint16_t> stack_moves, stack_scores;
+		std::vector<agb::solver::Frame> frames;
+};
+extern "C" void* hostsim_solver_create(int rules, int S, int draw_after, const uint8_t *pattern_table, const uint8_t *threat_table, const uint16_t *def_table,
+		const uint64_t *keys, size_t table_entries)
+{
+	HostSolver *h = new HostSolver();
+	h->rules = rules;
+	h->S = S;
+	h->draw_after = draw_after > 0 ? draw_after : S * S;
+	h->pattern_table.assign(pattern_table, pattern_table + (1 << 20));
+	h->threat_table.assign(threat_table, threat_table + 4096);
+	h->def_table.assign(def_table, def_table + agb::solver::kDefGroups * 256 * 2);
+	h->keys.assign(keys, keys + 4 * S * S);
+	h->table.resize(2 * table_entries);
+	agb::solver::tt_clear(h->table.data(), table_entries);
+	h->stack_moves.resize(S * S + 8192);
+	h->stack_scores.resize(S * S + 8192);
+	h->frames.resize(agb::solver::kMaxFrames);
+	return h;
+}
+extern "C" void hostsim_solver_destroy(void *p)
+{
+	delete static_cast<HostSolver*>(p);
+}
+extern "C" void hostsim_solver_next_generation(void *p)
+{
+	HostSolver *h = static_cast<HostSolver*>(p);
+	h->generation = (h->generation + 1) % 64;
+}
+extern "C" void hostsim_solver_clear(void *p)
+{
+	HostSolver *h = static_cast<HostSolver*>(p);
+	agb::solver::tt_clear(h->table.data(), h->table.size() / 2);
+}
+extern "C" int hostsim_solver_solve(void *p, const int8_t *board_in, int stm, int max_nodes, uint16_t *moves, uint16_t *scores, uint16_t *result_score,
+		int32_t *flags)
+{
+	using namespace agb::solver;
+	HostSolver *h = static_cast<HostSolver*>(p);
+	const int S = h->S, cells = S * S;
+	std::vector<int8_t> board(board_in, board_in + cells);
+	std::vector<uint64_t> lines(kMaxLines);
+	for (int l = 0; l < line_count(S); l++)
+		lines[l] = build_line(board.data(), S, l);
+	std::vector<uint32_t> ptypes(cells, 0);
+	std::vector<uint8_t> threats(cells, 0);
+	std::vector<int32_t> hist_count(2 * kHistTypes, 0);
+	std::vector<uint16_t> hist_cells(2 * kHistTypes * cells, 0);
+	int stones = 0;
+	for (int r = 0; r < S; r++)
+		for (int c = 0; c < S; c++)
+		{ // PatternCalculator::setBoard: classify, then fill the lists in row-major order
+			const int idx = r * S + c;
+			stones += (board[idx] != NONE);
+			if (board[idx] != NONE)
+				continue;
+			ptypes[idx] = classify_cell(lines.data(), h->pattern_table.data(), r, c, S);
+			threats[idx] = threat_of_cell(ptypes[idx], h->threat_table.data());
+			for (int colour = 0; colour < 2; colour++)
+			{
+				const int t = (threats[idx] >> (4 * colour)) & 15;
+				if (t != TT_NONE)
+					hist_cells[(colour * kHistTypes + t) * cells + hist_count[colour * kHistTypes + t]++] = mk_loc(r, c);
+			}
+		}
+	DynState d;
+	d.v = View { S, cells, h->rules, stm, stones, h->draw_after, cells, board.data(), lines.data(), ptypes.data(), threats.data(), nullptr, hist_count.data(),
+			hist_cells.data(), h->pattern_table.data(), h->def_table.data(), &d };
+	d.board = board.data();
+	d.lines = lines.data();
+	d.ptypes = ptypes.data();
+	d.threats = threats.data();
+	d.hist_count = hist_count.data();
+	d.hist_cells = hist_cells.data();
+	d.threat_table = h->threat_table.data();
+	if (h->rules == RULE_RENJU)
+	{ // NNInputFeatures::encode runs first in AlphaBetaSearch::solve and asks isForbidden for every empty cell in row-major order
+		encode_forbidden_pass(d);
+	}
+	HashTable tt { h->table.data(), h->table.size() / 8 - 1, h->generation, h->keys.data() };
+	SearchMemory mem { h->stack_moves.data(), h->stack_scores.data(), static_cast<int>(h->stack_moves.size()), h->frames.data() };
+	const SearchOutput out = solve_position(d, tt, mem, max_nodes, 100);
+	for (int i = 0; i < out.n_actions; i++)
+	{
+		moves[i] = mem.stack_moves[i];
+		scores[i] = mem.stack_scores[i];
+	}
+	*result_score = out.score;
+	*flags = static_cast<int>(out.must_defend) | (static_cast<int>(out.node_counter <= 1) << 1) | (static_cast<int>(sc_is_proven(out.score)) << 2)
+			| (out.node_counter << 8) | (out.overflow ? (1 << 30) : 0);
+	return out.n_actions;
 }

@@ -150,6 +150,12 @@ class RefSelfplay:
         return dict(zip(["nb_network_evaluations", "nb_node_count", "nb_duplicate_nodes", "nb_information_leaks", "nb_proven_states",
                          "nb_wasted_expansions"], out.tolist()))
 
+    def solver_keys(self):
+        """Zobrist words of this instance's AlphaBetaSearch table: uint64 [2 * cells, 2] (low, high)."""
+        keys = np.zeros((2 * self.cells, 2), np.uint64)
+        self.lib.agref_sp_solver_keys(self.h, _p(keys))
+        return keys
+
     def record(self):
         """GameDataStorage::serialize of the game (complete after step() returned 2)."""
         self.lib.agref_sp_record.restype = ctypes.c_size_t

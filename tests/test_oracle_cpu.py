@@ -298,3 +298,48 @@ def test_static_solver_renju_matches_reference_up_to_order(ref_fast, hostsim):
         a, b = _solve_both(ref, hostsim, tables, 2, 15, board, stm)
         assert a[2:] == b[2:], (i, a[2:], b[2:])
         assert sorted(zip(a[0].tolist(), a[1].tolist())) == sorted(zip(b[0].tolist(), b[1].tolist())), i
+
+
+@pytest.mark.parametrize("rules,size,max_nodes,use_fast", [(0, 15, 100, False), (1, 15, 100, False), (3, 20, 60, False), (4, 15, 400, False),
+                                                             (2, 15, 100, True), (2, 15, 1, True)])
+def test_alpha_beta_solver_matches_reference(ref, ref_fast, hostsim, rules, size, max_nodes, use_fast):
+    """AlphaBetaSearch::solve with its transposition table kept between positions and generations (AlphaBetaSearch.cpp:77-339,
+    SharedHashTable.hpp:27-220) against the host-compiled K5 search (solver_search.cuh): the same hash keys and table size, then the same
+    action order, action scores, position score, flags and node count for every position of a sequence. RENJU also pins the ORDER of the
+    threat lists after forbidden-move checks; it runs on the reference's Release build (its debug build asserts on unreachable boards)."""
+    oracle = ref_fast if use_fast else ref
+    lib = oracle.lib
+    lib.agref_solver_create.restype = ctypes.c_void_p
+    hostsim.hostsim_solver_create.restype = ctypes.c_void_p
+    tables = _solver_tables(hostsim, rules)
+    cells = size * size
+    rh = ctypes.c_void_p(lib.agref_solver_create(rules, size, size, 0))
+    keys = np.zeros(4 * cells, np.uint64)
+    lib.agref_solver_keys(rh, _p(keys))
+    entries = 4 * 1024 * 1024  # AlphaBetaSearch.cpp:55
+    hh = ctypes.c_void_p(hostsim.hostsim_solver_create(rules, size, 0, _p(tables[0]), _p(tables[1]), _p(tables[2]), _p(keys), ctypes.c_size_t(entries)))
+    rng = np.random.default_rng(500 + 7 * rules + max_nodes)
+    boards = random_boards(rng, size, 150, max_fill=0.45)
+    total_nodes = 0
+    for i, board in enumerate(boards):
+        stm = 1 if (np.count_nonzero(board) % 2 == 0) else 2
+        res = []
+        for which in range(2):
+            moves, scores = np.zeros(cells, np.uint16), np.zeros(cells, np.uint16)
+            result, flags = np.zeros(1, np.uint16), np.zeros(1, np.int32)
+            if which == 0:
+                n = lib.agref_solver_solve(rh, _p(board), stm, max_nodes, _p(moves), _p(scores), _p(result), _p(flags))
+            else:
+                n = hostsim.hostsim_solver_solve(hh, _p(board), stm, max_nodes, _p(moves), _p(scores), _p(result), _p(flags))
+            res.append((moves[:n].copy(), scores[:n].copy(), int(result[0]), int(flags[0])))
+        a, b = res
+        assert np.array_equal(a[0], b[0]), (i, a[0], b[0])
+        assert np.array_equal(a[1], b[1]), i
+        assert a[2:] == b[2:], (i, hex(a[2]), hex(b[2]), hex(a[3]), hex(b[3]))
+        total_nodes += a[3] >> 8
+        if i % 7 == 6:  # a new search (Search::setBoard) starts a new table generation
+            lib.agref_solver_next_generation(rh)
+            hostsim.hostsim_solver_next_generation(hh)
+    assert total_nodes > 150 or max_nodes == 1
+    lib.agref_solver_destroy(rh)
+    hostsim.hostsim_solver_destroy(hh)

@@ -31,7 +31,10 @@ def _openings(rng, size, n):
 @pytest.mark.parametrize("rules,q_head,init_to,batch,sims,solver", [
     (0, False, "parent", 4, 60, 0), (1, True, "q_head", 8, 80, 0), (2, False, "parent", 3, 50, 0), (0, False, "loss", 1, 55, 0),
     # K5 on: Search::solve with tss max_positions = 1 (static solver) on every leaf, proven leaves skip the network
-    (0, False, "parent", 4, 60, 1), (1, True, "q_head", 8, 80, 1), (4, False, "parent", 5, 70, 1), (3, True, "q_head", 2, 55, 1)])
+    (0, False, "parent", 4, 60, 1), (1, True, "q_head", 8, 80, 1), (4, False, "parent", 5, 70, 1), (3, True, "q_head", 2, 55, 1),
+    # alpha-beta search with the per-game transposition table (tss max_positions > 1), renju with forbidden moves in the solver
+    (0, False, "parent", 4, 60, 100), (1, True, "q_head", 8, 80, 100), (4, False, "parent", 3, 55, 30), (2, False, "parent", 4, 60, 1),
+    (2, True, "q_head", 8, 80, 100)])
 def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, batch, sims, solver):
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
@@ -41,7 +44,8 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
     # short games, so that game ends, restarts and finished-game records are exercised too (longer with the solver, so that real threats appear)
     draw_after = 14 if solver == 0 else 28
     eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
-                     games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver)
+                     games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver,
+                     solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0)  # the reference's table size (AlphaBetaSearch.cpp:55)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
     def evaluate(features):
@@ -49,13 +53,19 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
 
     rng = np.random.default_rng(rules + 17)
     boards, stm = _openings(rng, size, games)
-    eng.selfplay_reset(boards, stm)
     refs = []
+    # renju with the solver: the reference's debug build asserts in MoveGenerator.cpp:999 whenever black can win in one move, so that
+    # case runs its Release build (nothing on this path draws random numbers once the hash keys are shared)
+    fast = solver > 0 and rules == 2
     for g in range(games):
         r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=solver > 0,
-                                solver_max_positions=max(solver, 1), draw_after=draw_after)
-        r.set_position(boards[g], stm[g])
+                                solver_max_positions=max(solver, 1), draw_after=draw_after, fast=fast)
         refs.append(r)
+    if solver > 0:
+        eng.set_solver_keys(np.stack([r.solver_keys() for r in refs]))
+    eng.selfplay_reset(boards, stm)
+    for g in range(games):
+        refs[g].set_position(boards[g], stm[g])
     active = [True] * games
     moves_checked = 0
     ref_records = []
