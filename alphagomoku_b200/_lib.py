@@ -20,7 +20,7 @@ class AgbConfig(ctypes.Structure):
         ("policy_expansion_threshold", ctypes.c_float), ("max_children", ctypes.c_int32),
         ("solver_max_positions", ctypes.c_int32), ("use_symmetries", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("solver_table_entries", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 6),
+        ("pipeline_groups", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
     ]
 
 
@@ -30,7 +30,7 @@ class AgbStats(ctypes.Structure):
         ("nb_information_leaks", ctypes.c_uint64), ("nb_proven_states", ctypes.c_uint64), ("nb_wasted_expansions", ctypes.c_uint64),
         ("nb_moves_played", ctypes.c_uint64), ("nb_games_finished", ctypes.c_uint64), ("nb_kernel_launches", ctypes.c_uint64),
         ("overflow_flags", ctypes.c_uint64), ("nn_kernel_ns", ctypes.c_uint64), ("nn_kernel_launches", ctypes.c_uint64),
-        ("nn_positions", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 3),
+        ("nn_positions", ctypes.c_uint64), ("solver_kernel_ns", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 2),
     ]
 
 

@@ -4,8 +4,10 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define AGB_HD __host__ __device__
+#define AGB_HD_NOINLINE __host__ __device__ __noinline__ // keeps the single-lane solver's code small enough for the instruction cache
 #else
 #define AGB_HD
+#define AGB_HD_NOINLINE
 #endif
 
 namespace agb

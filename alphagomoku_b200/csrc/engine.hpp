@@ -20,6 +20,7 @@ struct AgbEngine
 		std::string error;
 		uint64_t launches = 0;
 		uint64_t nn_kernel_ns = 0, nn_kernel_launches = 0, nn_positions = 0; // device timing of K4 inside agb_step
+		uint64_t solver_kernel_ns = 0; // device timing of K5 inside agb_step
 		std::vector<cudaEvent_t> events; // reusable event pool for that timing
 
 		// static tables
@@ -82,12 +83,14 @@ namespace agb
 	int solver_state_create(AgbEngine *e, int games, int batch, SolverState *st);
 	int solver_state_reset(AgbEngine *e, SolverState *st);
 	void solver_state_destroy(SolverState *st);
-	int launch_solve_games(AgbEngine *e, const SolverState &st, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count);
+	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
+			int *nn_count, cudaStream_t stream);
 	// tables.cu
 	int build_tables(AgbEngine *e);
 	// patterns.cu
 	int launch_set_boards(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, int n, uint32_t *features_dev);
-	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev);
+	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev,
+			int slot_base = 0, cudaStream_t stream = nullptr);
 	int launch_add_undo(AgbEngine *e, const uint16_t *moves_dev, int n, bool undo);
 	int launch_encode(AgbEngine *e, int n, uint32_t *features_dev);
 	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse);

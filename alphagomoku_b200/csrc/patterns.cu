@@ -408,10 +408,29 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
 	}
-	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev)
-	{
-		set_boards_kernel<<<grid_for(max_n), kWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, boards_dev, stm_dev, max_n, e->cfg.rows, e->cfg.rules,
-				features_dev, e->d_status, n_dev);
+	BoardStore store_at(const BoardStore &s, int slot)
+	{ // the store seen from `slot` on: slot i of the result is slot (slot + i) of `s`
+		BoardStore r = s;
+		const size_t b = static_cast<size_t>(slot);
+		r.capacity = s.capacity - slot;
+		r.board += b * kCellPitch;
+		r.sign_to_move += b;
+		r.lines += b * kLinePitch;
+		r.ptypes += b * kCellPitch;
+		r.threats += b * kCellPitch;
+		r.forbidden += b * kCellPitch;
+		r.hist_count += b * 2 * kHistTypes;
+		r.hist_cells += b * 2 * kHistTypes * kCellPitch;
+		return r;
+	}
+	int launch_set_boards_counted(AgbEngine *e, const int8_t *boards_dev, const int8_t *stm_dev, const int *n_dev, int max_n, uint32_t *features_dev,
+			int slot_base, cudaStream_t stream)
+	{ // slots [slot_base, slot_base + *n_dev) of the store, the board / sign / feature arrays being indexed by slot as well
+		if (stream == nullptr)
+			stream = e->stream;
+		const size_t off = static_cast<size_t>(slot_base);
+		set_boards_kernel<<<grid_for(max_n), kWarpsPerBlock * 32, 0, stream>>>(store_at(e->store, slot_base), e->tables, boards_dev + off * e->cells, stm_dev + off,
+				max_n, e->cfg.rows, e->cfg.rules, features_dev + off * e->cells, e->d_status, n_dev);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

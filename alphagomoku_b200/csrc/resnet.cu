@@ -65,6 +65,7 @@ namespace agb
 			int n_boards;
 			const int *n_boards_dev; // if set, the batch size is read from device memory
 			const int *gather; // if set, board i of this launch lives in slot gather[i] of the feature / output arrays
+			int slot_base; // otherwise board i lives in slot slot_base + i
 			long long *trace; // optional [n_layers][4] clock64 stamps of CTA 0's first board (AGB_NET_TRACE)
 	};
 
@@ -346,7 +347,7 @@ namespace agb
 				{
 					const int bi = b0 + rank; // this CTA's board in the launch
 					const bool live = bi < n_boards;
-					const int b = (live and prm.gather != nullptr) ? prm.gather[bi] : bi; // its slot in the feature / output arrays // an odd batch leaves the last peer without a board: it still runs every barrier
+					const int b = (live and prm.gather != nullptr) ? prm.gather[bi] : bi + prm.slot_base; // its slot in the feature / output arrays // an odd batch leaves the last peer without a board: it still runs every barrier
 					// ---- prologue: feature words -> bf16 stem image (32 channels, halo 2) in the h buffer ----
 					for (uint32_t i = et; i < 4 * in_chunk_bytes / 16; i += kEpilogueThreads)
 						reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
@@ -601,7 +602,7 @@ namespace agb
 		// one CTA per board, D threads; 0.02 % of the network's FLOPs
 		__global__ void value_head_kernel(const float *__restrict__ hidden, const float *__restrict__ wd1, const float *__restrict__ bd1,
 				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D, const int *__restrict__ n_dev,
-				const int *__restrict__ gather)
+				const int *__restrict__ gather, int slot_base)
 		{
 			if (n_dev != nullptr)
 				n = *n_dev;
@@ -609,7 +610,7 @@ namespace agb
 			float *sx = sh, *sd = sh + in_dim;
 			for (int bi = blockIdx.x; bi < n; bi += gridDim.x)
 			{
-				const int b = gather ? gather[bi] : bi;
+				const int b = gather ? gather[bi] : bi + slot_base;
 				for (int i = threadIdx.x; i < in_dim; i += blockDim.x)
 					sx[i] = hidden[static_cast<size_t>(b) * in_dim + i];
 				__syncthreads();
@@ -825,8 +826,10 @@ namespace agb
 	}
 
 	int net_forward_impl(AgbEngine *e, const uint32_t *features_dev, int n_boards, const int *n_dev, const int *gather_dev, float *policy_dev, float *value_dev,
-			float *q_dev)
+			float *q_dev, int slot_base = 0, cudaStream_t stream = nullptr)
 	{
+		if (stream == nullptr)
+			stream = e->stream;
 		NetWeights *n = e->net;
 		if (n == nullptr or not n->loaded)
 			return e->fail(AGB_ESTATE, "no weights loaded");
@@ -837,6 +840,7 @@ namespace agb
 		p.n_boards = n_boards;
 		p.n_boards_dev = n_dev;
 		p.gather = gather_dev;
+		p.slot_base = slot_base;
 		static long long *d_trace = nullptr;
 		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
 		if (trace and d_trace == nullptr)
@@ -847,15 +851,15 @@ namespace agb
 		const int pairs = std::min((n_boards + 1) / 2, sms / 2);
 		const int grid = 2 * pairs; // clusters of two CTAs, one board each
 		if (p.F == 128)
-			resnet_board_kernel<128><<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
+			resnet_board_kernel<128><<<grid, kThreads, n->smem_bytes, stream>>>(p);
 		else
-			resnet_board_kernel<64><<<grid, kThreads, n->smem_bytes, e->stream>>>(p);
+			resnet_board_kernel<64><<<grid, kThreads, n->smem_bytes, stream>>>(p);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		if (trace)
 		{
 			std::vector<long long> h(kMaxConvLayers * 6);
-			cudaStreamSynchronize(e->stream);
+			cudaStreamSynchronize(stream);
 			cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
 			FILE *f = fopen(getenv("AGB_NET_TRACE"), "w");
 			if (f)
@@ -867,8 +871,8 @@ namespace agb
 			}
 		}
 		const int cells = e->cells, D = n->dense_width;
-		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, e->stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
-				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev, gather_dev);
+		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
+				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev, gather_dev, slot_base);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
@@ -882,9 +886,9 @@ namespace agb
 		return net_forward_impl(e, features_dev, n_boards, nullptr, nullptr, policy_dev, value_dev, q_dev);
 	}
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
-			float *value_dev, float *q_dev)
+			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream)
 	{
-		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev);
+		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev, slot_base, stream);
 	}
 }
 

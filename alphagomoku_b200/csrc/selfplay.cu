@@ -119,6 +119,7 @@ namespace agb
 			int32_t path_edge[kMaxPath];
 	};
 
+	constexpr int kMaxGroups = 2;
 	struct SelfplayState
 	{
 			int games = 0, batch = 0, cells = 0, S = 0;
@@ -148,6 +149,12 @@ namespace agb
 			int32_t *nn_list = nullptr, *nn_count = nullptr; // slots that go to the network when the solver is on
 			SolverOutputs solver_out { };
 			SolverState solver { }; // per-game search memory (solver.cu)
+			// pipeline groups: the games are split into `groups` independent halves that advance on their own streams, so that the
+			// solver / tree kernels of one half overlap the network kernel of the other (the network launches share one stream)
+			int groups = 1;
+			cudaStream_t group_stream[2] = { nullptr, nullptr };
+			cudaStream_t nn_stream = nullptr;
+			cudaEvent_t ready[2] = { nullptr, nullptr }, evaluated[2] = { nullptr, nullptr }, joined = nullptr;
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
 			uint64_t *zobrist = nullptr; // [cells][2] + [2]
@@ -185,7 +192,10 @@ namespace agb
 				int max_simulations, init_to;
 				float exploration_constant, leak_threshold;
 				int q_head;
-				int solver_mode; // 0: terminal checks in K7, 1: K5 static solver on every leaf
+				int solver_mode; // 0: terminal checks in K7, 1: K5 solver on every leaf
+				// pipeline group served by this launch: games [game_begin, game_begin + game_count), evaluation slots from slot_base on
+				int game_begin, game_count, slot_base;
+				int32_t *eval_count; // this group's slot counter
 				Tables tables;
 				BoardStore store;
 				uint32_t *status;
@@ -299,9 +309,9 @@ namespace agb
 		__global__ void __launch_bounds__(128) select_kernel(const __grid_constant__ Params p)
 		{
 			const int lane = threadIdx.x & 31;
-			const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
-			if (g >= p.s.games)
+			if (blockIdx.x * 4 + (threadIdx.x >> 5) >= p.game_count)
 				return;
+			const int g = p.game_begin + blockIdx.x * 4 + (threadIdx.x >> 5);
 			const int cells = p.s.cells, S = p.s.S;
 			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
 			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
@@ -510,7 +520,7 @@ namespace agb
 				int slot = 0;
 				if (lane == 0)
 				{
-					slot = atomicAdd(p.s.eval_count, 1);
+					slot = p.slot_base + atomicAdd(p.eval_count, 1);
 					task.nn_slot = slot;
 					p.s.task_stm[slot] = task.stm;
 					p.s.slot_is_root[slot] = (task.path_len == 0) ? 1 : 0;
@@ -552,9 +562,9 @@ namespace agb
 		__global__ void __launch_bounds__(128) expand_backup_kernel(const __grid_constant__ Params p)
 		{
 			const int lane = threadIdx.x & 31;
-			const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
-			if (g >= p.s.games)
+			if (blockIdx.x * 4 + (threadIdx.x >> 5) >= p.game_count)
 				return;
+			const int g = p.game_begin + blockIdx.x * 4 + (threadIdx.x >> 5);
 			const int cells = p.s.cells, S = p.s.S;
 			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
 			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
@@ -906,9 +916,9 @@ namespace agb
 		{
 			__shared__ int8_t sboards[4][kCellPitch];
 			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-			const int g = blockIdx.x * 4 + warp;
-			if (g >= p.s.games)
+			if (blockIdx.x * 4 + warp >= p.game_count)
 				return;
+			const int g = p.game_begin + blockIdx.x * 4 + warp;
 			const int cells = p.s.cells, S = p.s.S;
 			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
 			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
@@ -1246,6 +1256,10 @@ namespace agb
 			p.leak_threshold = e->cfg.information_leak_threshold;
 			p.q_head = e->cfg.q_head;
 			p.solver_mode = e->cfg.solver_max_positions > 0 ? 1 : 0;
+			p.game_begin = 0;
+			p.game_count = e->selfplay->games;
+			p.slot_base = 0;
+			p.eval_count = e->selfplay->eval_count;
 			p.tables = e->tables;
 			p.store = e->store;
 			p.status = e->d_status;
@@ -1254,7 +1268,7 @@ namespace agb
 	}
 
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
-			float *value_dev, float *q_dev);
+			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream);
 
 	int selfplay_create(AgbEngine *e)
 	{
@@ -1302,10 +1316,10 @@ namespace agb
 		alloc(&s->tasks, T);
 		alloc(&s->task_boards, T * cells);
 		alloc(&s->task_stm, T);
-		alloc(&s->eval_count, 1);
+		alloc(&s->eval_count, kMaxGroups);
 		alloc(&s->slot_is_root, T);
 		alloc(&s->nn_list, T);
-		alloc(&s->nn_count, 1);
+		alloc(&s->nn_count, kMaxGroups);
 		s->solver_out.pitch = static_cast<int>(cells);
 		alloc(&s->solver_out.moves, T * cells);
 		alloc(&s->solver_out.scores, T * cells);
@@ -1338,6 +1352,20 @@ namespace agb
 			ok = cudaMemset(s->tasks, 0, T * sizeof(TaskD)) == cudaSuccess; // sticky per-slot flags start cleared
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
+		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : ((c.solver_max_positions > 0 and c.games >= 2) ? 2 : 1);
+		if (s->groups > kMaxGroups or s->groups > c.games)
+			return e->fail(AGB_EINVAL, "pipeline_groups must be 1 or 2 and not exceed the number of games");
+		if (s->groups > 1)
+		{
+			for (int k = 0; k < s->groups; k++)
+			{
+				AGB_CUDA_CHECK(e, cudaStreamCreateWithFlags(&s->group_stream[k], cudaStreamNonBlocking));
+				AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->ready[k], cudaEventDisableTiming));
+				AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->evaluated[k], cudaEventDisableTiming));
+			}
+			AGB_CUDA_CHECK(e, cudaStreamCreateWithFlags(&s->nn_stream, cudaStreamNonBlocking));
+			AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->joined, cudaEventDisableTiming));
+		}
 		if (c.solver_max_positions > 0)
 		{
 			const int rc = solver_state_create(e, c.games, c.max_batch_size, &s->solver);
@@ -1370,6 +1398,19 @@ namespace agb
 			if (ptr)
 				cudaFree(ptr);
 		solver_state_destroy(&s->solver);
+		for (int k = 0; k < kMaxGroups; k++)
+		{
+			if (s->group_stream[k])
+				cudaStreamDestroy(s->group_stream[k]);
+			if (s->ready[k])
+				cudaEventDestroy(s->ready[k]);
+			if (s->evaluated[k])
+				cudaEventDestroy(s->evaluated[k]);
+		}
+		if (s->nn_stream)
+			cudaStreamDestroy(s->nn_stream);
+		if (s->joined)
+			cudaEventDestroy(s->joined);
 		delete s;
 		e->selfplay = nullptr;
 	}
@@ -1453,10 +1494,9 @@ extern "C"
 			return e->fail(AGB_ESTATE, "engine was created without games");
 		if (e->net == nullptr)
 			return e->fail(AGB_ESTATE, "no weights loaded");
-		const Params p = make_params(e);
-		const unsigned grid = static_cast<unsigned>((s->games + 3) / 4);
-		const int max_tasks = s->games * s->batch;
-		while (static_cast<int>(e->events.size()) < 2 * n_steps)
+		const int groups = s->groups;
+		const int per_group = (s->games + groups - 1) / groups;
+		while (static_cast<int>(e->events.size()) < 4 * n_steps * groups)
 		{
 			cudaEvent_t ev;
 			AGB_CUDA_CHECK(e, cudaEventCreate(&ev));
@@ -1464,48 +1504,91 @@ extern "C"
 		}
 		unsigned long long evals_before = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&evals_before, s->stats + ST_EVALS, 8, cudaMemcpyDeviceToHost, e->stream));
-		for (int step = 0; step < n_steps; step++)
+		// fork: the group streams and the network stream start after whatever is already queued on the engine's stream
+		if (groups > 1)
 		{
-			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->eval_count, 0, sizeof(int32_t), e->stream));
-			select_kernel<<<grid, 128, 0, e->stream>>>(p);
-			e->launches++;
-			// K1 + K3 on the leaf positions, then K4; both read the batch size from device memory
-			int rc = launch_set_boards_counted(e, s->task_boards, s->task_stm, s->eval_count, max_tasks, s->features);
-			if (rc != AGB_OK)
-				return rc;
-			AGB_CUDA_CHECK(e, cudaEventRecord(e->events[2 * step], e->stream));
-			if (p.solver_mode != 0)
-			{ // K5 on every leaf; only unproven positions (and roots) go on to the network
-				AGB_CUDA_CHECK(e, cudaMemsetAsync(s->nn_count, 0, sizeof(int32_t), e->stream));
-				rc = launch_solve_games(e, s->solver, s->solver_out, s->slot_is_root, s->nn_list, s->nn_count);
+			AGB_CUDA_CHECK(e, cudaEventRecord(s->joined, e->stream));
+			for (int k = 0; k < groups; k++)
+				AGB_CUDA_CHECK(e, cudaStreamWaitEvent(s->group_stream[k], s->joined, 0));
+			AGB_CUDA_CHECK(e, cudaStreamWaitEvent(s->nn_stream, s->joined, 0));
+		}
+		for (int step = 0; step < n_steps; step++)
+			for (int k = 0; k < groups; k++)
+			{ // one lockstep iteration of group k; with two groups the only cross-stream edges are group -> network -> group
+				Params p = make_params(e);
+				p.game_begin = k * per_group;
+				p.game_count = std::min(per_group, s->games - p.game_begin);
+				p.slot_base = p.game_begin * s->batch;
+				p.eval_count = s->eval_count + k;
+				int32_t *nn_count = s->nn_count + k;
+				const int max_tasks = p.game_count * s->batch;
+				const unsigned grid = static_cast<unsigned>((p.game_count + 3) / 4);
+				cudaStream_t gs = (groups > 1) ? s->group_stream[k] : e->stream;
+				cudaStream_t ns = (groups > 1) ? s->nn_stream : e->stream;
+				cudaEvent_t *ev = e->events.data() + 4 * (step * groups + k); // before / after K5 (group stream), before / after K4 (network stream)
+
+				AGB_CUDA_CHECK(e, cudaMemsetAsync(p.eval_count, 0, sizeof(int32_t), gs));
+				select_kernel<<<grid, 128, 0, gs>>>(p);
+				e->launches++;
+				// K1 + K3 on the leaf positions, then K5 and K4; all read their batch size from device memory
+				int rc = launch_set_boards_counted(e, s->task_boards, s->task_stm, p.eval_count, max_tasks, s->features, p.slot_base, gs);
 				if (rc != AGB_OK)
 					return rc;
+				AGB_CUDA_CHECK(e, cudaEventRecord(ev[0], gs));
+				if (p.solver_mode != 0)
+				{ // K5 on every leaf; only unproven positions (and roots) go on to the network
+					AGB_CUDA_CHECK(e, cudaMemsetAsync(nn_count, 0, sizeof(int32_t), gs));
+					rc = launch_solve_games(e, s->solver, p.game_begin, p.game_count, s->solver_out, s->slot_is_root, s->nn_list + p.slot_base, nn_count, gs);
+					if (rc != AGB_OK)
+						return rc;
+				}
+				AGB_CUDA_CHECK(e, cudaEventRecord(ev[1], gs));
+				if (groups > 1)
+				{
+					AGB_CUDA_CHECK(e, cudaEventRecord(s->ready[k], gs));
+					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(ns, s->ready[k], 0));
+				}
+				AGB_CUDA_CHECK(e, cudaEventRecord(ev[2], ns));
+				rc = net_forward_dev_gather(e, s->features, p.solver_mode != 0 ? nn_count : p.eval_count, p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr,
+						max_tasks, s->policy, s->value, s->q, p.slot_base, ns);
+				if (rc != AGB_OK)
+					return rc;
+				AGB_CUDA_CHECK(e, cudaEventRecord(ev[3], ns));
+				if (groups > 1)
+				{
+					AGB_CUDA_CHECK(e, cudaEventRecord(s->evaluated[k], ns));
+					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(gs, s->evaluated[k], 0));
+				}
+				expand_backup_kernel<<<grid, 128, 0, gs>>>(p);
+				make_move_kernel<<<grid, 128, 0, gs>>>(p);
+				e->launches += 2;
+				AGB_CUDA_CHECK(e, cudaGetLastError());
 			}
-			rc = net_forward_dev_gather(e, s->features, p.solver_mode != 0 ? s->nn_count : s->eval_count, p.solver_mode != 0 ? s->nn_list : nullptr, max_tasks,
-					s->policy, s->value, s->q);
-			if (rc != AGB_OK)
-				return rc;
-			AGB_CUDA_CHECK(e, cudaEventRecord(e->events[2 * step + 1], e->stream));
-			expand_backup_kernel<<<grid, 128, 0, e->stream>>>(p);
-			make_move_kernel<<<grid, 128, 0, e->stream>>>(p);
-			e->launches += 2;
-			AGB_CUDA_CHECK(e, cudaGetLastError());
-		}
+		// join: everything the groups queued is ordered before what follows on the engine's stream
+		if (groups > 1)
+			for (int k = 0; k < groups; k++)
+			{
+				AGB_CUDA_CHECK(e, cudaEventRecord(s->ready[k], s->group_stream[k]));
+				AGB_CUDA_CHECK(e, cudaStreamWaitEvent(e->stream, s->ready[k], 0));
+			}
 		uint32_t status = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, 4, cudaMemcpyDeviceToHost, e->stream));
- 		unsigned long long evals_after = 0;
+		unsigned long long evals_after = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&evals_after, s->stats + ST_EVALS, 8, cudaMemcpyDeviceToHost, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
-		for (int step = 0; step < n_steps; step++)
-		{ // device time of the network kernels (K4 + value head) of this call
+		for (int i = 0; i < n_steps * groups; i++)
+		{ // device time of the network kernels (K4 + value head) and of the solver kernel (K5) of this call
 			float ms = 0.0f;
-			if (cudaEventElapsedTime(&ms, e->events[2 * step], e->events[2 * step + 1]) == cudaSuccess)
+			if (cudaEventElapsedTime(&ms, e->events[4 * i + 2], e->events[4 * i + 3]) == cudaSuccess)
 				e->nn_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
+			if (e->cfg.solver_max_positions > 0 and cudaEventElapsedTime(&ms, e->events[4 * i], e->events[4 * i + 1]) == cudaSuccess)
+				e->solver_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
 		}
-		e->nn_kernel_launches += n_steps;
+		e->nn_kernel_launches += static_cast<uint64_t>(n_steps) * groups;
 		e->nn_positions += evals_after - evals_before;
 		if (status != 0)
-			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status) + " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table, 32 record, 64 finished queue)");
+			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status)
+					+ " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table, 32 record, 64 finished queue, 256/512 solver forbidden-move recursion/cache, 1024 solver action stack, 2048 solver frames)");
 		return AGB_OK;
 	}
 
@@ -1544,6 +1627,7 @@ extern "C"
 		stats->nn_kernel_ns = e->nn_kernel_ns;
 		stats->nn_kernel_launches = e->nn_kernel_launches;
 		stats->nn_positions = e->nn_positions;
+		stats->solver_kernel_ns = e->solver_kernel_ns;
 		if (e->selfplay != nullptr)
 		{
 			unsigned long long h[16];

@@ -1,4 +1,4 @@
-// K5: the per-leaf solver of the lockstep engine. One warp owns one game and its lane 0 solves that game's leaf positions of
+// K5: the per-leaf solver of the lockstep engine. One warp owns one game and solves that game's leaf positions of
 // the current batch one after another, in task order, on top of the K1 state of their slots: staged move generation, static
 // evaluation and (max_positions > 1) the alpha-beta threat-space search with the game's transposition table
 // (solver_logic.cuh, solver_search.cuh). Replaces Search::solve -> AlphaBetaSearch::solve
@@ -6,7 +6,8 @@
 // stay unproven or are tree roots, Search::scheduleToNN (Search.cpp:184-198).
 //
 // The positions of one game must be solved in order because they share the table (what task i stores, task i+1 may read);
-// games are independent, so the parallelism is one warp per game with all of the sequential logic in lane 0.
+// games are independent, so the parallelism is one warp per game; its lanes run the sequential logic in lockstep and share the
+// per-move pattern updates (solver_search.cuh).
 #include "engine.hpp"
 #include "solver_search.cuh"
 
@@ -18,13 +19,15 @@ namespace agb
 	{
 		constexpr int kSolverWarpsPerBlock = 4;
 
-		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int games, int S, int rules,
+		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32, 7) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int game_begin, int games, int S, int rules,
 				int draw_after, int max_nodes, SolverOutputs out, const uint8_t *__restrict__ slot_is_root, int *__restrict__ nn_list, int *__restrict__ nn_count,
 				uint32_t *__restrict__ status)
 		{
-			const int g = blockIdx.x * kSolverWarpsPerBlock + (threadIdx.x >> 5);
-			if (g >= games or (threadIdx.x & 31) != 0)
+			const int local = blockIdx.x * kSolverWarpsPerBlock + (threadIdx.x >> 5);
+			if (local >= games)
 				return;
+			const int g = game_begin + local;
+			const bool leader = (threadIdx.x & 31) == 0; // all lanes run the solver in lockstep (solver_search.cuh); one of them publishes
 			const int cells = S * S;
 			const int n_slots = st.game_slot_count[g];
 			solver::HashTable tt { st.table + static_cast<size_t>(g) * st.table_entries * 2, st.table_entries / 4 - 1, st.generation[g], st.keys + static_cast<size_t>(g) * st.keys_stride };
@@ -60,10 +63,11 @@ namespace agb
 				out.score[slot] = res.score;
 				out.must_defend[slot] = res.must_defend ? 1 : 0;
 				out.nodes[slot] = res.node_counter;
-				if (res.overflow)
+				if (leader and res.overflow)
 					atomicOr(status, res.overflow << 8); // bits 8..11, see AgbStats::overflow_flags
-				if (slot_is_root[slot] or not solver::sc_is_proven(res.score))
+				if (leader and (slot_is_root[slot] or not solver::sc_is_proven(res.score)))
 					nn_list[atomicAdd(nn_count, 1)] = slot;
+				__syncwarp();
 			}
 		}
 		__global__ void clear_tables_kernel(uint64_t *table, size_t n_entries)
@@ -145,11 +149,12 @@ namespace agb
 		cudaFree(st->frames);
 		*st = SolverState { };
 	}
-	int launch_solve_games(AgbEngine *e, const SolverState &st, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list, int *nn_count)
+	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
+			int *nn_count, cudaStream_t stream)
 	{
 		const int draw_after = e->cfg.draw_after > 0 ? e->cfg.draw_after : e->cells;
-		solve_games_kernel<<<(st.games + kSolverWarpsPerBlock - 1) / kSolverWarpsPerBlock, kSolverWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, st,
-				st.games, e->cfg.rows, e->cfg.rules, draw_after, e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		solve_games_kernel<<<(game_count + kSolverWarpsPerBlock - 1) / kSolverWarpsPerBlock, kSolverWarpsPerBlock * 32, 0, stream>>>(e->store, e->tables, st,
+				game_begin, game_count, e->cfg.rows, e->cfg.rules, draw_after, e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

@@ -82,7 +82,7 @@ namespace agb
 			return true;
 		}
 		// DefensiveMoveTable::getMoves: 13-cell window around an attacker threat -> bit i set: cell (i - 6) along the line defends
-		AGB_HD inline uint32_t defensive_mask(const uint16_t *table, int rules, uint32_t window13, int defender, int threat)
+		AGB_HD_NOINLINE inline uint32_t defensive_mask(const uint16_t *table, int rules, uint32_t window13, int defender, int threat)
 		{
 			const int attacker = 3 - defender;
 			const uint32_t colour_scale = (attacker == CROSS) ? 1u : 2u; // circle masks are the cross masks with every stone doubled
@@ -90,16 +90,19 @@ namespace agb
 			switch (threat)
 			{
 				case PT_FIVE:
+#pragma unroll 1
 					for (int i = 0; i < 5; i++)
 						if (sub_pattern(window13, 2 + i, 5) == DefMasks::five(i) * colour_scale)
 							return table[((0 + i) * 256 + neighbour_index(window13, 2 + i, 2 + i + 5)) * 2 + d];
 					return 0;
 				case PT_OPEN_4:
+#pragma unroll 1
 					for (int i = 0; i < 4; i++)
 						if (sub_pattern(window13, 2 + i, 6) == DefMasks::open_four(i) * colour_scale)
 							return table[((5 + i) * 256 + neighbour_index(window13, 2 + i, 2 + i + 6)) * 2 + d];
 					return 0;
 				case PT_DOUBLE_4:
+#pragma unroll 1
 					for (int i = 0; i < 6; i++)
 					{
 						const int len = DefMasks::double_four_len(i), begin = DefMasks::double_four_off(i);
@@ -110,6 +113,7 @@ namespace agb
 				case PT_HALF_OPEN_4:
 				{
 					uint32_t result = 1u << 6;
+#pragma unroll 1
 					for (int i = 0; i < 20; i++)
 					{
 						const int begin = DefMasks::half_open_four_off(i);
@@ -127,6 +131,7 @@ namespace agb
 					return result;
 				}
 				case PT_OPEN_3:
+#pragma unroll 1
 					for (int i = 0; i < 12; i++)
 					{
 						const int begin = DefMasks::open_three_off(i);
@@ -151,9 +156,11 @@ namespace agb
 			inline uint32_t with(uint32_t line, int i, int v) { return (line & ~(3u << (2 * i))) | (static_cast<uint32_t>(v) << (2 * i)); }
 			inline bool has_five(uint32_t line, int size, int rules, int attacker, int defender)
 			{
+#pragma unroll 1
 				for (int i = 1; i < size - 5; i++)
 				{
 					bool all = true;
+#pragma unroll 1
 					for (int k = 0; k < 5; k++)
 						all = all and cell(line, i + k) == attacker;
 					if (all and sides_allow_five(rules, attacker, defender, cell(line, i - 1), cell(line, i + 5)))
@@ -164,6 +171,7 @@ namespace agb
 			inline int search(uint32_t line, int size, int rules, int attacker, int defender, int sign, int depth)
 			{ // +1: `sign` to move can force the attacker's five, 0: nothing decided within depth, -1: no empty cell
 				int outcome = -1;
+#pragma unroll 1
 				for (int i = 0; i < size; i++)
 					if (cell(line, i) == NONE)
 					{
@@ -183,6 +191,7 @@ namespace agb
 				if (search(line, size, rules, attacker, defender, attacker, depth) == 0)
 					return 0;
 				uint16_t result = 0;
+#pragma unroll 1
 				for (int i = 0; i < size; i++)
 					if (cell(line, i) == NONE)
 						if (search(with(line, i, defender), size, rules, attacker, defender, attacker, depth) != 1)
@@ -192,6 +201,7 @@ namespace agb
 			// table[kDefGroups][256][2]
 			inline void defensive_table(int rules, uint16_t *table)
 			{
+#pragma unroll 1
 				for (int g = 0; g < kDefGroups; g++)
 				{
 					uint32_t base;
@@ -199,7 +209,9 @@ namespace agb
 					if (g < 5) { base = DefMasks::five(g); len = 5; off = 2 + g; depth = 1; }
 					else if (g < 9) { base = DefMasks::open_four(g - 5); len = 6; off = 2 + (g - 5); depth = 3; }
 					else { base = DefMasks::double_four(g - 9); len = DefMasks::double_four_len(g - 9); off = DefMasks::double_four_off(g - 9); depth = 3; }
+#pragma unroll 1
 					for (int j = 0; j < 256; j++)
+#pragma unroll 1
 						for (int d = 0; d < 2; d++)
 						{ // defender d+1 faces the pattern drawn with the attacker's stones
 							const uint32_t stones = base * ((d == 0) ? 2u : 1u); // cross defends circle stones and vice versa
@@ -240,6 +252,7 @@ namespace agb
 				}
 				AGB_HD bool group_contains(int sign, int r, int c, int pt) const
 				{
+#pragma unroll 1
 					for (int d = 0; d < 4; d++)
 						if (ptype_at(sign, r, c, d) == pt)
 							return true;
@@ -248,12 +261,14 @@ namespace agb
 				AGB_HD int group_count(int sign, int r, int c, int pt) const
 				{
 					int n = 0;
+#pragma unroll 1
 					for (int d = 0; d < 4; d++)
 						n += (ptype_at(sign, r, c, d) == pt);
 					return n;
 				}
 				AGB_HD int direction_of(int sign, int r, int c, int pt) const
 				{
+#pragma unroll 1
 					for (int d = 0; d < 4; d++)
 						if (ptype_at(sign, r, c, d) == pt)
 							return d;
@@ -287,6 +302,7 @@ namespace agb
 				int size = 0;
 				AGB_HD bool contains(uint16_t v) const
 				{
+#pragma unroll 1
 					for (int i = 0; i < size; i++)
 						if (data[i] == v)
 							return true;
@@ -296,6 +312,7 @@ namespace agb
 				AGB_HD void remove_at(int i) { data[i] = data[--size]; }
 				AGB_HD void remove_value(uint16_t v)
 				{
+#pragma unroll 1
 					for (int i = 0; i < size; i++)
 						if (data[i] == v)
 						{
@@ -309,10 +326,11 @@ namespace agb
 				LocList<24> list;
 				bool not_initialized = true;
 				template<int N>
-				AGB_HD void intersect(const LocList<N> &other)
+				AGB_HD_NOINLINE void intersect(const LocList<N> &other)
 				{
 					if (not_initialized)
 					{
+#pragma unroll 1
 						for (int i = 0; i < other.size; i++)
 							list.add(other.data[i]);
 						not_initialized = false;
@@ -354,7 +372,7 @@ namespace agb
 				uint16_t temp[kTempCapacity];
 				int temp_size = 0;
 				bool temp_overflow = false;
-				AGB_HD void copy_list(int sign, int tt)
+				AGB_HD_NOINLINE void copy_list(int sign, int tt)
 				{
 					temp_size = v.count(sign, tt);
 					if (temp_size > kTempCapacity)
@@ -362,17 +380,19 @@ namespace agb
 						temp_size = kTempCapacity;
 						temp_overflow = true;
 					}
+#pragma unroll 1
 					for (int i = 0; i < temp_size; i++)
 						temp[i] = v.item(sign, tt, i);
 				}
 
 				AGB_HD MoveGenerator(const View &view, uint16_t *m, uint16_t *s) : v(view), moves(m), scores(s)
 				{
+#pragma unroll 1
 					for (int i = 0; i < kMaxSize; i++)
 						added[i] = 0;
 				}
 				AGB_HD uint16_t wire(uint16_t loc) const { return static_cast<uint16_t>(v.own() | (loc_row(loc) << 2) | (loc_col(loc) << 9)); }
-				AGB_HD void add_move(uint16_t loc, uint16_t s, bool override_duplicate)
+				AGB_HD_NOINLINE void add_move(uint16_t loc, uint16_t s, bool override_duplicate)
 				{
 					const int r = loc_row(loc), c = loc_col(loc);
 					if ((added[r] >> c) & 1u)
@@ -380,6 +400,7 @@ namespace agb
 						if (override_duplicate)
 						{
 							const uint16_t w = wire(loc);
+#pragma unroll 1
 							for (int i = 0; i < out.n_actions; i++)
 								if (moves[i] == w)
 								{
@@ -396,32 +417,35 @@ namespace agb
 						added[r] |= 1u << c;
 					}
 				}
-				AGB_HD void add_list(int sign, int tt, uint16_t s, bool override_duplicate = false)
+				AGB_HD_NOINLINE void add_list(int sign, int tt, uint16_t s, bool override_duplicate = false)
 				{
 					const int n = v.count(sign, tt);
+#pragma unroll 1
 					for (int i = 0; i < n; i++)
 						add_move(v.item(sign, tt, i), s, override_duplicate);
 				}
 				template<int N>
-				AGB_HD void add_all(const LocList<N> &l, uint16_t s = kScoreDefault)
+				AGB_HD_NOINLINE void add_all(const LocList<N> &l, uint16_t s = kScoreDefault)
 				{
+#pragma unroll 1
 					for (int i = 0; i < l.size; i++)
 						add_move(l.data[i], s, false);
 				}
 				// PatternCalculator::getDefensiveMoves: all cells of the table mask, in increasing offset order
-				AGB_HD LocList<7> raw_defensive_moves(int defender, int r, int c, int dir) const
+				AGB_HD_NOINLINE LocList<7> raw_defensive_moves(int defender, int r, int c, int dir) const
 				{
 					const uint32_t window = extended_window(v.lines, dir, r, c, v.S);
 					const int threat = v.ptype_at(3 - defender, r, c, dir);
 					const uint32_t mask = defensive_mask(v.def_table, v.rules, window, defender, threat);
 					LocList<7> result;
+#pragma unroll 1
 					for (int i = -6; i <= 6; i++)
 						if ((mask >> (6 + i)) & 1u)
 							result.add(mk_loc(r + i * dir_row_step(dir), c + i * dir_col_step(dir)));
 					return result;
 				}
 				// MoveGenerator::get_defensive_moves (MoveGenerator.cpp:259-307)
-				AGB_HD LocList<7> get_defensive_moves(uint16_t loc, int dir)
+				AGB_HD_NOINLINE LocList<7> get_defensive_moves(uint16_t loc, int dir)
 				{
 					const int r = loc_row(loc), c = loc_col(loc);
 					LocList<7> result = raw_defensive_moves(v.own(), r, c, dir);
@@ -459,7 +483,7 @@ namespace agb
 					}
 					return result;
 				}
-				AGB_HD void create_remaining(const uint32_t *mask, uint16_t s = kScoreDefault)
+				AGB_HD_NOINLINE void create_remaining(const uint32_t *mask, uint16_t s = kScoreDefault)
 				{ // MoveGenerator::create_remaining_moves
 					for (int r = 0; r < v.S; r++)
 					{
@@ -485,7 +509,7 @@ namespace agb
 					}
 				}
 				// 7x7 stencils around stones (MoveGenerator.cpp:1011-1125); `sign` 0: around every stone (box-and-star), else star around `sign`
-				AGB_HD void stencil_mask(uint32_t *mask, int sign) const
+				AGB_HD_NOINLINE void stencil_mask(uint32_t *mask, int sign) const
 				{
 					const uint32_t box[7] = { 73u, 62u, 62u, 119u, 62u, 62u, 73u };
 					const uint32_t star[7] = { 73u, 42u, 28u, 119u, 28u, 42u, 73u };
@@ -512,7 +536,7 @@ namespace agb
 				}
 
 				// ---- stages -----------------------------------------------------------------------------------------------------
-				AGB_HD uint16_t try_solve_own_fork_4x3(uint16_t loc)
+				AGB_HD_NOINLINE uint16_t try_solve_own_fork_4x3(uint16_t loc)
 				{ // MoveGenerator.cpp:952-994
 					const uint16_t prior = sc_eval(15);
 					if (v.anything_forbidden_for(v.own()))
@@ -547,7 +571,7 @@ namespace agb
 							return loss_in(2);
 					}
 				}
-				AGB_HD uint16_t add_own_4x3_forks()
+				AGB_HD_NOINLINE uint16_t add_own_4x3_forks()
 				{
 					uint16_t result = kScoreDefault;
 					const int n = v.count(v.own(), TT_FORK_4x3);
@@ -561,7 +585,7 @@ namespace agb
 					}
 					return result;
 				}
-				AGB_HD void add_own_half_open_fours()
+				AGB_HD_NOINLINE void add_own_half_open_fours()
 				{
 					const uint16_t prior = sc_eval(14);
 					int hidden = 0;
@@ -594,7 +618,7 @@ namespace agb
 					}
 					return false;
 				}
-				AGB_HD bool try_draw_in_1(uint16_t &score)
+				AGB_HD_NOINLINE bool try_draw_in_1(uint16_t &score)
 				{ // MoveGenerator.cpp:308-355
 					out.baseline = draw_in(1);
 					if (v.anything_forbidden_for(v.own()))
@@ -624,7 +648,7 @@ namespace agb
 					}
 					return true;
 				}
-				AGB_HD bool defend_loss_in_2(uint16_t &score)
+				AGB_HD_NOINLINE bool defend_loss_in_2(uint16_t &score)
 				{ // MoveGenerator.cpp:372-461
 					const int n_fives = v.count(v.opp(), TT_FIVE);
 					if (n_fives == 0)
@@ -687,7 +711,7 @@ namespace agb
 					score = best;
 					return true;
 				}
-				AGB_HD bool try_win_in_3(uint16_t &score)
+				AGB_HD_NOINLINE bool try_win_in_3(uint16_t &score)
 				{ // MoveGenerator.cpp:462-553
 					int threats = 0;
 					if (v.anything_forbidden_for(v.own()))
@@ -750,7 +774,7 @@ namespace agb
 					}
 					return false;
 				}
-				AGB_HD bool defend_loss_in_4(uint16_t &score)
+				AGB_HD_NOINLINE bool defend_loss_in_4(uint16_t &score)
 				{ // MoveGenerator.cpp:554-685
 					const bool has_any_four = v.has_any_four(v.own());
 					out.baseline = loss_in(4);
@@ -758,6 +782,7 @@ namespace agb
 					{
 						DefensiveSet defensive;
 						const int n_open4 = v.count(v.opp(), TT_OPEN_4);
+#pragma unroll 1
 						for (int i = 0; i < n_open4; i++)
 						{
 							out.must_defend = true;
@@ -772,11 +797,13 @@ namespace agb
 							}
 						}
 						const int n_44 = v.count(v.opp(), TT_FORK_4x4);
+#pragma unroll 1
 						for (int i = 0; i < n_44; i++)
 						{
 							out.must_defend = true;
 							const uint16_t loc = v.item(v.opp(), TT_FORK_4x4, i);
 							const int r = loc_row(loc), c = loc_col(loc);
+#pragma unroll 1
 							for (int dir = 0; dir < 4; dir++)
 							{
 								const int pt = v.ptype_at(v.opp(), r, c, dir);
@@ -786,10 +813,12 @@ namespace agb
 							if (v.group_count(v.opp(), r, c, PT_HALF_OPEN_4) > 0)
 							{
 								LocList<24> storage;
+#pragma unroll 1
 								for (int dir = 0; dir < 4; dir++)
 									if (v.ptype_at(v.opp(), r, c, dir) == PT_HALF_OPEN_4)
 									{
 										const LocList<7> tmp = get_defensive_moves(loc, dir);
+#pragma unroll 1
 										for (int k = 0; k < tmp.size; k++)
 											if (not storage.contains(tmp.data[k]))
 												storage.add(tmp.data[k]);
@@ -808,6 +837,7 @@ namespace agb
 					else
 					{
 						copy_list(v.opp(), TT_OPEN_4);
+#pragma unroll 1
 						for (int i = 0; i < temp_size; i++)
 						{
 							out.must_defend = true;
@@ -818,6 +848,7 @@ namespace agb
 						if (v.anything_forbidden_for(v.opp()))
 						{
 							copy_list(v.opp(), TT_FORK_3x3);
+#pragma unroll 1
 							for (int i = 0; i < temp_size; i++)
 							{
 								const uint16_t loc = temp[i];
@@ -832,10 +863,12 @@ namespace agb
 						if (not v.anything_forbidden_for(v.opp()))
 						{
 							copy_list(v.opp(), TT_FORK_4x4);
+#pragma unroll 1
 							for (int i = 0; i < temp_size; i++)
 							{
 								out.must_defend = true;
 								const uint16_t loc = temp[i];
+#pragma unroll 1
 								for (int dir = 0; dir < 4; dir++)
 								{
 									const int pt = v.ptype_at(v.opp(), loc_row(loc), loc_col(loc), dir);
@@ -856,7 +889,7 @@ namespace agb
 					out.baseline = kScoreDefault;
 					return false;
 				}
-				AGB_HD bool try_win_in_5(uint16_t &score)
+				AGB_HD_NOINLINE bool try_win_in_5(uint16_t &score)
 				{ // MoveGenerator.cpp:686-715
 					uint16_t best = add_own_4x3_forks();
 					if (not v.anything_forbidden_for(v.own()) and v.available_fours(v.opp()) == 0 and v.count(v.own(), TT_FORK_3x3) > 0)
@@ -872,7 +905,7 @@ namespace agb
 					}
 					return false;
 				}
-				AGB_HD bool defend_loss_in_6(uint16_t &score)
+				AGB_HD_NOINLINE bool defend_loss_in_6(uint16_t &score)
 				{ // MoveGenerator.cpp:716-815
 					if (v.available_fours(v.own()) > 0)
 						return false;
@@ -884,28 +917,35 @@ namespace agb
 					}
 					// the reference walks the LIVE lists here and dereferences its iterator again for every get_defensive_moves() call, while
 					// the pattern group was read once at the top of the iteration; is_forbidden() inside may have reordered the list in between
+#pragma unroll 1
 					for (int i = 0; i < n43; i++)
 					{
 						const uint16_t loc = v.item(v.opp(), TT_FORK_4x3, i);
 						const int r = loc_row(loc), c = loc_col(loc);
 						int group[4];
+#pragma unroll 1
 						for (int dir = 0; dir < 4; dir++)
 							group[dir] = v.ptype_at(v.opp(), r, c, dir);
+#pragma unroll 1
 						for (int dir = 0; dir < 4; dir++)
 							if (group[dir] == PT_OPEN_3)
 								add_all(get_defensive_moves(v.item(v.opp(), TT_FORK_4x3, i), dir), sc_eval(0));
 						int four_dir = 0;
+#pragma unroll 1
 						for (int dir = 3; dir >= 0; dir--)
 							if (group[dir] == PT_HALF_OPEN_4)
 								four_dir = dir;
 						const LocList<7> four_defence = get_defensive_moves(v.item(v.opp(), TT_FORK_4x3, i), four_dir);
 						add_all(four_defence, sc_eval(0));
+#pragma unroll 1
 						for (int k = 0; k < four_defence.size; k++)
 						{
 							const int dr = loc_row(four_defence.data[k]), dc = loc_col(four_defence.data[k]);
+#pragma unroll 1
 							for (int dir = 0; dir < 4; dir++)
 							{
 								const uint32_t reduced = static_cast<uint32_t>(v.lines[line_index(dir, dr, dc, v.S)] >> (2 * pos_in_line(dir, dr, dc, v.S) + 4)) & 0x3FFFFu;
+#pragma unroll 1
 								for (int i2 = -4; i2 <= 4; i2++)
 									if (((reduced >> (2 * (i2 + 4))) & 3u) == 0u)
 									{
@@ -916,13 +956,16 @@ namespace agb
 							}
 						}
 					}
+#pragma unroll 1
 					for (int i = 0; i < n33; i++)
 					{
 						const uint16_t loc = v.item(v.opp(), TT_FORK_3x3, i);
 						const int r = loc_row(loc), c = loc_col(loc);
 						int group[4];
+#pragma unroll 1
 						for (int dir = 0; dir < 4; dir++)
 							group[dir] = v.ptype_at(v.opp(), r, c, dir);
+#pragma unroll 1
 						for (int dir = 0; dir < 4; dir++)
 							if (group[dir] == PT_OPEN_3)
 								add_all(get_defensive_moves(v.item(v.opp(), TT_FORK_3x3, i), dir), sc_eval(0));
@@ -930,11 +973,14 @@ namespace agb
 						add_list(v.own(), TT_OPEN_3, sc_eval(1));
 						uint32_t mask[kMaxSize];
 						stencil_mask(mask, v.own());
+#pragma unroll 1
 						for (int rr = 0; rr < v.S; rr++)
 						{
 							uint32_t tmp = mask[rr] & ~added[rr];
+#pragma unroll 1
 							for (int cc = 0; cc < v.S; cc++, tmp >>= 1)
 								if (tmp & 1u)
+#pragma unroll 1
 									for (int dir = 0; dir < 4; dir++)
 										if (v.half_open_three_at(v.own(), rr, cc, dir))
 										{
@@ -951,7 +997,7 @@ namespace agb
 					}
 					return false;
 				}
-				AGB_HD void mark_forbidden_moves()
+				AGB_HD_NOINLINE void mark_forbidden_moves()
 				{ // MoveGenerator.cpp:995-1010
 					add_list(v.own(), TT_OVERLINE, loss_in(1), true);
 					add_list(v.own(), TT_FORK_4x4, loss_in(1), true);
@@ -964,13 +1010,35 @@ namespace agb
 					}
 				}
 				AGB_HD void generate_optimal() { generate(GEN_OPTIMAL); }
+				// true when neither side has a 3x3 fork or anything stronger: the THREATS stages (MoveGenerator.cpp:176-196) and
+				// mark_forbidden_moves then find every list they walk empty
+				AGB_HD bool is_quiet() const
+				{
+#ifdef __CUDA_ARCH__
+					const int lane = threadIdx.x & 31; // the warp runs in lockstep (solver_search.cuh): one list length per lane
+					const bool busy = lane < 2 * kHistTypes and (lane % kHistTypes) >= TT_FORK_3x3 and v.hist_count[lane] != 0;
+					return __ballot_sync(0xFFFFFFFFu, busy) == 0u;
+#else
+					for (int colour = 0; colour < 2; colour++)
+						for (int t = TT_FORK_3x3; t < kHistTypes; t++)
+							if (v.hist_count[colour * kHistTypes + t] != 0)
+								return false;
+					return true;
+#endif
+				}
 				// MoveGenerator::generate in THREATS or OPTIMAL mode (MoveGenerator.cpp:159-223)
-				AGB_HD void generate(int mode)
+				AGB_HD_NOINLINE void generate(int mode)
 				{
 					const int distance_to_draw = v.draw_after - v.stones;
 					if (distance_to_draw <= 0)
 					{
 						out.score = mk_score(PV_DRAW, 0);
+						return;
+					}
+					if (mode == GEN_THREATS and distance_to_draw >= 2 and is_quiet())
+					{ // no list any stage below looks at has an entry: they would all fall through without adding a move
+						out.score = kScoreDefault;
+						out.is_fully_expanded = false;
 						return;
 					}
 					uint16_t score = kScoreDefault;
@@ -1015,13 +1083,41 @@ namespace agb
 		};
 
 		// AlphaBetaSearch::evaluate (AlphaBetaSearch.cpp:345-365)
-		AGB_HD inline uint16_t static_evaluation(const View &v)
+		AGB_HD_NOINLINE inline uint16_t static_evaluation(const View &v)
 		{
+			int result = 12;
+#ifdef __CUDA_ARCH__
+			{ // one list length per lane, then a warp sum (the warp runs in lockstep, solver_search.cuh)
+				const int lane = threadIdx.x & 31;
+				int term = 0;
+				if (lane < 2 * kHistTypes)
+				{
+					const int t = lane % kHistTypes;
+					const bool own = (lane / kHistTypes) == v.own() - 1;
+					int w = 0;
+					switch (t)
+					{
+						case TT_OPEN_3: w = own ? 19 : -1; break;
+						case TT_FORK_3x3: w = own ? 49 : -50; break;
+						case TT_HALF_OPEN_4: w = own ? 76 : -45; break;
+						case TT_FORK_4x3: w = own ? 170 : -135; break;
+						case TT_FORK_4x4: w = own ? 33 : -14; break;
+						case TT_OPEN_4: w = own ? 159 : -154; break;
+						case TT_FIVE: w = own ? 252 : -496; break;
+						default: break;
+					}
+					term = w * v.hist_count[lane];
+				}
+				for (int o = 16; o > 0; o >>= 1)
+					term += __shfl_xor_sync(0xFFFFFFFFu, term, o);
+				result += term;
+			}
+#else
 			const int own_values[10] = { 0, 0, 19, 49, 76, 170, 33, 159, 252, 0 };
 			const int opp_values[10] = { 0, 0, -1, -50, -45, -135, -14, -154, -496, 0 };
-			int result = 12;
 			for (int i = TT_OPEN_3; i <= TT_FIVE; i++)
 				result += own_values[i] * v.count(v.own(), i) + opp_values[i] * v.count(v.opp(), i);
+#endif
 			result = result < -1000 ? -1000 : (result > 1000 ? 1000 : result);
 			return sc_eval(result);
 		}

@@ -6,8 +6,10 @@
 // PatternCalculator::addMove / undoMove / update_around (src/patterns/PatternCalculator.cpp:68-106, 278-366) and
 // PatternCalculator::isForbidden / is_3x3_forbidden (PatternCalculator.hpp:173-189, PatternCalculator.cpp:213-244).
 //
-// One thread owns one game: it solves that game's leaf positions one after another (they share the game's transposition
-// table, so the order is part of the result). The recursion of the reference is unrolled into an explicit frame stack;
+// One warp owns one game: it solves that game's leaf positions one after another (they share the game's transposition
+// table, so the order is part of the result). All 32 lanes execute the sequential logic in lockstep on identical data (a warp
+// instruction costs the same with 1 or 32 active lanes) and split the data-parallel part, the 40-cell pattern update of every
+// move made or taken back, between them. The recursion of the reference is unrolled into an explicit frame stack;
 // the position is updated in place with the same incremental update as K2, which also keeps the ORDER of the threat lists
 // identical to the reference's (swap-with-last removal, append on change, visiting order of update_around).
 #pragma once
@@ -35,7 +37,7 @@ namespace agb
 				uint32_t overflow = 0; // 1: forbidden-move recursion too deep, 2: forbidden cache full
 		};
 
-		AGB_HD inline void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
+		AGB_HD_NOINLINE inline void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
 		{ // ThreatHistogram::remove (ThreatHistogram.hpp:74-91)
 			if (type == TT_NONE)
 				return;
@@ -57,9 +59,64 @@ namespace agb
 			d.hist_cells[(colour * kHistTypes + type) * d.v.pitch + count] = loc;
 			count++;
 		}
-		AGB_HD inline void dyn_update_neighbours(DynState &d, int r, int c, const uint64_t *line4, const int *pos4)
+		AGB_HD_NOINLINE inline void dyn_update_neighbours(DynState &d, int r, int c, const uint64_t *line4, const int *pos4)
 		{ // the 40 cells at distance 1..5 in the visiting order of update_around (PatternCalculator.cpp:320-330)
 			const int S = d.v.S;
+#ifdef __CUDA_ARCH__
+			// On the device all 32 lanes of the game's warp run the solver in lockstep on identical data; here they split the 40 cells
+			// (entry q = 4 * k + dir, k-th offset of -5..-1,1..5, like K2) and then replay the list changes together, in visiting order.
+			const int lane = threadIdx.x & 31;
+			uint32_t old_t[2] = { 0, 0 }, new_t[2] = { 0, 0 }, loc[2] = { 0, 0 };
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				const int q = lane + 32 * half;
+				if (q < 40)
+				{
+					const int dir = q & 3;
+					const int k = q >> 2;
+					const int off = (k < 5) ? (k - 5) : (k - 4);
+					const int nr = r + off * dir_row_step(dir), nc = c + off * dir_col_step(dir);
+					if (nr >= 0 and nr < S and nc >= 0 and nc < S and d.board[nr * S + nc] == NONE)
+					{
+						const int ncell = nr * S + nc;
+						const uint32_t window = static_cast<uint32_t>(line4[dir] >> (2 * (pos4[dir] + off) + 2)) & 0x3FFFFFu;
+						const uint32_t byte = d.v.pattern_table[narrow_window(window)];
+						const uint32_t p = (d.ptypes[ncell] & ~(0xFFu << (8 * dir))) | (byte << (8 * dir));
+						old_t[half] = d.threats[ncell];
+						new_t[half] = threat_of_cell(p, d.threat_table);
+						loc[half] = mk_loc(nr, nc);
+						d.ptypes[ncell] = p;
+						d.threats[ncell] = static_cast<uint8_t>(new_t[half]);
+					}
+				}
+			}
+			__syncwarp();
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				unsigned changed = __ballot_sync(0xFFFFFFFFu, old_t[half] != new_t[half]);
+				while (changed)
+				{
+					const int src = __ffs(changed) - 1;
+					changed &= changed - 1;
+					const int o = __shfl_sync(0xFFFFFFFFu, static_cast<int>(old_t[half]), src);
+					const int nw = __shfl_sync(0xFFFFFFFFu, static_cast<int>(new_t[half]), src);
+					const uint16_t l = static_cast<uint16_t>(__shfl_sync(0xFFFFFFFFu, static_cast<int>(loc[half]), src));
+					if ((o & 15) != (nw & 15))
+					{
+						dyn_hist_remove(d, 0, o & 15, l);
+						dyn_hist_add(d, 0, nw & 15, l);
+					}
+					if ((o >> 4) != (nw >> 4))
+					{
+						dyn_hist_remove(d, 1, o >> 4, l);
+						dyn_hist_add(d, 1, nw >> 4, l);
+					}
+				}
+			}
+			__syncwarp();
+#else
 			for (int off = -5; off <= 5; off++)
 				if (off != 0)
 					for (int dir = 0; dir < 4; dir++)
@@ -92,8 +149,9 @@ namespace agb
 							}
 						}
 					}
+#endif
 		}
-		AGB_HD inline void dyn_add_move(DynState &d, int r, int c, int sign)
+		AGB_HD_NOINLINE inline void dyn_add_move(DynState &d, int r, int c, int sign)
 		{ // PatternCalculator::addMove (PatternCalculator.cpp:68-86)
 			const int S = d.v.S;
 			uint64_t line4[4];
@@ -116,7 +174,7 @@ namespace agb
 			d.v.stm = 3 - d.v.stm;
 			d.v.stones++;
 		}
-		AGB_HD inline void dyn_undo_move(DynState &d, int r, int c, int sign)
+		AGB_HD_NOINLINE inline void dyn_undo_move(DynState &d, int r, int c, int sign)
 		{ // PatternCalculator::undoMove (PatternCalculator.cpp:87-106)
 			(void) sign;
 			const int S = d.v.S;
@@ -152,7 +210,7 @@ namespace agb
 			Overlay none;
 			return makes_straight_four(raw_window(d.board, d.v.S, r, c, dir, none));
 		}
-		AGB_HD inline bool dyn_is_3x3_forbidden(DynState &d, int r, int c, int depth)
+		AGB_HD_NOINLINE inline bool dyn_is_3x3_forbidden(DynState &d, int r, int c, int depth)
 		{ // PatternCalculator::is_3x3_forbidden (PatternCalculator.cpp:213-244)
 			if (depth >= kMaxForbiddenDepth)
 			{
@@ -205,7 +263,7 @@ namespace agb
 				return dyn_is_3x3_forbidden(d, r, c, depth);
 			return false;
 		}
-		AGB_HD inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c)
+		AGB_HD_NOINLINE inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c)
 		{ // MoveGenerator::is_forbidden (MoveGenerator.cpp:1167-1180): cached per generate() call
 			if (not (d->v.rules == RULE_RENJU and sign == CROSS))
 				return false;
@@ -227,7 +285,7 @@ namespace agb
 
 		// NNInputFeatures::encode (NNInputFeatures.cpp:104-110) asks isForbidden for every cell before the search starts; only its side
 		// effect on the list order matters here (the feature words themselves come from K3)
-		AGB_HD inline void encode_forbidden_pass(DynState &d)
+		AGB_HD_NOINLINE inline void encode_forbidden_pass(DynState &d)
 		{
 			if (d.v.rules != RULE_RENJU or d.v.stm != CROSS)
 				return;
@@ -268,7 +326,7 @@ namespace agb
 				entries[2 * i + 1] = kEmptyEntryData;
 			}
 		}
-		AGB_HD inline uint64_t tt_seek(const HashTable &t, uint64_t lo, uint64_t hi)
+		AGB_HD_NOINLINE inline uint64_t tt_seek(const HashTable &t, uint64_t lo, uint64_t hi)
 		{
 			const uint64_t *bucket = t.entries + 8 * (lo & t.bucket_mask);
 			for (int i = 0; i < 4; i++)
@@ -276,7 +334,7 @@ namespace agb
 					return bucket[2 * i + 1];
 			return kEmptyEntryData;
 		}
-		AGB_HD inline void tt_insert(HashTable &t, uint64_t lo, uint64_t hi, uint64_t value)
+		AGB_HD_NOINLINE inline void tt_insert(HashTable &t, uint64_t lo, uint64_t hi, uint64_t value)
 		{
 			value &= ~(kKeyMask | 0xFCull);
 			value |= static_cast<uint64_t>(t.generation) << 2;
@@ -387,17 +445,28 @@ namespace agb
 			lo ^= k[0];
 			hi ^= k[1];
 		}
-		AGB_HD inline void hash_of_board(const HashTable &t, const DynState &d, uint64_t &lo, uint64_t &hi)
+		AGB_HD_NOINLINE inline void hash_of_board(const HashTable &t, const DynState &d, uint64_t &lo, uint64_t &hi)
 		{ // FastZobristHashing::getHash
 			lo = 0;
 			hi = 0;
+#ifdef __CUDA_ARCH__
+			for (int i = threadIdx.x & 31; i < d.v.cells; i += 32) // the lanes of the lockstep warp take interleaved cells
+#else
 			for (int i = 0; i < d.v.cells; i++)
+#endif
 				if (d.board[i] == CROSS or d.board[i] == CIRCLE)
 				{
 					const uint64_t *k = t.keys + 2 * (2 * i + d.board[i] - 1);
 					lo ^= k[0];
 					hi ^= k[1];
 				}
+#ifdef __CUDA_ARCH__
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				lo ^= __shfl_xor_sync(0xFFFFFFFFu, lo, o);
+				hi ^= __shfl_xor_sync(0xFFFFFFFFu, hi, o);
+			}
+#endif
 		}
 
 		// AlphaBetaSearch::solve (AlphaBetaSearch.cpp:77-156) without the time limit; `max_depth` is Search::solve's 100
@@ -557,9 +626,27 @@ namespace agb
 						if (not ordered)
 						{ // selection step: first maximum of the remaining actions
 							int idx = i;
+#ifdef __CUDA_ARCH__
+							{ // the lanes of the warp scan interleaved slices; ties go to the lowest index, like the sequential scan
+								const int lane = threadIdx.x & 31;
+								uint32_t best = 0; // (score << 16) | (0xFFFF - index): larger score first, then smaller index
+								for (int j = i + lane; j < f.list_size; j += 32)
+								{
+									const uint32_t key = (static_cast<uint32_t>(as[j]) << 16) | static_cast<uint32_t>(0xFFFF - j);
+									best = key > best ? key : best;
+								}
+								for (int o = 16; o > 0; o >>= 1)
+								{
+									const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+									best = other > best ? other : best;
+								}
+								idx = 0xFFFF - static_cast<int>(best & 0xFFFFu);
+							}
+#else
 							for (int j = i + 1; j < f.list_size; j++)
 								if (as[idx] < as[j])
 									idx = j;
+#endif
 							const uint16_t tm = am[i], ts = as[i];
 							am[i] = am[idx];
 							as[i] = as[idx];

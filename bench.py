@@ -31,14 +31,15 @@ UNIT = "positions/s"
 SIZE, RULES = 15, 1  # standard 15x15
 BLOCKS, FILTERS = 20, 128
 GAMES, BATCH, SIMS = 4096, 8, 400
+SOLVER_POSITIONS, SOLVER_TABLE_ENTRIES = 100, 65536  # tss max_positions as in the reference config; per-game table 1 MiB (reference: 64 MiB)
 FLOP_PER_POSITION = 2 * 1383.70e6  # BASELINE.md section 3 (algorithmic, ResNet 20x128 @ 15x15, heads p+v)
 
 
-def workload_config(n_gpus, impl="ours"):
+def workload_config(n_gpus, impl="ours", solver=0):
     return {"workload": "configs[1]: standard 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", "rules": "STANDARD",
             "board": "15x15", "network": "ResnetPV 20x128", "games_per_gpu": GAMES, "max_batch_size": BATCH, "max_simulations": SIMS,
-            "solver": ("on (AlphaBetaSearch, max_positions 100)" if impl == "reference" else
-                       "off (device solver K5 not built yet; tasks take the reference's not-processed-by-solver path)"),
+            "solver": ("on (AlphaBetaSearch, max_positions 100, 4 Mi-entry table per game)" if impl == "reference" else
+                       f"on (K5 alpha-beta, max_positions {solver}, {SOLVER_TABLE_ENTRIES}-entry table per game)" if solver > 0 else "off"),
             "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
             "cache_note": "each step streams ~12 MB of weights per board from L2 and touches >1 GB of tree/pattern state, larger than L2"}
 
@@ -171,6 +172,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--games", type=int, default=GAMES)
+    ap.add_argument("--groups", type=int, default=0, help="pipeline groups (0 = engine default)")
+    ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -193,7 +196,8 @@ def main():
     games = args.games
     eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * BATCH, device=local_rank, blocks=BLOCKS, filters=FILTERS,
                      q_head=False, games=games, max_batch_size=BATCH, max_simulations=SIMS, init_to="parent", max_nodes_per_game=1536,
-                     max_edges_per_game=1536 * 200, seed=1234, first_game_id=rank * games)
+                     max_edges_per_game=1536 * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
+                     solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups)
     # C1: rank 0 owns the weights and broadcasts them over NCCL (NetworkLoader::get per thread in the reference)
     blob = netblob.pack(netblob.random_tensors(SIZE, SIZE, BLOCKS, FILTERS, False), SIZE, SIZE, BLOCKS, FILTERS, False) if rank == 0 else None
     eng.load_weights(sharding.broadcast_weights(blob))
@@ -268,14 +272,15 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": max_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(world),
+                "config": workload_config(world, solver=args.solver),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * (SIZE * SIZE + 1)), "d2h_bytes_per_step": int(n_e2e * (SIZE * SIZE + 3) * 4),
                         "api": "agb_evaluate (NNEvaluator::evaluateGraph drop-in): pinned host boards -> K1+K3+K4 -> host policy/value"},
                 "gpu_launches": int(sums[4]),
                 "roofline": {"bound": "tensor", "kernel": "resnet_board_kernel (+ value head)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                              "positions_per_launch": nn_positions / max(nn_launches, 1), "ms_per_launch": nn_ns / max(nn_launches, 1) * 1e-6,
-                             "share_of_step": (nn_ns * 1e-6) / ms},
+                             "share_of_step": (nn_ns * 1e-6) / ms, "solver_share_of_step": (st1["solver_kernel_ns"] - st0["solver_kernel_ns"]) * 1e-6 / ms,
+                             "leaf_positions_per_step": (st1["nb_node_count"] - st0["nb_node_count"]) / args.steps},
                 "clocks": clocks.summary()}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, _ = run_reference(args.cpu_seconds)

@@ -83,7 +83,10 @@ typedef struct AgbConfig
 	int32_t first_game_id; /* global id of this engine's game 0 (rank * games when sharded) */
 	int32_t solver_table_entries; /* entries of each game's solver transposition table (power of two; 0 = 65536; the reference uses 4 Mi,
 	                                 AlphaBetaSearch.cpp:55) */
-	int32_t reserved[6];
+	int32_t pipeline_groups; /* 1: all games advance together; 2: two halves on their own streams, so that one half's solver and tree
+	                            kernels overlap the other half's network kernel; 0 = 2 when the solver is on, else 1. Per-game results
+	                            do not depend on it */
+	int32_t reserved[5];
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -175,7 +178,8 @@ typedef struct AgbStats
 	uint64_t nn_kernel_ns; /* total CUDA-event time of the network kernel launches issued by agb_step */
 	uint64_t nn_kernel_launches;
 	uint64_t nn_positions; /* positions those launches evaluated */
-	uint64_t reserved[3];
+	uint64_t solver_kernel_ns; /* total CUDA-event time of the solver kernel (K5) launches issued by agb_step */
+	uint64_t reserved[2];
 } AgbStats;
 int agb_get_stats(AgbEngine *engine, AgbStats *stats);
 
