@@ -599,45 +599,68 @@ namespace agb
 		}
 
 		// ---- value head: dense(4*cells -> D) + ReLU, dense(D -> 3), softmax (createValueHead, blocks.cpp:112-117) --------
-		// one CTA per board, D threads; 0.02 % of the network's FLOPs
-		__global__ void value_head_kernel(const float *__restrict__ hidden, const float *__restrict__ wd1, const float *__restrict__ bd1,
+		// 0.02 % of the network's FLOPs but 0.9 MB of fp32 weights: a CTA takes kValueBoards boards at a time so that every weight
+		// it pulls from L2 feeds that many dot products (one warp per output neuron, lanes stride over the inputs)
+		constexpr int kValueBoards = 8;
+		__global__ void __launch_bounds__(256) value_head_kernel(const float *__restrict__ hidden, const float *__restrict__ wd1, const float *__restrict__ bd1,
 				const float *__restrict__ wd2, const float *__restrict__ bd2, float *__restrict__ value, int n, int in_dim, int D, const int *__restrict__ n_dev,
 				const int *__restrict__ gather, int slot_base)
 		{
 			if (n_dev != nullptr)
 				n = *n_dev;
-			extern __shared__ float sh[]; // [in_dim] + [D]
-			float *sx = sh, *sd = sh + in_dim;
-			for (int bi = blockIdx.x; bi < n; bi += gridDim.x)
+			extern __shared__ float sh[]; // [kValueBoards][in_dim] + [kValueBoards][D]
+			float *sx = sh, *sd = sh + kValueBoards * in_dim;
+			__shared__ int slot[kValueBoards];
+			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+			for (int b0 = blockIdx.x * kValueBoards; b0 < n; b0 += gridDim.x * kValueBoards)
 			{
-				const int b = gather ? gather[bi] : bi + slot_base;
-				for (int i = threadIdx.x; i < in_dim; i += blockDim.x)
-					sx[i] = hidden[static_cast<size_t>(b) * in_dim + i];
+				const int nb = min(kValueBoards, n - b0);
+				if (threadIdx.x < kValueBoards)
+					slot[threadIdx.x] = (threadIdx.x < nb) ? (gather ? gather[b0 + threadIdx.x] : b0 + threadIdx.x + slot_base) : -1;
 				__syncthreads();
-				const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-				for (int o = warp; o < D; o += nwarps)
-				{ // one warp per output neuron: coalesced reads of its weight row
-					const float *w = wd1 + static_cast<size_t>(o) * in_dim;
-					float s = 0.f;
-					for (int i = lane; i < in_dim; i += 32)
-						s += sx[i] * __ldg(w + i);
-					for (int k = 16; k > 0; k >>= 1)
-						s += __shfl_xor_sync(0xFFFFFFFFu, s, k);
-					if (lane == 0)
-						sd[o] = fmaxf(s + bd1[o], 0.f);
+				for (int k = 0; k < kValueBoards; k++)
+				{
+					const int b = slot[k];
+					for (int i = threadIdx.x; i < in_dim; i += blockDim.x)
+						sx[k * in_dim + i] = (b >= 0) ? hidden[static_cast<size_t>(b) * in_dim + i] : 0.0f;
 				}
 				__syncthreads();
-				if (warp == 0)
+				for (int o = warp; o < D; o += nwarps)
 				{
+					const float *w = wd1 + static_cast<size_t>(o) * in_dim;
+					float s[kValueBoards];
+#pragma unroll
+					for (int k = 0; k < kValueBoards; k++)
+						s[k] = 0.f;
+					for (int i = lane; i < in_dim; i += 32)
+					{
+						const float wi = __ldg(w + i);
+#pragma unroll
+						for (int k = 0; k < kValueBoards; k++)
+							s[k] += sx[k * in_dim + i] * wi;
+					}
+#pragma unroll
+					for (int k = 0; k < kValueBoards; k++)
+					{
+						for (int j = 16; j > 0; j >>= 1)
+							s[k] += __shfl_xor_sync(0xFFFFFFFFu, s[k], j);
+						if (lane == 0)
+							sd[k * D + o] = fmaxf(s[k] + bd1[o], 0.f);
+					}
+				}
+				__syncthreads();
+				if (warp < nb)
+				{ // one warp per board for the last layer
+					const int b = slot[warp];
 					float z[3];
 					for (int k = 0; k < 3; k++)
 					{
-						float s = 0.f;
+						float acc = 0.f;
 						for (int i = lane; i < D; i += 32)
-							s += sd[i] * wd2[k * D + i];
+							acc += sd[warp * D + i] * wd2[k * D + i];
 						for (int o = 16; o > 0; o >>= 1)
-							s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-						z[k] = s + bd2[k];
+							acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+						z[k] = acc + bd2[k];
 					}
 					if (lane == 0)
 					{
@@ -820,7 +843,7 @@ namespace agb
 			AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
 		else
 			AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
-		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cells * 4 + D) * 4));
+		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kValueBoards * (cells * 4 + D) * 4));
 		n->loaded = true;
 		return AGB_OK;
 	}
@@ -871,7 +894,7 @@ namespace agb
 			}
 		}
 		const int cells = e->cells, D = n->dense_width;
-		value_head_kernel<<<n_boards < 4 * sms ? n_boards : 4 * sms, 256, (cells * 4 + D) * 4, stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
+		value_head_kernel<<<std::min((n_boards + kValueBoards - 1) / kValueBoards, 4 * sms), 256, kValueBoards * (cells * 4 + D) * 4, stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
 				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev, gather_dev, slot_base);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());

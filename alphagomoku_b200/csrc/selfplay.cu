@@ -1352,7 +1352,7 @@ namespace agb
 			ok = cudaMemset(s->tasks, 0, T * sizeof(TaskD)) == cudaSuccess; // sticky per-slot flags start cleared
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
-		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : ((c.solver_max_positions > 0 and c.games >= 2) ? 2 : 1);
+		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : 1;
 		if (s->groups > kMaxGroups or s->groups > c.games)
 			return e->fail(AGB_EINVAL, "pipeline_groups must be 1 or 2 and not exceed the number of games");
 		if (s->groups > 1)

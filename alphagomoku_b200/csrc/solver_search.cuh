@@ -43,6 +43,27 @@ namespace agb
 				return;
 			int32_t &count = d.hist_count[colour * kHistTypes + type];
 			uint16_t *list = d.hist_cells + (colour * kHistTypes + type) * d.v.pitch;
+#ifdef __CUDA_ARCH__
+			// lockstep warp: the lanes search interleaved slices, the first match wins like in the sequential scan
+			const int len = count;
+			const int lane = threadIdx.x & 31;
+			int found = -1;
+			for (int base = 0; base < len and found < 0; base += 32)
+			{
+				const int i = base + lane;
+				const unsigned hit = __ballot_sync(0xFFFFFFFFu, i < len and list[i] == loc);
+				if (hit)
+					found = base + __ffs(hit) - 1;
+			}
+			if (found >= 0)
+			{
+				const uint16_t last = list[len - 1];
+				__syncwarp();
+				list[found] = last;
+				count = len - 1;
+			}
+			__syncwarp();
+#else
 			for (int i = 0; i < count; i++)
 				if (list[i] == loc)
 				{
@@ -50,6 +71,7 @@ namespace agb
 					count--;
 					return;
 				}
+#endif
 		}
 		AGB_HD inline void dyn_hist_add(DynState &d, int colour, int type, uint16_t loc)
 		{

@@ -45,7 +45,7 @@ def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, b
     draw_after = 14 if solver == 0 else 28
     eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
                      games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver,
-                     solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0)  # the reference's table size (AlphaBetaSearch.cpp:55)
+                     solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0, pipeline_groups=2 if solver > 0 else 1)  # the reference's table size (AlphaBetaSearch.cpp:55)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
     def evaluate(features):
