@@ -76,6 +76,8 @@ namespace agb
 			uint16_t *stack_moves = nullptr, *stack_scores = nullptr; // [games][stack_capacity]
 			int stack_capacity = 0;
 			void *frames = nullptr; // [games][kMaxFrames] solver::Frame
+			void *children = nullptr; // [games][cells] solver::ChildInfo (previews of the root actions)
+			unsigned long long *game_cycles = nullptr; // [games][2] SM clocks and positions visited by the last launch (load-balance diagnostics)
 			const uint16_t *def_table = nullptr;
 	};
 	// solver.cu

@@ -1487,6 +1487,17 @@ extern "C"
 		return AGB_OK;
 	}
 
+	// diagnostics (not part of the public header): per game, SM clocks and positions visited by the last solver launch
+	int agb_debug_solver_load(AgbEngine *e, unsigned long long *out_host)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or s->solver.game_cycles == nullptr)
+			return e->fail(AGB_ESTATE, "solver is off");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpy(out_host, s->solver.game_cycles, static_cast<size_t>(s->games) * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+		return AGB_OK;
+	}
+
 	int agb_step(AgbEngine *e, int n_steps)
 	{
 		SelfplayState *s = e->selfplay;

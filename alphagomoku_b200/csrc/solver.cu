@@ -30,9 +30,12 @@ namespace agb
 			const bool leader = (threadIdx.x & 31) == 0; // all lanes run the solver in lockstep (solver_search.cuh); one of them publishes
 			const int cells = S * S;
 			const int n_slots = st.game_slot_count[g];
+			const long long t_begin = clock64();
+			unsigned long long nodes_total = 0;
 			solver::HashTable tt { st.table + static_cast<size_t>(g) * st.table_entries * 2, st.table_entries / 4 - 1, st.generation[g], st.keys + static_cast<size_t>(g) * st.keys_stride };
 			solver::SearchMemory mem { st.stack_moves + static_cast<size_t>(g) * st.stack_capacity, st.stack_scores + static_cast<size_t>(g) * st.stack_capacity,
-					st.stack_capacity, reinterpret_cast<solver::Frame*>(st.frames) + static_cast<size_t>(g) * solver::kMaxFrames };
+					st.stack_capacity, reinterpret_cast<solver::Frame*>(st.frames) + static_cast<size_t>(g) * solver::kMaxFrames,
+					reinterpret_cast<solver::ChildInfo*>(st.children) + static_cast<size_t>(g) * cells };
 			for (int k = 0; k < n_slots; k++)
 			{
 				const int slot = st.game_slots[static_cast<size_t>(g) * st.batch + k];
@@ -63,11 +66,17 @@ namespace agb
 				out.score[slot] = res.score;
 				out.must_defend[slot] = res.must_defend ? 1 : 0;
 				out.nodes[slot] = res.node_counter;
+				nodes_total += res.node_counter;
 				if (leader and res.overflow)
 					atomicOr(status, res.overflow << 8); // bits 8..11, see AgbStats::overflow_flags
 				if (leader and (slot_is_root[slot] or not solver::sc_is_proven(res.score)))
 					nn_list[atomicAdd(nn_count, 1)] = slot;
 				__syncwarp();
+			}
+			if (leader)
+			{
+				st.game_cycles[2 * g] = static_cast<unsigned long long>(clock64() - t_begin);
+				st.game_cycles[2 * g + 1] = nodes_total;
 			}
 		}
 		__global__ void clear_tables_kernel(uint64_t *table, size_t n_entries)
@@ -118,6 +127,9 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaMalloc(&st->stack_moves, static_cast<size_t>(games) * st->stack_capacity * sizeof(uint16_t)));
 		AGB_CUDA_CHECK(e, cudaMalloc(&st->stack_scores, static_cast<size_t>(games) * st->stack_capacity * sizeof(uint16_t)));
 		AGB_CUDA_CHECK(e, cudaMalloc(&st->frames, static_cast<size_t>(games) * solver::kMaxFrames * sizeof(solver::Frame)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->game_cycles, static_cast<size_t>(games) * 2 * sizeof(unsigned long long)));
+		AGB_CUDA_CHECK(e, cudaMemset(st->game_cycles, 0, static_cast<size_t>(games) * 2 * sizeof(unsigned long long)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->children, static_cast<size_t>(games) * e->cells * sizeof(solver::ChildInfo)));
 		AGB_CUDA_CHECK(e, cudaMemset(st->generation, 0, games * sizeof(int32_t)));
 		AGB_CUDA_CHECK(e, cudaMemset(st->game_slot_count, 0, games * sizeof(int32_t)));
 		st->def_table = e->d_def_table;
@@ -147,6 +159,8 @@ namespace agb
 		cudaFree(st->stack_moves);
 		cudaFree(st->stack_scores);
 		cudaFree(st->frames);
+		cudaFree(st->children);
+		cudaFree(st->game_cycles);
 		*st = SolverState { };
 	}
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,

@@ -445,11 +445,21 @@ namespace agb
 				uint8_t is_fully_expanded;
 				uint8_t pad;
 		};
+		// What playing one root action would do to the position, worked out without touching the state (see preview_children)
+		constexpr int kMaxChildOps = 14;
+		struct ChildInfo
+		{
+				uint16_t eval; // AlphaBetaSearch::evaluate() of the position after the move, from its side to move
+				uint8_t quiet; // 1: afterwards neither side has a 3x3 fork or anything stronger (MoveGenerator THREATS stages generate nothing)
+				uint8_t n_ops; // 255: more open-three list changes than fit below, the move takes the regular path
+				uint32_t ops[kMaxChildOps]; // cells entering or leaving an OPEN_3 list, in update order: loc | old threats << 16 | new threats << 24
+		};
 		struct SearchMemory
 		{ // scratch of one game (global memory on the device)
 				uint16_t *stack_moves, *stack_scores; // ActionStack
 				int stack_capacity;
 				Frame *frames; // [kMaxFrames]
+				ChildInfo *children; // [cells], indexed by the cell of the root action
 		};
 		struct SearchOutput
 		{
@@ -491,6 +501,180 @@ namespace agb
 #endif
 		}
 
+		// ---- quiet root children without add/undo -------------------------------------------------------------------------------------
+		// In a calm position (nobody has a 3x3 fork or better) nearly every root action leads to a position where the THREATS-mode
+		// generator finds nothing, so the reference's 100-node budget is spent on "add the stone, see that nothing is there, evaluate,
+		// take it back" (AlphaBetaSearch.cpp:262-339 with an empty child list). What such a visit leaves behind is fully determined by
+		// (a) the threat histogram of the child position -> quiet or not, evaluate(); (b) the transposition table traffic; (c) the new
+		// ORDER of the two OPEN_3 lists after addMove + undoMove (the only lists a later generate() reads that a quiet move can touch;
+		// HALF_OPEN_3 lists are never read). (a) and the list edits of (c) are computed for all root actions at once, one action per
+		// lane, straight from the line words; the visit itself then needs no pattern update at all.
+		AGB_HD inline bool is_calm(const View &v)
+		{
+			for (int colour = 0; colour < 2; colour++)
+				for (int t = TT_FORK_3x3; t < kHistTypes; t++)
+					if (v.hist_count[colour * kHistTypes + t] != 0)
+						return false;
+			return true;
+		}
+		AGB_HD inline int eval_weight(int type, bool own)
+		{
+			switch (type)
+			{
+				case TT_OPEN_3: return own ? 19 : -1;
+				case TT_FORK_3x3: return own ? 49 : -50;
+				case TT_HALF_OPEN_4: return own ? 76 : -45;
+				case TT_FORK_4x3: return own ? 170 : -135;
+				case TT_FORK_4x4: return own ? 33 : -14;
+				case TT_OPEN_4: return own ? 159 : -154;
+				case TT_FIVE: return own ? 252 : -496;
+				default: return 0;
+			}
+		}
+		AGB_HD inline void preview_child(const DynState &d, uint16_t move, ChildInfo &out)
+		{ // valid for a calm parent only (the strong lists are empty, so "quiet" is "no strong threat appears")
+			const int S = d.v.S;
+			const int r = (move >> 2) & 127, c = (move >> 9) & 127, sign = move & 3;
+			const int child_own = 3 - sign; // side to move after the move
+			// evaluate() of the parent's histogram seen from the child's side to move, then corrected cell by cell
+			int sum = 12;
+			for (int t = TT_OPEN_3; t <= TT_FIVE; t++)
+				sum += eval_weight(t, true) * d.v.count(child_own, t) + eval_weight(t, false) * d.v.count(3 - child_own, t);
+			int strong = 0, n_ops = 0;
+			const uint8_t centre_t = d.threats[r * S + c];
+			for (int colour = 0; colour < 2; colour++)
+				sum -= eval_weight((centre_t >> (4 * colour)) & 15, colour + 1 == child_own);
+			if ((centre_t & 15) == TT_OPEN_3 or (centre_t >> 4) == TT_OPEN_3)
+				out.ops[n_ops++] = mk_loc(r, c) | (static_cast<uint32_t>(centre_t) << 16);
+			for (int off = -5; off <= 5; off++)
+				if (off != 0)
+					for (int dir = 0; dir < 4; dir++)
+					{
+						const int nr = r + off * dir_row_step(dir), nc = c + off * dir_col_step(dir);
+						if (nr < 0 or nr >= S or nc < 0 or nc >= S)
+							continue;
+						const int ncell = nr * S + nc;
+						if (d.board[ncell] != NONE)
+							continue;
+						const int pos = pos_in_line(dir, r, c, S);
+						const uint64_t line = d.lines[line_index(dir, r, c, S)] | (static_cast<uint64_t>(sign) << (12 + 2 * pos));
+						const uint32_t window = static_cast<uint32_t>(line >> (2 * (pos + off) + 2)) & 0x3FFFFFu;
+						const uint32_t byte = d.v.pattern_table[narrow_window(window)];
+						const uint32_t p = (d.ptypes[ncell] & ~(0xFFu << (8 * dir))) | (byte << (8 * dir));
+						const uint8_t old_t = d.threats[ncell];
+						const uint8_t new_t = threat_of_cell(p, d.threat_table);
+						if (old_t == new_t)
+							continue;
+						bool touches_open3 = false;
+						for (int colour = 0; colour < 2; colour++)
+						{
+							const int o = (old_t >> (4 * colour)) & 15, n = (new_t >> (4 * colour)) & 15;
+							if (o == n)
+								continue;
+							const bool own = (colour + 1 == child_own);
+							sum += eval_weight(n, own) - eval_weight(o, own);
+							strong += (n >= TT_FORK_3x3) ? 1 : 0; // o < FORK_3x3 in a calm parent
+							touches_open3 = touches_open3 or o == TT_OPEN_3 or n == TT_OPEN_3;
+						}
+						if (touches_open3)
+						{
+							if (n_ops < kMaxChildOps)
+								out.ops[n_ops] = mk_loc(nr, nc) | (static_cast<uint32_t>(old_t) << 16) | (static_cast<uint32_t>(new_t) << 24);
+							n_ops++;
+						}
+					}
+			sum = sum < -1000 ? -1000 : (sum > 1000 ? 1000 : sum);
+			out.eval = sc_eval(sum);
+			out.quiet = (strong == 0) ? 1 : 0;
+			out.n_ops = (n_ops <= kMaxChildOps) ? static_cast<uint8_t>(n_ops) : 255;
+		}
+		AGB_HD_NOINLINE inline void preview_children(const DynState &d, const uint16_t *moves, int n, ChildInfo *children)
+		{
+#ifdef __CUDA_ARCH__
+			for (int j = threadIdx.x & 31; j < n; j += 32) // lockstep warp: one root action per lane
+#else
+			for (int j = 0; j < n; j++)
+#endif
+			{
+				const uint16_t mv = moves[j];
+				preview_child(d, mv, children[((mv >> 2) & 127) * d.v.S + ((mv >> 9) & 127)]);
+			}
+#ifdef __CUDA_ARCH__
+			__syncwarp();
+#endif
+		}
+		// the edits addMove + undoMove of this action make to the OPEN_3 lists, in the reference's order (PatternCalculator.cpp:278-366)
+		AGB_HD_NOINLINE inline void replay_open3_edits(DynState &d, uint16_t move, const ChildInfo &info)
+		{
+			const uint16_t centre = mk_loc((move >> 2) & 127, (move >> 9) & 127);
+			for (int phase = 0; phase < 2; phase++) // 0: addMove, 1: undoMove
+				for (int k = 0; k < info.n_ops; k++)
+				{
+					const uint32_t op = info.ops[k];
+					const uint16_t loc = static_cast<uint16_t>(op & 0xFFFFu);
+					const int from = (phase == 0) ? (op >> 16) & 255 : (op >> 24) & 255;
+					const int to = (phase == 0) ? (op >> 24) & 255 : (op >> 16) & 255;
+					for (int colour = 0; colour < 2; colour++)
+					{
+						const int o = (from >> (4 * colour)) & 15, n = (to >> (4 * colour)) & 15;
+						if (o == n)
+							continue;
+						if (o == TT_OPEN_3 and not (phase == 1 and loc == centre)) // undoMove only appends the centre
+							dyn_hist_remove(d, colour, TT_OPEN_3, loc);
+						if (n == TT_OPEN_3 and not (phase == 0 and loc == centre)) // addMove only removes the centre
+							dyn_hist_add(d, colour, TT_OPEN_3, loc);
+					}
+				}
+		}
+
+		// One visit of a quiet child of a calm root, step by step what recursive_solve does for it (AlphaBetaSearch.cpp:185-339 with an
+		// empty action list): table probe, node count, evaluate(), table store; plus the list edits of the add / undo pair around it.
+		// Returns false (nothing done) when the child is not quiet and must take the regular path.
+		AGB_HD_NOINLINE inline bool quiet_child_visit(DynState &d, HashTable &tt, SearchMemory &mem, Frame &f, uint16_t *am, uint16_t *as, int i, uint64_t &key_lo,
+				uint64_t &key_hi, bool &children_previewed, SearchOutput &out)
+		{
+			if (not children_previewed)
+			{
+				preview_children(d, am, f.list_size, mem.children);
+				children_previewed = true;
+			}
+			const uint16_t mv = am[i];
+			const ChildInfo &info = mem.children[((mv >> 2) & 127) * d.v.S + ((mv >> 9) & 127)];
+			if (info.quiet == 0 or info.n_ops == 255)
+				return false;
+			const int depth = f.depth_remaining - 1;
+			const uint16_t alpha = sc_invert(f.beta, -1), beta = sc_invert(f.alpha, -1);
+			hash_toggle(tt, key_lo, key_hi, d.v.S, mv);
+			uint16_t best_move = 0, returned = kScoreDefault;
+			bool done = false;
+			const uint64_t entry = tt_seek(tt, key_lo, key_hi);
+			if (tt_bound(entry) != BOUND_NONE)
+			{
+				best_move = tt_move(entry);
+				const uint16_t s = tt_score(entry);
+				const int b = tt_bound(entry);
+				if (sc_is_proven(s) or (tt_depth(entry) >= depth and (b == BOUND_EXACT or (b == BOUND_LOWER and s >= beta) or (b == BOUND_UPPER and s <= alpha))))
+				{
+					returned = s;
+					done = true;
+				}
+			}
+			if (not done)
+			{
+				out.node_counter++;
+				returned = info.eval;
+				if (depth > 0)
+				{
+					const int bound = (returned <= alpha) ? BOUND_UPPER : ((returned >= beta) ? BOUND_LOWER : BOUND_EXACT);
+					tt_insert(tt, key_lo, key_hi, tt_pack(bound, depth, returned, best_move));
+				}
+			}
+			hash_toggle(tt, key_lo, key_hi, d.v.S, mv);
+			replay_open3_edits(d, mv, info);
+			as[i] = sc_invert(returned, +1);
+			return true;
+		}
+
 		// AlphaBetaSearch::solve (AlphaBetaSearch.cpp:77-156) without the time limit; `max_depth` is Search::solve's 100
 		AGB_HD inline SearchOutput solve_position(DynState &d, HashTable &tt, SearchMemory &mem, int max_nodes, int max_depth)
 		{
@@ -502,6 +686,7 @@ namespace agb
 			bool root_fully_expanded = false;
 			uint16_t result = kScoreDefault;
 			Frame *frames = mem.frames;
+			bool root_calm = false, children_previewed = false;
 
 			for (int depth = 0; depth <= max_depth; depth += 4)
 			{
@@ -571,6 +756,7 @@ namespace agb
 										root_size = gen.out.n_actions;
 										root_fully_expanded = gen.out.is_fully_expanded;
 										out.must_defend = gen.out.must_defend;
+										root_calm = is_calm(d.v);
 									}
 									if (sc_is_proven(gen.out.score))
 									{
@@ -680,6 +866,10 @@ namespace agb
 							if (top + 1 >= kMaxFrames)
 							{
 								out.overflow |= 8u;
+							}
+							else if (top == 0 and root_calm and mem.children != nullptr and d.v.draw_after - (d.v.stones + 1) >= 2
+									and quiet_child_visit(d, tt, mem, f, am, as, i, key_lo, key_hi, children_previewed, out))
+							{ // the visit was carried out without touching the position; as[i] holds the child's score
 							}
 							else
 							{

@@ -167,6 +167,7 @@ struct HostSolver
 		int generation = 0;
 		std::vector<uint16_t> stack_moves, stack_scores;
 		std::vector<agb::solver::Frame> frames;
+		std::vector<agb::solver::ChildInfo> children;
 };
 extern "C" void* hostsim_solver_create(int rules, int S, int draw_after, const uint8_t *pattern_table, const uint8_t *threat_table, const uint16_t *def_table,
 		const uint64_t *keys, size_t table_entries)
@@ -184,6 +185,7 @@ extern "C" void* hostsim_solver_create(int rules, int S, int draw_after, const u
 	h->stack_moves.resize(S * S + 8192);
 	h->stack_scores.resize(S * S + 8192);
 	h->frames.resize(agb::solver::kMaxFrames);
+	h->children.resize(S * S);
 	return h;
 }
 extern "C" void hostsim_solver_destroy(void *p)
@@ -246,7 +248,7 @@ extern "C" int hostsim_solver_solve(void *p, const int8_t *board_in, int stm, in
 		encode_forbidden_pass(d);
 	}
 	HashTable tt { h->table.data(), h->table.size() / 8 - 1, h->generation, h->keys.data() };
-	SearchMemory mem { h->stack_moves.data(), h->stack_scores.data(), static_cast<int>(h->stack_moves.size()), h->frames.data() };
+	SearchMemory mem { h->stack_moves.data(), h->stack_scores.data(), static_cast<int>(h->stack_moves.size()), h->frames.data(), h->children.data() };
 	const SearchOutput out = solve_position(d, tt, mem, max_nodes, 100);
 	for (int i = 0; i < out.n_actions; i++)
 	{

@@ -300,9 +300,12 @@ def test_static_solver_renju_matches_reference_up_to_order(ref_fast, hostsim):
         assert sorted(zip(a[0].tolist(), a[1].tolist())) == sorted(zip(b[0].tolist(), b[1].tolist())), i
 
 
-@pytest.mark.parametrize("rules,size,max_nodes,use_fast", [(0, 15, 100, False), (1, 15, 100, False), (3, 20, 60, False), (4, 15, 400, False),
-                                                             (2, 15, 100, True), (2, 15, 1, True)])
-def test_alpha_beta_solver_matches_reference(ref, ref_fast, hostsim, rules, size, max_nodes, use_fast):
+@pytest.mark.parametrize("rules,size,max_nodes,use_fast,max_fill", [
+    (0, 15, 100, False, 0.45), (1, 15, 100, False, 0.45), (3, 20, 60, False, 0.45), (4, 15, 400, False, 0.45), (2, 15, 100, True, 0.45),
+    (2, 15, 1, True, 0.45),
+    # sparse boards: calm positions, where quiet root children are visited without add/undo (solver_search.cuh: quiet_child_visit)
+    (0, 15, 100, False, 0.08), (1, 15, 100, False, 0.12), (3, 20, 100, False, 0.06), (2, 15, 100, True, 0.08)])
+def test_alpha_beta_solver_matches_reference(ref, ref_fast, hostsim, rules, size, max_nodes, use_fast, max_fill):
     """AlphaBetaSearch::solve with its transposition table kept between positions and generations (AlphaBetaSearch.cpp:77-339,
     SharedHashTable.hpp:27-220) against the host-compiled K5 search (solver_search.cuh): the same hash keys and table size, then the same
     action order, action scores, position score, flags and node count for every position of a sequence. RENJU also pins the ORDER of the
@@ -319,7 +322,7 @@ def test_alpha_beta_solver_matches_reference(ref, ref_fast, hostsim, rules, size
     entries = 4 * 1024 * 1024  # AlphaBetaSearch.cpp:55
     hh = ctypes.c_void_p(hostsim.hostsim_solver_create(rules, size, 0, _p(tables[0]), _p(tables[1]), _p(tables[2]), _p(keys), ctypes.c_size_t(entries)))
     rng = np.random.default_rng(500 + 7 * rules + max_nodes)
-    boards = random_boards(rng, size, 150, max_fill=0.45)
+    boards = random_boards(rng, size, 150, max_fill=max_fill)
     total_nodes = 0
     for i, board in enumerate(boards):
         stm = 1 if (np.count_nonzero(board) % 2 == 0) else 2
