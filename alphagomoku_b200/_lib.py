@@ -57,8 +57,12 @@ SYMBOLS = {
     "agb_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "agb_forward_dev": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "agb_evaluate": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
+    "agb_seed_openings": (_I, [_VP, ctypes.c_uint32]),
+    "agb_prepare_opening": (_I, [_VP, _I, _VP, _VP]),
+    "agb_generate_openings": (_I, [_VP, _I, _VP, _VP]),
     "agb_selfplay_reset": (_I, [_VP, _VP, _VP]),
     "agb_set_solver_keys": (_I, [_VP, _VP, ctypes.c_size_t]),
+    "agb_solve": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "agb_step": (_I, [_VP, _I]),
     "agb_pop_finished": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I)]),
     "agb_get_stats": (_I, [_VP, ctypes.POINTER(AgbStats)]),

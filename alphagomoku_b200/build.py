@@ -7,6 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
 SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu"]
+# host-only sources, compiled by g++ with the reference's floating-point flags (no FMA contraction, libm overloads as in the reference)
+HOST_SOURCES = ["openings.cpp"]
+HOST_FLAGS = ["-O2", "-std=c++17", "-msse2", "-fPIC", "-I/usr/local/cuda/include"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-rdc=false",
@@ -37,6 +40,10 @@ def build(force=False, verbose=False):
         extra = ["-fmad=false"] if src == "selfplay.cu" else []  # tree arithmetic follows the reference op by op (no FMA contraction)
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src in HOST_SOURCES:
+        obj = os.path.join(objdir, src.replace(".cpp", ".o"))
+        cmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     log = []
     for src, obj, p in procs:
@@ -44,7 +51,7 @@ def build(force=False, verbose=False):
         log.append(f"==== {src}\n{out}")
         if p.returncode != 0:
             sys.stderr.write(out)
-            raise RuntimeError(f"nvcc failed on {src}")
+            raise RuntimeError(f"compiler failed on {src}")
         objs.append(obj)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))

@@ -12,6 +12,10 @@ namespace agb
 	struct SelfplayState; // tree.cu
 }
 
+namespace agb
+{
+	struct SolveScratch;
+}
 struct AgbEngine
 {
 		AgbConfig cfg { };
@@ -40,6 +44,9 @@ struct AgbEngine
 
 		agb::NetWeights *net = nullptr;
 		agb::SelfplayState *selfplay = nullptr;
+		agb::SolveScratch *solve_scratch = nullptr; // agb_solve: solver memory for positions outside the lockstep engine
+		std::vector<uint64_t> solver_keys_host; // Zobrist words given through agb_set_solver_keys (applied to every solver state)
+		void *opening_rng = nullptr; // std::mt19937 of the opening generator (openings.cu)
 
 		int fail(int code, const std::string &msg)
 		{
@@ -85,6 +92,8 @@ namespace agb
 	int solver_state_create(AgbEngine *e, int games, int batch, SolverState *st);
 	int solver_state_reset(AgbEngine *e, SolverState *st);
 	void solver_state_destroy(SolverState *st);
+	void solve_scratch_destroy(AgbEngine *e);
+	void openings_destroy(AgbEngine *e);
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
 			int *nn_count, cudaStream_t stream);
 	// tables.cu

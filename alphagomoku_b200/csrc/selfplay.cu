@@ -1467,22 +1467,27 @@ extern "C"
 	int agb_set_solver_keys(AgbEngine *e, const uint64_t *keys_host, size_t n_words)
 	{
 		SelfplayState *s = e->selfplay;
-		if (s == nullptr or s->solver.keys == nullptr)
-			return e->fail(AGB_ESTATE, "engine was created without games or without the solver");
-		const size_t per_set = static_cast<size_t>(s->cells) * 4;
-		if (keys_host == nullptr or (n_words != per_set and n_words != per_set * s->games))
+		const size_t per_set = static_cast<size_t>(e->cells) * 4;
+		const size_t games = (s != nullptr) ? static_cast<size_t>(s->games) : 0;
+		if (keys_host == nullptr or (n_words != per_set and (games == 0 or n_words != per_set * games)))
 			return e->fail(AGB_EINVAL, "expected 2 x 64-bit words for each of 2 * rows * cols (cell, colour) pairs, once or once per game");
-		if (n_words != per_set)
-		{ // one key set per game, like one AlphaBetaSearch per GameGenerator in the reference
-			uint64_t *fresh = nullptr;
-			AGB_CUDA_CHECK(e, cudaMalloc(&fresh, n_words * sizeof(uint64_t)));
-			cudaFree(s->solver.keys);
-			s->solver.keys = fresh;
-			s->solver.keys_stride = per_set;
+		// agb_solve uses the first set (kept on the host for a scratch that is created later)
+		e->solver_keys_host.assign(keys_host, keys_host + per_set);
+		if (s != nullptr and s->solver.keys != nullptr)
+		{
+			if (n_words != per_set)
+			{ // one key set per game, like one AlphaBetaSearch per GameGenerator in the reference
+				uint64_t *fresh = nullptr;
+				AGB_CUDA_CHECK(e, cudaMalloc(&fresh, n_words * sizeof(uint64_t)));
+				cudaFree(s->solver.keys);
+				s->solver.keys = fresh;
+				s->solver.keys_stride = per_set;
+			}
+			else
+				s->solver.keys_stride = 0;
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->solver.keys, keys_host, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
 		}
-		else
-			s->solver.keys_stride = 0;
-		AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->solver.keys, keys_host, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+		solve_scratch_destroy(e); // rebuilt with the new words on the next agb_solve
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		return AGB_OK;
 	}

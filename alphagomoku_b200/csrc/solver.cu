@@ -11,6 +11,8 @@
 #include "engine.hpp"
 #include "solver_search.cuh"
 
+#include <algorithm>
+#include <string>
 #include <vector>
 
 namespace agb
@@ -173,4 +175,133 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
 	}
+}
+
+// ---- agb_solve: the solver on caller-supplied positions (AlphaBetaSearch::solve as a service) -----------------------------------------
+namespace agb
+{
+	struct SolveScratch
+	{
+			SolverState state { };
+			SolverOutputs out { };
+			uint8_t *slot_is_root = nullptr;
+			int32_t *nn_list = nullptr, *nn_count = nullptr;
+			int capacity = 0;
+	};
+	namespace
+	{
+		__global__ void iota_kernel(int32_t *slots, int32_t *counts, int n)
+		{
+			const int i = blockIdx.x * blockDim.x + threadIdx.x;
+			if (i < n)
+			{
+				slots[i] = i;
+				counts[i] = 1;
+			}
+		}
+		int solve_scratch_create(AgbEngine *e)
+		{
+			SolveScratch *sc = new SolveScratch();
+			e->solve_scratch = sc;
+			const size_t entries = e->cfg.solver_table_entries > 0 ? static_cast<size_t>(e->cfg.solver_table_entries) : 65536;
+			const size_t by_memory = std::max<size_t>(1, (static_cast<size_t>(4) << 30) / (entries * 16)); // at most 4 GiB of tables
+			sc->capacity = static_cast<int>(std::min<size_t>(std::min(e->cfg.max_boards, 2048), by_memory));
+			const size_t n = sc->capacity, cells = e->cells;
+			int rc = solver_state_create(e, sc->capacity, 1, &sc->state);
+			if (rc != AGB_OK)
+				return rc;
+			sc->out.pitch = static_cast<int>(cells);
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->out.moves, n * cells * sizeof(uint16_t)));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->out.scores, n * cells * sizeof(uint16_t)));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->out.n_actions, n * sizeof(int32_t)));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->out.score, n * sizeof(uint16_t)));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->out.must_defend, n));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->out.nodes, n * sizeof(int32_t)));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->slot_is_root, n));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->nn_list, n * sizeof(int32_t)));
+			AGB_CUDA_CHECK(e, cudaMalloc(&sc->nn_count, sizeof(int32_t)));
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(sc->slot_is_root, 0, n, e->stream));
+			iota_kernel<<<(sc->capacity + 255) / 256, 256, 0, e->stream>>>(sc->state.game_slots, sc->state.game_slot_count, sc->capacity);
+			AGB_CUDA_CHECK(e, cudaGetLastError());
+			if (not e->solver_keys_host.empty() and e->solver_keys_host.size() == static_cast<size_t>(e->cells) * 4)
+				AGB_CUDA_CHECK(e, cudaMemcpyAsync(sc->state.keys, e->solver_keys_host.data(), e->solver_keys_host.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
+						e->stream));
+			AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+			return AGB_OK;
+		}
+	}
+	void solve_scratch_destroy(AgbEngine *e)
+	{
+		SolveScratch *sc = e->solve_scratch;
+		if (sc == nullptr)
+			return;
+		solver_state_destroy(&sc->state);
+		void *ptrs[] = { sc->out.moves, sc->out.scores, sc->out.n_actions, sc->out.score, sc->out.must_defend, sc->out.nodes, sc->slot_is_root, sc->nn_list,
+				sc->nn_count };
+		for (void *ptr : ptrs)
+			if (ptr)
+				cudaFree(ptr);
+		delete sc;
+		e->solve_scratch = nullptr;
+	}
+}
+
+extern "C" int agb_solve(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, int max_positions, uint16_t *scores_host,
+		int32_t *n_actions_host, uint16_t *moves_host, uint16_t *action_scores_host, int32_t *flags_host)
+{
+	using namespace agb;
+	if (boards_host == nullptr or sign_to_move_host == nullptr or scores_host == nullptr)
+		return e->fail(AGB_EINVAL, "null pointer");
+	if (n < 0 or max_positions < 1)
+		return e->fail(AGB_EINVAL, "n must be >= 0 and max_positions >= 1");
+	if (e->solve_scratch == nullptr)
+	{
+		const int rc = solve_scratch_create(e);
+		if (rc != AGB_OK)
+			return rc;
+	}
+	SolveScratch *sc = e->solve_scratch;
+	const size_t cells = e->cells;
+	const int saved = e->cfg.solver_max_positions;
+	for (int begin = 0; begin < n; begin += sc->capacity)
+	{
+		const int count = std::min(sc->capacity, n - begin);
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8, boards_host + begin * cells, count * cells, cudaMemcpyHostToDevice, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8b, sign_to_move_host + begin, count, cudaMemcpyHostToDevice, e->stream));
+		int rc = launch_set_boards(e, e->d_io8, e->d_io8b, count, e->d_features); // K1 (+K3)
+		if (rc != AGB_OK)
+			return rc;
+		rc = solver_state_reset(e, &sc->state); // every position starts from a cleared table (AlphaBetaSearch::clear)
+		if (rc != AGB_OK)
+			return rc;
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(sc->nn_count, 0, sizeof(int32_t), e->stream));
+		e->cfg.solver_max_positions = max_positions;
+		rc = launch_solve_games(e, sc->state, 0, count, sc->out, sc->slot_is_root, sc->nn_list, sc->nn_count, e->stream);
+		e->cfg.solver_max_positions = saved;
+		if (rc != AGB_OK)
+			return rc;
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(scores_host + begin, sc->out.score, count * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream));
+		if (n_actions_host)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(n_actions_host + begin, sc->out.n_actions, count * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+		if (moves_host)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(moves_host + begin * cells, sc->out.moves, count * cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream));
+		if (action_scores_host)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(action_scores_host + begin * cells, sc->out.scores, count * cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream));
+		if (flags_host)
+		{ // bit0 must_defend, bits 8.. positions visited
+			std::vector<uint8_t> md(count);
+			std::vector<int32_t> nodes(count);
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(md.data(), sc->out.must_defend, count, cudaMemcpyDeviceToHost, e->stream));
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(nodes.data(), sc->out.nodes, count * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+			AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+			for (int i = 0; i < count; i++)
+				flags_host[begin + i] = static_cast<int32_t>(md[i]) | (nodes[i] << 8);
+		}
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+	}
+	uint32_t status = 0;
+	AGB_CUDA_CHECK(e, cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+	if (status != 0)
+		return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status));
+	return AGB_OK;
 }

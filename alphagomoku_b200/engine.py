@@ -187,11 +187,40 @@ class Engine:
         self._check(self._lib.agb_evaluate(self._h, _ptr(boards), _ptr(stm), _ptr(sym), n, _ptr(policy), _ptr(value), _ptr(q)))
         return policy, value, q
 
+    # ---- openings (OpeningGenerator) ------------------------------------------------------------------------------------
+    def seed_openings(self, seed):
+        self._check(self._lib.agb_seed_openings(self._h, seed))
+
+    def prepare_opening(self, min_moves=1):
+        """prepareOpening(config, min_moves): list of Move::toShort words."""
+        moves = np.zeros(self.cells, np.uint16)
+        n = ctypes.c_int32()
+        self._check(self._lib.agb_prepare_opening(self._h, min_moves, _ptr(moves), ctypes.byref(n)))
+        return moves[:n.value].copy()
+
+    def generate_openings(self, count):
+        """OpeningGenerator::generate: `count` unproven, balanced openings -> boards int8 [count, cells], sign_to_move int8 [count]."""
+        boards, stm = np.zeros((count, self.cells), np.int8), np.zeros(count, np.int8)
+        self._check(self._lib.agb_generate_openings(self._h, count, _ptr(boards), _ptr(stm)))
+        return boards, stm
+
     # ---- lockstep self-play ------------------------------------------------------------------------------------------
     def selfplay_reset(self, boards=None, sign_to_move=None):
         b = None if boards is None else np.ascontiguousarray(boards, np.int8)
         s = None if sign_to_move is None else np.ascontiguousarray(sign_to_move, np.int8)
         self._check(self._lib.agb_selfplay_reset(self._h, _ptr(b), _ptr(s)))
+
+    def solve(self, boards, sign_to_move, max_positions=100):
+        """AlphaBetaSearch::solve on n positions (each from a cleared table). Returns scores uint16 [n], n_actions int32 [n],
+        moves uint16 [n, cells], action_scores uint16 [n, cells], flags int32 [n] (bit 0 must-defend, bits 8.. positions visited)."""
+        b = np.ascontiguousarray(boards, np.int8).reshape(-1, self.cells)
+        s = np.ascontiguousarray(sign_to_move, np.int8)
+        n = b.shape[0]
+        scores, n_actions, flags = np.zeros(n, np.uint16), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        moves, action_scores = np.zeros((n, self.cells), np.uint16), np.zeros((n, self.cells), np.uint16)
+        self._check(self._lib.agb_solve(self._h, _ptr(b), _ptr(s), n, max_positions, _ptr(scores), _ptr(n_actions), _ptr(moves), _ptr(action_scores),
+                                        _ptr(flags)))
+        return scores, n_actions, moves, action_scores, flags
 
     def set_solver_keys(self, keys):
         """Zobrist words of the solver's transposition tables: uint64 [2 * cells, 2] (FastZobristHashing::m_keys)."""

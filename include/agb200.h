@@ -146,14 +146,32 @@ int agb_forward_dev(AgbEngine *engine, const uint32_t *features_dev, int n, floa
 int agb_evaluate(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *symmetry_host, int n,
 		float *policy_host, float *value_host, float *q_host);
 
+/* ---- opening generation (OpeningGenerator, src/selfplay/OpeningGenerator.cpp:21-78; prepareOpening, src/utils/misc.cpp:142-170) -----
+ * The generator's std::mt19937 starts from the low 32 bits of AgbConfig::seed; agb_seed_openings restarts it. */
+int agb_seed_openings(AgbEngine *engine, uint32_t seed);
+/* one random opening like prepareOpening(config, min_moves): moves[<= rows*cols] Move::toShort words, *n_moves their number */
+int agb_prepare_opening(AgbEngine *engine, int min_moves, uint16_t *moves_host, int32_t *n_moves);
+/* `count` balanced openings: random openings that the solver (1000 positions) cannot prove and whose network expectation is within
+ * 0.1 + 0.01 * trials of 0.5 (OpeningGenerator::generate). boards[count][rows*cols] int8, sign_to_move[count]; feed them to
+ * agb_selfplay_reset. Needs loaded weights. */
+int agb_generate_openings(AgbEngine *engine, int count, int8_t *boards_host, int8_t *sign_to_move_host);
+
 /* ---- lockstep self-play (GameGenerator::generate, src/selfplay/GameGenerator.cpp:46-121, over all games) ------- */
 /* start (or restart) all games from given positions: boards[games][cells], sign_to_move[games]; NULL = empty boards, cross to move */
 int agb_selfplay_reset(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host);
+/* ---- solver as a service (AlphaBetaSearch::solve, src/search/alpha_beta/AlphaBetaSearch.cpp:77-156) -------------------------------
+ * Solves n caller-supplied positions, each from a cleared transposition table, with a budget of max_positions search nodes
+ * (1 = static move generator + evaluation only). scores[n]: Score::to_short of the position score. Optional outputs (NULL to skip):
+ * n_actions[n]; moves[n][cells] / action_scores[n][cells]: the root action list in its final order (what Search::solve leaves in
+ * SearchTask::getEdges / getActionScores); flags[n]: bit 0 must-defend, bits 8.. positions visited. */
+int agb_solve(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, int max_positions, uint16_t *scores_host,
+		int32_t *n_actions_host, uint16_t *moves_host, uint16_t *action_scores_host, int32_t *flags_host);
 /* replace the Zobrist words of the solver's transposition tables: keys[2 * rows * cols][2] = (low, high) 64-bit word of
  * (cell, CROSS) then (cell, CIRCLE), i.e. FastZobristHashing::m_keys (include/alphagomoku/search/ZobristHashing.hpp:111-127).
  * The words only decide which bucket a position maps to; parity tests pass the reference's own so that bucket replacement
  * (SharedHashTable::insert, SharedHashTable.hpp:160-181) sees the same collisions. n_words = 4 * rows * cols for one set shared by all
- * games, or games times that for one set per game (the reference has one per GameGenerator). Call before agb_selfplay_reset. */
+ * games, or games times that for one set per game (the reference has one per GameGenerator); agb_solve uses the first set. Call before
+ * agb_selfplay_reset. */
 int agb_set_solver_keys(AgbEngine *engine, const uint64_t *keys_host, size_t n_words);
 /* advance every game by n_steps lockstep iterations of select -> solve/encode -> evaluate -> expand -> backup (-> move) */
 int agb_step(AgbEngine *engine, int n_steps);

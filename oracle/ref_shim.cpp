@@ -5,6 +5,7 @@
 // Every entry point is a thin call into a reference class; no algorithm lives here.
 #include <alphagomoku/game/Board.hpp>
 #include <alphagomoku/game/rules.hpp>
+#include <alphagomoku/utils/misc.hpp>
 #include <alphagomoku/networks/NNInputFeatures.hpp>
 #include <alphagomoku/patterns/DefensiveMoveTable.hpp>
 #include <alphagomoku/patterns/PatternCalculator.hpp>
@@ -197,5 +198,14 @@ extern "C"
 	int agref_inverse_symmetry(int mode)
 	{
 		return static_cast<int>(get_inverse_symmetry(int_to_symmetry(mode)));
+	}
+	// prepareOpening (src/utils/misc.cpp:142-170) with the library's own thread-local generator (seed 0 in this debug build, advanced
+	// by every randInt / randFloat the calling thread has made so far)
+	int agref_prepare_opening(int rules, int rows, int cols, int min_moves, uint16_t *moves)
+	{
+		const std::vector<Move> result = prepareOpening(GameConfig(static_cast<GameRules>(rules), rows, cols), min_moves);
+		for (size_t i = 0; i < result.size(); i++)
+			moves[i] = result[i].toShort();
+		return static_cast<int>(result.size());
 	}
 }

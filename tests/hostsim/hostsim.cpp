@@ -260,3 +260,22 @@ extern "C" int hostsim_solver_solve(void *p, const int8_t *board_in, int stm, in
 			| (out.node_counter << 8) | (out.overflow ? (1 << 30) : 0);
 	return out.n_actions;
 }
+
+// a22: prepareOpening with a std::mt19937 seeded like the reference's debug build (seed 0)
+#include "../../alphagomoku_b200/csrc/openings_logic.hpp"
+extern "C" void* hostsim_openings_create(uint32_t seed)
+{
+	return new agb::openings::Random(seed);
+}
+extern "C" void hostsim_openings_destroy(void *p)
+{
+	delete static_cast<agb::openings::Random*>(p);
+}
+extern "C" int hostsim_prepare_opening(void *p, int rules, int S, int min_moves, const uint8_t *pattern_table, const uint8_t *threat_table, uint16_t *moves)
+{
+	std::vector<int8_t> board;
+	const agb::Tables tables { pattern_table, threat_table };
+	const std::vector<uint16_t> result = agb::openings::prepare_opening(rules, S, S, tables, *static_cast<agb::openings::Random*>(p), min_moves, board);
+	std::copy(result.begin(), result.end(), moves);
+	return static_cast<int>(result.size());
+}
