@@ -79,6 +79,7 @@ namespace agb
 			float *d_policy = nullptr, *d_value = nullptr, *d_q = nullptr; // staging for host entry point
 			int dense_width = 0;
 			size_t smem_bytes = 0;
+			bool split = false; // one board per CTA pair (boards of more than 15 rows)
 			bool loaded = false;
 	};
 
@@ -105,15 +106,15 @@ namespace agb
 			hi = __uint_as_float(w & 0xFFFF0000u);
 		}
 
-		// Straight-line MMA schedule of one 3x3, F -> F convolution on a 15x15 board (the trunk and head convs: 40 of the
+		// Straight-line MMA schedule of one 3x3, F -> F convolution with row pitch P (17: 15x15 board, 22: 20x20 board split over the CTA
+		// pair) (the trunk and head convs: 40 of the
 		// 42 layers of a 20-block net). The issuing lane cannot hide latency, so everything that can be a compile-time constant
 		// is one: tap offsets (row pitch 17), K-slice offsets and the weight-ring geometry (32 KiB stages). Per MMA pair the lane
 		// executes two 64-bit adds and the two tcgen05.mma instructions.
-		template<int F>
-		__device__ __forceinline__ void issue_conv3x3_15(uint32_t tmem_base, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
+		template<int F, int P>
+		__device__ __forceinline__ void issue_conv3x3(uint32_t tmem_base, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
 				uint32_t stage_step, uint64_t *w_full, uint64_t *peer_full, uint64_t *w_empty, int &stage, uint32_t &phase, int n_stages)
 		{
-			constexpr int P = 17;
 			constexpr int KC = F / 8; // 8-channel slices per tap
 			constexpr int TPS = 32768 / ((F / 2) * 16 * KC); // taps per 32 KiB stage: 2 (F = 128) or 8 (F = 64)
 #pragma unroll
@@ -153,7 +154,10 @@ namespace agb
 			}
 		}
 
-		template<int F>
+		// SPLIT = false: one board per CTA (two per pair), boards up to 15x15. SPLIT = true: one board per PAIR, boards of 16..20 rows: rank 0
+		// owns the upper rows, rank 1 the lower ones; after every layer each CTA writes its boundary row into the other's halo row through
+		// distributed shared memory, so the tensor-core schedule is the same as for two independent boards.
+		template<int F, bool SPLIT>
 		__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) resnet_board_kernel(const __grid_constant__ NetParams prm)
 		{
 			extern __shared__ __align__(1024) uint8_t smem[];
@@ -167,12 +171,14 @@ namespace agb
 			float *logits = partial + 2 * 3 * 256; // [256]
 			float *reduce = logits + 256; // [8]
 			float *sbias2 = reduce + 8; // [2][128]
-			uint64_t *bars = reinterpret_cast<uint64_t*>(sbias2 + 256);
-			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *img_ready = bars + 17, *peer_full = bars + 18;
-			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+			float *xchg = sbias2 + 256; // [2] softmax (max, sum) of the peer's half board (SPLIT)
+			uint64_t *bars = reinterpret_cast<uint64_t*>(xchg + 8);
+			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *img_ready = bars + 17, *peer_full = bars + 18, *xbar = bars + 26;
+			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 			// CTA pair: rank 0 (leader) issues the MMAs for both boards; each CTA loads half of every weight tile
 			const uint32_t rank = cluster_ctarank();
 			const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+			const int board_first = SPLIT ? pair : 2 * pair, board_step = SPLIT ? n_pairs : 2 * n_pairs;
 
 			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 			const uint32_t img_chunk_bytes = prm.img_rows * 16;
@@ -188,6 +194,7 @@ namespace agb
 					mbar_init(&peer_full[s], 1);
 				}
 				mbar_init(acc_full, 1);
+				mbar_init(xbar, 1);
 				mbar_init(img_ready, 2 * (kEpilogueThreads / 32)); // one arrival per epilogue warp of both CTAs, on the leader's barrier
 				fence_mbar_init();
 			}
@@ -211,7 +218,7 @@ namespace agb
 				{
 					int stage = 0;
 					uint32_t phase = 0;
-					for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
+					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -239,7 +246,7 @@ namespace agb
 					int stage = 0;
 					uint32_t phase = 0, img_phase = 0;
 					const uint32_t idesc = idesc_bf16_f32(256, F); // M = 256: 128 positions of this CTA's board + 128 of the peer's
-					for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
+					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -258,9 +265,9 @@ namespace agb
 								prm.trace[6 * l + 0] = clock64();
 							int kin = 0, ky = 0, kx = 0; // position in the layer's stream of 8-channel weight slices
 							long long wait_own = 0, wait_peer = 0;
-							const bool fast = (S == 15 and L.radius == 1 and cin_chunks == F / 8 and prm.stage_bytes == 32768);
+							const bool fast = (S == (SPLIT ? 20 : 15) and L.radius == 1 and cin_chunks == F / 8 and prm.stage_bytes == 32768);
 							if (fast)
-								issue_conv3x3_15<F>(tmem_base, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, stage, phase, NS);
+								issue_conv3x3<F, SPLIT ? 22 : 17>(tmem_base, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, stage, phase, NS);
 							else
 							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
@@ -319,7 +326,7 @@ namespace agb
 				{ // peer CTA: tell the leader when our half of each weight stage has landed
 					int stage = 0;
 					uint32_t phase = 0;
-					for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
+					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const int total_kc = prm.layers[l].n_taps * prm.layers[l].cin_chunks;
@@ -342,20 +349,28 @@ namespace agb
 				const int quadrant = warp & 3; // TMEM lanes 32*quadrant .. +31 are the ones this warp may read
 				const int half = (warp - 2) >> 2; // which half of the output channels
 				const int cells = S * S;
-				uint32_t acc_phase = 0;
-				for (int b0 = 2 * pair; b0 < n_boards; b0 += 2 * n_pairs)
+				uint32_t acc_phase = 0, xchg_phase = 0;
+				// rows of the board this CTA computes: all of them, or (SPLIT) the upper / lower part
+				const int rows0 = SPLIT ? (S + 1) / 2 : S;
+				const int my_rows = SPLIT ? (rank == 0 ? rows0 : S - rows0) : S;
+				const int row_begin = (SPLIT and rank == 1) ? rows0 : 0;
+				const int halo_in = SPLIT ? 2 : 0; // rows of the neighbouring part that the 5x5 stem reads: taken from the features directly
+				for (int b0 = board_first; b0 < n_boards; b0 += board_step)
 				{
-					const int bi = b0 + rank; // this CTA's board in the launch
+					const int bi = SPLIT ? b0 : b0 + rank; // this CTA's board in the launch
 					const bool live = bi < n_boards;
 					const int b = (live and prm.gather != nullptr) ? prm.gather[bi] : bi + prm.slot_base; // its slot in the feature / output arrays // an odd batch leaves the last peer without a board: it still runs every barrier
 					// ---- prologue: feature words -> bf16 stem image (32 channels, halo 2) in the h buffer ----
 					for (uint32_t i = et; i < 4 * in_chunk_bytes / 16; i += kEpilogueThreads)
 						reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
 					named_barrier_epilogue();
-					for (int cell = et; cell < cells; cell += kEpilogueThreads)
+					for (int lc = et; lc < (my_rows + 2 * halo_in) * S; lc += kEpilogueThreads)
 					{
-						const uint32_t f = live ? prm.features[static_cast<size_t>(b) * cells + cell] : 0u;
-						const int y = cell / S, x = cell - y * S;
+						const int y = lc / S - halo_in, x = lc - (y + halo_in) * S; // row relative to this CTA's first row
+						const int gy = row_begin + y;
+						if (gy < 0 or gy >= S)
+							continue;
+						const uint32_t f = live ? prm.features[static_cast<size_t>(b) * cells + gy * S + x] : 0u;
 						const uint32_t idx = (y + 2) * P + x + 2;
 #pragma unroll
 						for (int k = 0; k < 4; k++)
@@ -402,12 +417,16 @@ namespace agb
 						uint8_t *out_img = (L.mode == MODE_CONV1) ? buf_h : buf_x;
 						float head[2][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
 						constexpr int HC = F / 2; // output channels handled by this warp (its half), as HC/16 TMEM loads of 16 columns
+						// SPLIT: the row next to the other part also goes into the peer's halo row of the same image (distributed shared memory)
+						const uint32_t peer_img = SPLIT ? map_to_rank(smem_u32(out_img), rank ^ 1u) : 0u;
 						for (int tile = 0; tile < 2; tile++)
 						{
 							const int p = tile * 128 + quadrant * 32 + lane;
 							const int y = p / P, x = p - y * P;
-							const bool valid = (y < S) and (x < S);
+							const bool valid = (y < my_rows) and (x < S);
 							const uint32_t out_idx = p + P + 1;
+							const bool send = SPLIT and valid and (rank == 0 ? (y == my_rows - 1) : (y == 0));
+							const uint32_t peer_idx = (rank == 0) ? (x + 1) : ((rows0 + 1) * P + x + 1);
 							// all TMEM loads of this tile are issued back to back and waited for once
 							uint32_t v[HC];
 #pragma unroll
@@ -478,6 +497,8 @@ namespace agb
 											o.z = pack_bf16_relu(a[8 * h8 + 4], a[8 * h8 + 5]);
 											o.w = pack_bf16_relu(a[8 * h8 + 6], a[8 * h8 + 7]);
 											*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
+											if (send)
+												st_peer_v4(peer_img + (c0 / 8 + h8) * img_chunk_bytes + peer_idx * 16, o);
 										}
 									}
 								}
@@ -492,7 +513,7 @@ namespace agb
 							named_barrier_epilogue();
 							{
 								const int p = et, y = p / P, x = p - y * P;
-								const bool valid = (y < S) and (x < S);
+								const bool valid = (y < my_rows) and (x < S);
 								logits[p] = valid ? (partial[p] + partial[256 + p] + __ldg(prm.policy_w1 + F)) : -INFINITY;
 							}
 							named_barrier_epilogue();
@@ -516,9 +537,26 @@ namespace agb
 							s = 0.0f;
 							for (int w = 0; w < 8; w++)
 								s += reduce[w];
+							float out = e / s;
+							if constexpr (SPLIT)
+							{ // the two halves of the board merge their (max, sum) pairs: one exchange through the peer's shared memory
+								if (et == 0)
+								{
+									const uint32_t peer_xchg = map_to_rank(smem_u32(xchg), rank ^ 1u);
+									st_peer_f32(peer_xchg, m);
+									st_peer_f32(peer_xchg + 4, s);
+									mbar_arrive_remote(xbar, rank ^ 1u);
+								}
+								mbar_wait_cluster(xbar, xchg_phase & 1);
+								xchg_phase++;
+								const float m_peer = xchg[0], s_peer = xchg[1];
+								const float m_all = fmaxf(m, m_peer);
+								const float scale = expf(m - m_all);
+								out = e * scale / (s * scale + s_peer * expf(m_peer - m_all));
+							}
 							const int p = et, y = p / P, x = p - y * P;
-							if (live and y < S and x < S)
-								prm.policy[static_cast<size_t>(b) * cells + y * S + x] = e / s;
+							if (live and y < my_rows and x < S)
+								prm.policy[static_cast<size_t>(b) * cells + (row_begin + y) * S + x] = out;
 							named_barrier_epilogue();
 						}
 						else if (L.mode == MODE_QHEAD)
@@ -528,7 +566,7 @@ namespace agb
 									partial[(half * 3 + k) * 256 + tile * 128 + quadrant * 32 + lane] = head[tile][k];
 							named_barrier_epilogue();
 							const int p = et, y = p / P, x = p - y * P;
-							if (live and y < S and x < S and prm.q != nullptr)
+							if (live and y < my_rows and x < S and prm.q != nullptr)
 							{
 								float z[3];
 								for (int k = 0; k < 3; k++)
@@ -536,7 +574,7 @@ namespace agb
 								const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
 								const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
 								const float inv = 1.0f / (e0 + e1 + e2);
-								float *dst = prm.q + (static_cast<size_t>(b) * cells + y * S + x) * 3;
+								float *dst = prm.q + (static_cast<size_t>(b) * cells + (row_begin + y) * S + x) * 3;
 								dst[0] = e0 * inv;
 								dst[1] = e1 * inv;
 								dst[2] = e2 * inv;
@@ -546,9 +584,10 @@ namespace agb
 						else if (L.last_trunk)
 						{ // value head 1x1 conv F -> 4 + ReLU on the final trunk output (createValueHead, blocks.cpp:108-111)
 							named_barrier_epilogue();
-							for (int cell = et; cell < cells; cell += kEpilogueThreads)
+							for (int lc = et; lc < my_rows * S; lc += kEpilogueThreads)
 							{
-								const int y = cell / S, x = cell - y * S;
+								const int y = lc / S, x = lc - y * S;
+								const int cell = (row_begin + y) * S + x;
 								const uint32_t idx = (y + 1) * P + x + 1;
 								float s4[4] = { 0.f, 0.f, 0.f, 0.f };
 								for (int ch = 0; ch < F / 8; ch++)
@@ -578,12 +617,20 @@ namespace agb
 							prm.trace[6 * l + 3] = clock64();
 						if (l + 1 < prm.n_layers)
 						{ // hand the image (and the drained accumulators) to the MMA warp
-							fence_proxy_async();
+							if constexpr (SPLIT)
+								fence_proxy_async_all(); // covers the rows written into the peer's image
+							else
+								fence_proxy_async();
 							__syncwarp();
 							if (lane == 0)
 							{
 								if (rank == 0)
-									mbar_arrive(img_ready);
+								{
+									if constexpr (SPLIT)
+										mbar_arrive_cluster(img_ready);
+									else
+										mbar_arrive(img_ready);
+								}
 								else
 									mbar_arrive_remote(img_ready, 0);
 							}
@@ -712,8 +759,8 @@ namespace agb
 		const AgbConfig &c = e->cfg;
 		if (c.filters != 64 and c.filters != 128)
 			return e->fail(AGB_EINVAL, "filters must be 64 or 128");
-		if (c.rows * (c.rows + 2) > 256)
-			return e->fail(AGB_EINVAL, "network kernel supports boards up to 15x15 in this build (20x20 planned, see DESIGN.md)");
+		if (c.rows != c.cols or c.rows > 20 or c.rows < 5)
+			return e->fail(AGB_EINVAL, "network kernel supports square boards of 5..20 rows");
 		if (1 + 2 * c.blocks + 2 > kMaxConvLayers)
 			return e->fail(AGB_EINVAL, "too many blocks");
 		e->net = new NetWeights();
@@ -838,11 +885,13 @@ namespace agb
 		p.q_w1 = c.q_head ? n->d_small + q_w1_off : nullptr;
 		p.value_hidden = n->d_value_hidden;
 		n->dense_width = D;
-		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (2 * 3 * 256 + 256 + 8 + 256) * 4 + 20 * 8;
-		if (F == 128)
-			AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
-		else
-			AGB_CUDA_CHECK(e, cudaFuncSetAttribute(resnet_board_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
+		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (2 * 3 * 256 + 256 + 8 + 256 + 8) * 4 + 32 * 8;
+		n->split = S * (S + 2) > 256; // the board does not fit one CTA's 256 accumulator rows: one board per CTA pair
+		if (n->smem_bytes > 232448)
+			return e->fail(AGB_EINVAL, "network kernel needs " + std::to_string(n->smem_bytes) + " bytes of shared memory per CTA, more than the device has");
+		const void *kernel = n->split ? (F == 128 ? reinterpret_cast<const void*>(resnet_board_kernel<128, true>) : reinterpret_cast<const void*>(resnet_board_kernel<64, true>))
+				: (F == 128 ? reinterpret_cast<const void*>(resnet_board_kernel<128, false>) : reinterpret_cast<const void*>(resnet_board_kernel<64, false>));
+		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(n->smem_bytes)));
 		AGB_CUDA_CHECK(e, cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kValueBoards * (cells * 4 + D) * 4));
 		n->loaded = true;
 		return AGB_OK;
@@ -871,12 +920,22 @@ namespace agb
 		p.trace = trace ? d_trace : nullptr;
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
-		const int pairs = std::min((n_boards + 1) / 2, sms / 2);
-		const int grid = 2 * pairs; // clusters of two CTAs, one board each
-		if (p.F == 128)
-			resnet_board_kernel<128><<<grid, kThreads, n->smem_bytes, stream>>>(p);
+		const int pairs = std::min(n->split ? n_boards : (n_boards + 1) / 2, sms / 2);
+		const int grid = 2 * pairs; // clusters of two CTAs: one board each, or (large boards) one board per pair
+		if (n->split)
+		{
+			if (p.F == 128)
+				resnet_board_kernel<128, true><<<grid, kThreads, n->smem_bytes, stream>>>(p);
+			else
+				resnet_board_kernel<64, true><<<grid, kThreads, n->smem_bytes, stream>>>(p);
+		}
 		else
-			resnet_board_kernel<64><<<grid, kThreads, n->smem_bytes, stream>>>(p);
+		{
+			if (p.F == 128)
+				resnet_board_kernel<128, false><<<grid, kThreads, n->smem_bytes, stream>>>(p);
+			else
+				resnet_board_kernel<64, false><<<grid, kThreads, n->smem_bytes, stream>>>(p);
+		}
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		if (trace)

@@ -186,6 +186,29 @@ namespace agb
 					:: "r"(smem_u32(bar)), "r"(target_rank) : "memory");
 		}
 		// wait with cluster-scope acquire: pairs with remote arrivals from the peer CTA
+		// ---- distributed shared memory of the CTA pair (board split over two CTAs) ----
+		__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t target_rank)
+		{
+			uint32_t r;
+			asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(target_rank));
+			return r;
+		}
+		__device__ __forceinline__ void st_peer_v4(uint32_t cluster_addr, uint4 v)
+		{
+			asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+		}
+		__device__ __forceinline__ void st_peer_f32(uint32_t cluster_addr, float v)
+		{
+			asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(cluster_addr), "f"(v) : "memory");
+		}
+		__device__ __forceinline__ void fence_proxy_async_all()
+		{ // generic-proxy writes (also those into the peer's shared memory) before async-proxy reads (tcgen05.mma operands)
+			asm volatile("fence.proxy.async;" ::: "memory");
+		}
+		__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar)
+		{ // local barrier, cluster-scope release: publishes this thread's writes into the peer's shared memory as well
+			asm volatile("{\n\t.reg .b64 state;\n\tmbarrier.arrive.release.cluster.shared::cta.b64 state, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
+		}
 		__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
 		{
 			uint32_t ok = 0;

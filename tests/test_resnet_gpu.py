@@ -19,13 +19,12 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 pytestmark = pytest.mark.gpu
 
 
-def _run(blocks, filters, q_head, n, seed):
+def _run(blocks, filters, q_head, n, seed, size=15, rules=None):
     import torch
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import nn_oracle
-    size = 15
-    eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD, size, size), max_boards=n, blocks=blocks, filters=filters, q_head=q_head)
+    eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD if rules is None else agb.GameRules(rules), size, size), max_boards=n, blocks=blocks, filters=filters, q_head=q_head)
     tensors = netblob.random_tensors(size, size, blocks, filters, q_head, seed=seed)
     blob = netblob.pack(tensors, size, size, blocks, filters, q_head)
     assert eng.weights_size() == blob.nbytes
@@ -68,3 +67,15 @@ def test_persistent_loop_more_boards_than_sms():
 def test_baseline_configs_20x128_and_10x64():
     _check(*_run(20, 128, True, n=64, seed=11))
     _check(*_run(10, 64, False, n=64, seed=12))
+
+
+@pytest.mark.parametrize("size,blocks,filters,q_head", [(20, 1, 64, False), (20, 3, 128, True), (19, 2, 64, True), (16, 2, 128, False), (12, 2, 64, True)])
+def test_large_boards_split_over_the_cta_pair(size, blocks, filters, q_head):
+    """Boards of more than 15 rows (caro 20x20, BASELINE configs[3]) run one board per CTA pair with a halo exchange through
+    distributed shared memory; 19 rows splits unevenly (10 + 9), 16..19 take the generic MMA schedule, 12 stays one board per CTA."""
+    _check(*_run(blocks, filters, q_head, n=37, seed=size + blocks, size=size, rules=3))
+
+
+def test_caro_20x20_baseline_network():
+    """BASELINE configs[3]: caro 20x20, 20 blocks x 128 channels; more boards than CTA pairs."""
+    _check(*_run(20, 128, True, n=150, seed=21, size=20, rules=3))
