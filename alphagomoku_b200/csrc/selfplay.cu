@@ -28,6 +28,8 @@ namespace agb
 	using namespace plogic;
 
 	constexpr int kMaxPath = 96;
+	// exact position compare of the node cache: one bit per cell and colour; 7 words cover the 400 cells of a 20x20 board
+	constexpr int kWordsPerColour = 7, kBitWords = 2 * kWordsPerColour;
 	constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 	// Score (search/Score.hpp:47-321): 3 bits proven value, 13 bits eval + 4000
@@ -114,7 +116,7 @@ namespace agb
 			uint16_t score;
 			uint16_t pad2;
 			uint64_t hash;
-			uint64_t bits[8];
+			uint64_t bits[kBitWords]; // cross words, then circle words
 			int32_t path_node[kMaxPath];
 			int32_t path_edge[kMaxPath];
 	};
@@ -126,7 +128,7 @@ namespace agb
 			int max_nodes = 0, max_edges = 0, table_size = 0;
 			// per game
 			int8_t *root_board = nullptr; // [games][cells]
-			uint64_t *root_bits = nullptr; // [games][8]
+			uint64_t *root_bits = nullptr; // [games][kBitWords]
 			uint64_t *root_hash = nullptr;
 			int8_t *root_stm = nullptr;
 			int32_t *root_node = nullptr;
@@ -136,7 +138,7 @@ namespace agb
 			uint16_t *moves = nullptr; // [games][cells] played moves (incl. opening)
 			int8_t *outcome = nullptr; // last finished outcome
 			NodeD *nodes = nullptr; // [games][max_nodes]
-			uint64_t *node_bits = nullptr; // [games][max_nodes][8]
+			uint64_t *node_bits = nullptr; // [games][max_nodes][kBitWords]
 			EdgeD *edges = nullptr; // [games][max_edges]
 			int32_t *table = nullptr; // [games][table_size] open addressing, -1 empty
 			int32_t *remap = nullptr; // [games][max_nodes] scratch for cleanup
@@ -224,8 +226,8 @@ namespace agb
 					return -1;
 				if (nodes[idx].hash == hash and nodes[idx].stm == stm)
 				{
-					const uint64_t *nb = p.s.node_bits + (static_cast<size_t>(g) * p.s.max_nodes + idx) * 8;
-					const bool same = (lane >= 8) or (nb[lane] == bits[lane]);
+					const uint64_t *nb = p.s.node_bits + (static_cast<size_t>(g) * p.s.max_nodes + idx) * kBitWords;
+					const bool same = (lane >= kBitWords) or (nb[lane] == bits[lane]);
 					if (__all_sync(kFullMask, same))
 						return idx;
 				}
@@ -325,8 +327,8 @@ namespace agb
 				TaskD &task = tasks[stored];
 				// SearchTask::set
 				__syncwarp();
-				if (lane < 8)
-					task.bits[lane] = p.s.root_bits[static_cast<size_t>(g) * 8 + lane];
+				if (lane < kBitWords)
+					task.bits[lane] = p.s.root_bits[static_cast<size_t>(g) * kBitWords + lane];
 				if (lane == 0)
 				{
 					task.path_len = 0;
@@ -419,7 +421,7 @@ namespace agb
 						}
 						else
 							atomicOr(p.status, OVF_PATH);
-						task.bits[colour * 4 + (cell >> 6)] |= 1ull << (cell & 63);
+						task.bits[colour * kWordsPerColour + (cell >> 6)] |= 1ull << (cell & 63);
 						nodes[node].vloss = N.vloss + 1;
 						edges[eidx].vloss_flag = (chosen.vloss_flag & 0x8000) | ((chosen.vloss_flag & 0x7FFF) + 1);
 					}
@@ -531,7 +533,7 @@ namespace agb
 				slot = __shfl_sync(kFullMask, slot, 0);
 				for (int i = lane; i < cells; i += 32)
 				{
-					const uint64_t cross = task.bits[i >> 6], circle = task.bits[4 + (i >> 6)];
+					const uint64_t cross = task.bits[i >> 6], circle = task.bits[kWordsPerColour + (i >> 6)];
 					p.s.task_boards[static_cast<size_t>(slot) * cells + i] = static_cast<int8_t>(((cross >> (i & 63)) & 1) | (((circle >> (i & 63)) & 1) << 1));
 				}
 			}
@@ -827,8 +829,8 @@ namespace agb
 						p.s.n_nodes[g] = n_nodes + 1;
 						p.s.n_edges[g] = n_edges + count;
 					}
-					if (lane < 8)
-						p.s.node_bits[(static_cast<size_t>(g) * p.s.max_nodes + n_nodes) * 8 + lane] = task.bits[lane];
+					if (lane < kBitWords)
+						p.s.node_bits[(static_cast<size_t>(g) * p.s.max_nodes + n_nodes) * kBitWords + lane] = task.bits[lane];
 					__syncwarp();
 				}
 				else
@@ -1004,12 +1006,12 @@ namespace agb
 			const int row = (chosen.move >> 2) & 127, col = (chosen.move >> 9) & 127, sign = chosen.move & 3;
 			const int cell = row * S + col;
 			int8_t *board = p.s.root_board + static_cast<size_t>(g) * cells;
-			uint64_t *bits = p.s.root_bits + static_cast<size_t>(g) * 8;
+			uint64_t *bits = p.s.root_bits + static_cast<size_t>(g) * kBitWords;
 			__syncwarp();
 			if (lane == 0)
 			{
 				board[cell] = static_cast<int8_t>(sign);
-				bits[(sign - 1) * 4 + (cell >> 6)] |= 1ull << (cell & 63);
+				bits[(sign - 1) * kWordsPerColour + (cell >> 6)] |= 1ull << (cell & 63);
 				p.s.root_hash[g] ^= p.s.zobrist[cell * 2 + sign - 1] ^ p.s.zobrist[cells * 2] ^ p.s.zobrist[cells * 2 + 1];
 				p.s.root_stm[g] = static_cast<int8_t>(3 - sign);
 				p.s.moves[static_cast<size_t>(g) * cells + p.s.n_moves[g]] = chosen.move;
@@ -1094,10 +1096,10 @@ namespace agb
 				for (int i = lane; i < cells; i += 32)
 					board[i] = src ? src[i] : 0;
 				__syncwarp();
-				if (lane < 8)
+				if (lane < kBitWords)
 				{
 					uint64_t w = 0;
-					const int colour = lane >> 2, word = lane & 3;
+					const int colour = lane / kWordsPerColour, word = lane % kWordsPerColour;
 					for (int i = word * 64; i < min(cells, word * 64 + 64); i++)
 						if (board[i] == colour + 1)
 						{
@@ -1107,7 +1109,7 @@ namespace agb
 					bits[lane] = w;
 				}
 				(void) nb;
-				for (int o = 4; o > 0; o >>= 1)
+				for (int o = 8; o > 0; o >>= 1) // lanes kBitWords..15 contribute zero
 					h ^= __shfl_xor_sync(kFullMask, h, o);
 				if (lane == 0)
 				{
@@ -1133,9 +1135,9 @@ namespace agb
 			// prepare_search -> Tree::setBoard -> NodeCache::cleanup: keep every node whose position can still occur
 			const int n_nodes = p.s.n_nodes[g];
 			int32_t *remap = p.s.remap + static_cast<size_t>(g) * p.s.max_nodes;
-			uint64_t *node_bits = p.s.node_bits + static_cast<size_t>(g) * p.s.max_nodes * 8;
-			uint64_t rb[8];
-			for (int k = 0; k < 8; k++)
+			uint64_t *node_bits = p.s.node_bits + static_cast<size_t>(g) * p.s.max_nodes * kBitWords;
+			uint64_t rb[kBitWords];
+			for (int k = 0; k < kBitWords; k++)
 				rb[k] = bits[k];
 			int kept = 0;
 			for (int i0 = 0; i0 < n_nodes; i0 += 32)
@@ -1145,8 +1147,8 @@ namespace agb
 				if (i < n_nodes)
 				{
 					keep = true;
-					for (int k = 0; k < 8; k++)
-						keep = keep and ((node_bits[static_cast<size_t>(i) * 8 + k] & rb[k]) == rb[k]);
+					for (int k = 0; k < kBitWords; k++)
+						keep = keep and ((node_bits[static_cast<size_t>(i) * kBitWords + k] & rb[k]) == rb[k]);
 				}
 				const unsigned km = __ballot_sync(kFullMask, keep);
 				if (i < n_nodes)
@@ -1162,7 +1164,7 @@ namespace agb
 				if (dst < 0)
 					continue;
 				NodeD node = nodes[i];
-				uint64_t nbits = (lane < 8) ? node_bits[static_cast<size_t>(i) * 8 + lane] : 0;
+				uint64_t nbits = (lane < kBitWords) ? node_bits[static_cast<size_t>(i) * kBitWords + lane] : 0;
 				const int old_begin = node.edge_begin;
 				for (int e0 = 0; e0 < node.n_edges; e0 += 32)
 				{
@@ -1180,8 +1182,8 @@ namespace agb
 				__syncwarp();
 				if (lane == 0)
 					nodes[dst] = node;
-				if (lane < 8)
-					node_bits[static_cast<size_t>(dst) * 8 + lane] = nbits;
+				if (lane < kBitWords)
+					node_bits[static_cast<size_t>(dst) * kBitWords + lane] = nbits;
 				__syncwarp();
 			}
 			int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
@@ -1211,19 +1213,19 @@ namespace agb
 			if (g >= p.s.games)
 				return;
 			const int cells = p.s.cells;
-			uint64_t bits[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			uint64_t bits[kBitWords] = { };
 			uint64_t h = 0;
 			for (int i = 0; i < cells; i++)
 			{
 				const int v = p.s.root_board[static_cast<size_t>(g) * cells + i];
 				if (v == CROSS or v == CIRCLE)
 				{
-					bits[(v - 1) * 4 + (i >> 6)] |= 1ull << (i & 63);
+					bits[(v - 1) * kWordsPerColour + (i >> 6)] |= 1ull << (i & 63);
 					h ^= p.s.zobrist[i * 2 + v - 1];
 				}
 			}
-			for (int k = 0; k < 8; k++)
-				p.s.root_bits[static_cast<size_t>(g) * 8 + k] = bits[k];
+			for (int k = 0; k < kBitWords; k++)
+				p.s.root_bits[static_cast<size_t>(g) * kBitWords + k] = bits[k];
 			p.s.root_hash[g] = h ^ p.s.zobrist[cells * 2 + p.s.root_stm[g] - 1];
 			p.s.root_node[g] = -1;
 			p.s.n_nodes[g] = 0;
@@ -1298,7 +1300,7 @@ namespace agb
 			ok = ok and cudaMalloc(reinterpret_cast<void**>(ptr), count * sizeof(**ptr)) == cudaSuccess;
 		};
 		alloc(&s->root_board, G * cells);
-		alloc(&s->root_bits, G * 8);
+		alloc(&s->root_bits, G * kBitWords);
 		alloc(&s->root_hash, G);
 		alloc(&s->root_stm, G);
 		alloc(&s->root_node, G);
@@ -1309,7 +1311,7 @@ namespace agb
 		alloc(&s->moves, G * cells);
 		alloc(&s->outcome, G);
 		alloc(&s->nodes, G * s->max_nodes);
-		alloc(&s->node_bits, G * s->max_nodes * 8);
+		alloc(&s->node_bits, G * s->max_nodes * kBitWords);
 		alloc(&s->edges, G * s->max_edges);
 		alloc(&s->table, G * s->table_size);
 		alloc(&s->remap, G * s->max_nodes);

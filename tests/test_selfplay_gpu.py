@@ -36,10 +36,20 @@ def _openings(rng, size, n):
     (0, False, "parent", 4, 60, 100), (1, True, "q_head", 8, 80, 100), (4, False, "parent", 3, 55, 30), (2, False, "parent", 4, 60, 1),
     (2, True, "q_head", 8, 80, 100)])
 def test_lockstep_engine_matches_reference_search(ref, rules, q_head, init_to, batch, sims, solver):
+    _run_case(ref, rules, q_head, init_to, batch, sims, solver)
+
+
+@pytest.mark.parametrize("rules,q_head,init_to,batch,sims,solver", [(3, False, "parent", 4, 60, 0), (3, True, "q_head", 6, 70, 50)])
+def test_lockstep_engine_caro_20x20(ref, rules, q_head, init_to, batch, sims, solver):
+    """BASELINE configs[3]: caro on a 20x20 board (K4 runs one board per CTA pair, 7-word bitboards in the tree)."""
+    _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=20)
+
+
+def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15):
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import refapi
-    size, games = 15, 6
+    games = 6
     blocks, filters = 2, 64
     # short games, so that game ends, restarts and finished-game records are exercised too (longer with the solver, so that real threats appear)
     draw_after = 14 if solver == 0 else 28
