@@ -12,6 +12,7 @@
 #include "solver_search.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
