@@ -104,8 +104,9 @@ namespace agb
 			int slot_base = 0, cudaStream_t stream = nullptr);
 	int launch_add_undo(AgbEngine *e, const uint16_t *moves_dev, int n, bool undo);
 	int launch_encode(AgbEngine *e, int n, uint32_t *features_dev);
-	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse);
-	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n);
+	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse,
+			cudaStream_t stream = nullptr);
+	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n, cudaStream_t stream = nullptr);
 	int launch_outcomes(AgbEngine *e, const int8_t *boards_dev, const uint16_t *moves_dev, int n, int8_t *out_dev);
 	// resnet.cu
 	int net_create(AgbEngine *e);

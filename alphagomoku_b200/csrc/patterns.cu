@@ -449,18 +449,22 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
 	}
-	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n)
+	int launch_augment(AgbEngine *e, const uint32_t *src_dev, uint32_t *dst_dev, const int8_t *sym_dev, int n, cudaStream_t stream)
 	{
+		if (stream == nullptr)
+			stream = e->stream;
 		const long long total = static_cast<long long>(n) * e->cells;
-		augment_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, e->stream>>>(src_dev, dst_dev, sym_dev, n, e->cfg.rows);
+		augment_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src_dev, dst_dev, sym_dev, n, e->cfg.rows);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;
 	}
-	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse)
+	int launch_symmetry_f32(AgbEngine *e, const float *src_dev, float *dst_dev, const int8_t *sym_dev, int n, int channels, bool inverse, cudaStream_t stream)
 	{
+		if (stream == nullptr)
+			stream = e->stream;
 		const long long total = static_cast<long long>(n) * e->cells;
-		symmetry_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, e->stream>>>(src_dev, dst_dev, sym_dev, n, e->cfg.rows, channels, inverse ? 1 : 0);
+		symmetry_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src_dev, dst_dev, sym_dev, n, e->cfg.rows, channels, inverse ? 1 : 0);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

@@ -159,6 +159,11 @@ namespace agb
 			cudaEvent_t ready[2] = { nullptr, nullptr }, evaluated[2] = { nullptr, nullptr }, joined = nullptr;
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
+			// SelfplayConfig::use_symmetries: every evaluation goes through a random board symmetry (NNEvaluator.cpp:134-146, 244-286)
+			int8_t *task_sym = nullptr; // [games*batch] symmetry of the slot's evaluation
+			uint32_t *sym_counter = nullptr; // [games] evaluations drawn so far (the random stream is keyed by the global game id)
+			uint32_t *features_aug = nullptr; // [games*batch][cells] augmented feature words
+			float *policy_raw = nullptr, *q_raw = nullptr; // network outputs before the inverse symmetry
 			uint64_t *zobrist = nullptr; // [cells][2] + [2]
 			unsigned long long *stats = nullptr; // device AgbStats mirror (16 words)
 			// openings pool
@@ -198,6 +203,8 @@ namespace agb
 				// pipeline group served by this launch: games [game_begin, game_begin + game_count), evaluation slots from slot_base on
 				int game_begin, game_count, slot_base;
 				int32_t *eval_count; // this group's slot counter
+				int use_symmetries, first_game_id;
+				unsigned long long sym_seed;
 				Tables tables;
 				BoardStore store;
 				uint32_t *status;
@@ -526,6 +533,14 @@ namespace agb
 					task.nn_slot = slot;
 					p.s.task_stm[slot] = task.stm;
 					p.s.slot_is_root[slot] = (task.path_len == 0) ? 1 : 0;
+					if (p.use_symmetries)
+					{ // randInt(8) of the reference's evaluator, as a counter-based stream per (seed, global game id)
+						unsigned long long z = p.sym_seed ^ (static_cast<unsigned long long>(p.first_game_id + g) << 32) ^ p.s.sym_counter[g]++;
+						z += 0x9E3779B97F4A7C15ull;
+						z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+						z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+						p.s.task_sym[slot] = static_cast<int8_t>((z ^ (z >> 31)) & 7ull);
+					}
 					if (p.solver_mode != 0)
 						p.s.solver.game_slots[static_cast<size_t>(g) * p.s.batch + n_slots] = slot; // the solver walks them in task order
 				}
@@ -1262,6 +1277,9 @@ namespace agb
 			p.game_count = e->selfplay->games;
 			p.slot_base = 0;
 			p.eval_count = e->selfplay->eval_count;
+			p.use_symmetries = e->cfg.use_symmetries != 0;
+			p.first_game_id = e->cfg.first_game_id;
+			p.sym_seed = e->cfg.seed * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull;
 			p.tables = e->tables;
 			p.store = e->store;
 			p.status = e->d_status;
@@ -1333,6 +1351,15 @@ namespace agb
 		alloc(&s->policy, T * cells);
 		alloc(&s->value, T * 3);
 		alloc(&s->q, T * cells * 3);
+		if (c.use_symmetries)
+		{
+			alloc(&s->task_sym, T);
+			alloc(&s->sym_counter, G);
+			alloc(&s->features_aug, T * cells);
+			alloc(&s->policy_raw, T * cells);
+			if (c.q_head)
+				alloc(&s->q_raw, T * cells * 3);
+		}
 		alloc(&s->zobrist, cells * 2 + 2);
 		alloc(&s->stats, 16);
 		alloc(&s->opening_cursor, 1);
@@ -1393,7 +1420,7 @@ namespace agb
 			return;
 		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
-				s->value, s->q, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
+				s->value, s->q, s->task_sym, s->sym_counter, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
 				s->sample_root, s->sample_draw, s->sample_score, s->slot_is_root, s->nn_list, s->nn_count, s->solver_out.moves, s->solver_out.scores,
 				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->solver_out.nodes, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
@@ -1451,6 +1478,11 @@ extern "C"
 			s->n_openings = 0;
 		}
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
+		if (s->sym_counter != nullptr)
+		{
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->sym_counter, 0, G * sizeof(uint32_t), e->stream));
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->task_sym, 0, G * s->batch, e->stream));
+		}
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
 		if (e->cfg.solver_max_positions > 0)
 		{
@@ -1566,12 +1598,28 @@ extern "C"
 					AGB_CUDA_CHECK(e, cudaEventRecord(s->ready[k], gs));
 					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(ns, s->ready[k], 0));
 				}
+				const bool sym = p.use_symmetries != 0;
+				const size_t off = static_cast<size_t>(p.slot_base);
+				if (sym)
+				{ // NNEvaluator::pack_to_network: features.augment(symmetry), over all slots of the group
+					rc = launch_augment(e, s->features + off * s->cells, s->features_aug + off * s->cells, s->task_sym + off, max_tasks, ns);
+					if (rc != AGB_OK)
+						return rc;
+				}
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[2], ns));
-				rc = net_forward_dev_gather(e, s->features, p.solver_mode != 0 ? nn_count : p.eval_count, p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr,
-						max_tasks, s->policy, s->value, s->q, p.slot_base, ns);
+				rc = net_forward_dev_gather(e, sym ? s->features_aug : s->features, p.solver_mode != 0 ? nn_count : p.eval_count,
+						p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr, max_tasks, sym ? s->policy_raw : s->policy, s->value, sym ? s->q_raw : s->q, p.slot_base, ns);
 				if (rc != AGB_OK)
 					return rc;
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[3], ns));
+				if (sym)
+				{ // unpack_from_network: the inverse symmetry on the policy and the action values
+					rc = launch_symmetry_f32(e, s->policy_raw + off * s->cells, s->policy + off * s->cells, s->task_sym + off, max_tasks, 1, true, ns);
+					if (rc == AGB_OK and e->cfg.q_head)
+						rc = launch_symmetry_f32(e, s->q_raw + off * s->cells * 3, s->q + off * s->cells * 3, s->task_sym + off, max_tasks, 3, true, ns);
+					if (rc != AGB_OK)
+						return rc;
+				}
 				if (groups > 1)
 				{
 					AGB_CUDA_CHECK(e, cudaEventRecord(s->evaluated[k], ns));

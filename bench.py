@@ -37,7 +37,7 @@ FLOP_PER_POSITION = 2 * 1383.70e6  # BASELINE.md section 3 (algorithmic, ResNet 
 
 def workload_config(n_gpus, impl="ours", solver=0):
     return {"workload": "configs[1]: standard 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", "rules": "STANDARD",
-            "board": "15x15", "network": "ResnetPV 20x128", "games_per_gpu": GAMES, "max_batch_size": BATCH, "max_simulations": SIMS,
+            "board": "15x15", "network": "ResnetPV 20x128", "games_per_gpu": GAMES, "max_batch_size": BATCH, "max_simulations": SIMS, "use_symmetries": True,
             "solver": ("on (AlphaBetaSearch, max_positions 100, 4 Mi-entry table per game)" if impl == "reference" else
                        f"on (K5 alpha-beta, max_positions {solver}, {SOLVER_TABLE_ENTRIES}-entry table per game)" if solver > 0 else "off"),
             "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
@@ -197,7 +197,7 @@ def main():
     eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * BATCH, device=local_rank, blocks=BLOCKS, filters=FILTERS,
                      q_head=False, games=games, max_batch_size=BATCH, max_simulations=SIMS, init_to="parent", max_nodes_per_game=1536,
                      max_edges_per_game=1536 * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
-                     solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups)
+                     solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups, use_symmetries=True)
     # C1: rank 0 owns the weights and broadcasts them over NCCL (NetworkLoader::get per thread in the reference)
     blob = netblob.pack(netblob.random_tensors(SIZE, SIZE, BLOCKS, FILTERS, False), SIZE, SIZE, BLOCKS, FILTERS, False) if rank == 0 else None
     eng.load_weights(sharding.broadcast_weights(blob))

@@ -117,3 +117,50 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15):
     for r in refs:
         r.close()
     eng.close()
+
+
+def test_random_evaluation_symmetries():
+    """SelfplayConfig::use_symmetries: every leaf is evaluated through a random board symmetry (NNEvaluator.cpp:134-146, 244-286). The
+    root's priors after the first step must equal the NNEvaluator drop-in (agb_evaluate) for one of the 8 symmetries, all 8 must occur
+    over the games, and the stream is keyed by (seed, global game id): a shard of the games reproduces the same trees."""
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob
+    size, games, blocks, filters = 15, 64, 2, 64
+    blob = netblob.pack(netblob.random_tensors(size, size, blocks, filters, True, seed=9), size, size, blocks, filters, True)
+    rng = np.random.default_rng(123)
+    boards, stm = _openings(rng, size, games)
+
+    def make(n_games, first):
+        eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD, size, size), max_boards=n_games * 4, blocks=blocks, filters=filters, q_head=True,
+                         games=n_games, max_batch_size=4, max_simulations=60, use_symmetries=True, seed=77, first_game_id=first)
+        eng.load_weights(blob)
+        eng.selfplay_reset(boards[first:first + n_games], stm[first:first + n_games])
+        return eng
+
+    eng = make(games, 0)
+    eng.step(1)
+    used = set()
+    for g in range(games):
+        _, priors, _, _, visits = eng.get_root(g)
+        assert visits == 1
+        empty = boards[g] == 0
+        match = None
+        for k in range(8):
+            policy, _, _ = eng.evaluate(boards[g:g + 1], stm[g:g + 1], symmetry=[k])
+            expect = np.where(empty, policy[0], 0.0)
+            expect = expect / expect.sum()
+            if np.abs(expect - priors).max() < 2e-6:
+                match = k
+                break
+        assert match is not None, g
+        used.add(match)
+    assert len(used) == 8
+    eng.step(40)
+    shard = make(16, 32)
+    shard.step(41)
+    for g in range(16):
+        a, b = eng.get_root(32 + g), shard.get_root(g)
+        assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all() and a[4] == b[4], g
+    assert eng.stats()["overflow_flags"] == 0
+    eng.close()
+    shard.close()
