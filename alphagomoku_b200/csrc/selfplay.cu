@@ -1222,8 +1222,8 @@ namespace agb
 			}
 		}
 
-		__global__ void reset_games_kernel(const __grid_constant__ Params p)
-		{ // Zobrist hash + bitboards of every game's root position
+		__global__ void reset_games_kernel(const __grid_constant__ Params p, int keep_history)
+		{ // Zobrist hash + bitboards of every game's root position; keep_history: resumed games keep their move lists and samples
 			const int g = blockIdx.x * blockDim.x + threadIdx.x;
 			if (g >= p.s.games)
 				return;
@@ -1246,10 +1246,13 @@ namespace agb
 			p.s.n_nodes[g] = 0;
 			p.s.n_edges[g] = 0;
 			p.s.n_stored[g] = 0;
-			p.s.n_moves[g] = opening_moves(p.s.root_board + static_cast<size_t>(g) * cells, cells, p.s.S, p.s.moves + static_cast<size_t>(g) * cells);
 			p.s.outcome[g] = 0;
-			p.s.rec_len[g] = 4;
-			p.s.rec_samples[g] = 0;
+			if (not keep_history)
+			{
+				p.s.n_moves[g] = opening_moves(p.s.root_board + static_cast<size_t>(g) * cells, cells, p.s.S, p.s.moves + static_cast<size_t>(g) * cells);
+				p.s.rec_len[g] = 4;
+				p.s.rec_samples[g] = 0;
+			}
 			if (p.solver_mode != 0)
 				p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64; // prepare_search -> Search::setBoard -> increaseGeneration
 		}
@@ -1491,7 +1494,114 @@ extern "C"
 				return rc;
 		}
 		const Params p = make_params(e);
-		reset_games_kernel<<<static_cast<unsigned>((G + 127) / 128), 128, 0, e->stream>>>(p);
+		reset_games_kernel<<<static_cast<unsigned>((G + 127) / 128), 128, 0, e->stream>>>(p, 0);
+		e->launches++;
+		AGB_CUDA_CHECK(e, cudaGetLastError());
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		return AGB_OK;
+	}
+
+	// ---- games in flight: GeneratorManager::saveState / loadState (GeneratorManager.cpp:240-290), GameGenerator::save / load
+	// (GameGenerator.cpp:122-141). Like the reference, what survives is each game's position, move list and the samples recorded so
+	// far; the search trees are rebuilt (prepare_search). Blob: AgbSavedHeader, then per game: board[cells] int8, sign to move int8,
+	// n_moves int32, moves[n_moves] uint16, samples int32, record bytes int32, record[bytes].
+	struct AgbSavedHeader
+	{
+			uint32_t magic, version;
+			int32_t games, rows, cols, rules;
+	};
+	int agb_save_games(AgbEngine *e, void *blob_host, size_t capacity, size_t *used)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games");
+		if (used == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		const size_t G = s->games, cells = s->cells;
+		std::vector<int8_t> boards(G * cells), stm(G);
+		std::vector<int32_t> n_moves(G), rec_len(G), rec_samples(G);
+		std::vector<uint16_t> moves(G * cells);
+		std::vector<uint8_t> rec(G * s->rec_cap);
+		AGB_CUDA_CHECK(e, cudaMemcpy(boards.data(), s->root_board, boards.size(), cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(stm.data(), s->root_stm, G, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(n_moves.data(), s->n_moves, G * 4, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(moves.data(), s->moves, moves.size() * 2, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(rec_len.data(), s->rec_len, G * 4, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(rec_samples.data(), s->rec_samples, G * 4, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(rec.data(), s->rec_buf, rec.size(), cudaMemcpyDeviceToHost));
+		std::vector<uint8_t> out;
+		const auto put = [&](const void *ptr, size_t bytes)
+		{
+			const uint8_t *b = static_cast<const uint8_t*>(ptr);
+			out.insert(out.end(), b, b + bytes);
+		};
+		const AgbSavedHeader header { 0x53424741u /* "AGBS" */, 1u, s->games, e->cfg.rows, e->cfg.cols, e->cfg.rules };
+		put(&header, sizeof(header));
+		for (size_t g = 0; g < G; g++)
+		{
+			put(boards.data() + g * cells, cells);
+			put(&stm[g], 1);
+			put(&n_moves[g], 4);
+			put(moves.data() + g * cells, static_cast<size_t>(n_moves[g]) * 2);
+			put(&rec_samples[g], 4);
+			put(&rec_len[g], 4);
+			put(rec.data() + g * s->rec_cap, rec_len[g]);
+		}
+		*used = out.size();
+		if (blob_host == nullptr or capacity < out.size())
+			return e->fail(AGB_ENOMEM, "state buffer too small: need " + std::to_string(out.size()) + " bytes");
+		std::memcpy(blob_host, out.data(), out.size());
+		return AGB_OK;
+	}
+	int agb_load_games(AgbEngine *e, const void *blob_host, size_t bytes)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games");
+		const uint8_t *cur = static_cast<const uint8_t*>(blob_host), *end = cur + bytes;
+		AgbSavedHeader header { };
+		if (blob_host == nullptr or bytes < sizeof(header))
+			return e->fail(AGB_EINVAL, "saved state is truncated");
+		std::memcpy(&header, cur, sizeof(header));
+		cur += sizeof(header);
+		if (header.magic != 0x53424741u or header.version != 1u)
+			return e->fail(AGB_EINVAL, "not a saved-games blob of this library");
+		if (header.games != s->games or header.rows != e->cfg.rows or header.cols != e->cfg.cols or header.rules != e->cfg.rules)
+			return e->fail(AGB_EINVAL, "saved state was written for another configuration (games, board or rules differ)");
+		const size_t G = s->games, cells = s->cells;
+		std::vector<int8_t> boards(G * cells), stm(G);
+		std::vector<int32_t> n_moves(G), rec_len(G), rec_samples(G);
+		std::vector<uint16_t> moves(G * cells, 0);
+		std::vector<uint8_t> rec(G * s->rec_cap, 0);
+		const auto get = [&](void *dst, size_t n) -> bool
+		{
+			if (static_cast<size_t>(end - cur) < n)
+				return false;
+			std::memcpy(dst, cur, n);
+			cur += n;
+			return true;
+		};
+		for (size_t g = 0; g < G; g++)
+		{
+			bool ok = get(boards.data() + g * cells, cells) and get(&stm[g], 1) and get(&n_moves[g], 4);
+			ok = ok and n_moves[g] >= 0 and n_moves[g] <= static_cast<int32_t>(cells) and get(moves.data() + g * cells, static_cast<size_t>(n_moves[g]) * 2);
+			ok = ok and get(&rec_samples[g], 4) and get(&rec_len[g], 4) and rec_len[g] >= 4 and rec_len[g] <= s->rec_cap and get(rec.data() + g * s->rec_cap, rec_len[g]);
+			if (not ok)
+				return e->fail(AGB_EINVAL, "saved state is truncated or corrupt at game " + std::to_string(g));
+		}
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->root_board, boards.data(), boards.size(), cudaMemcpyHostToDevice));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->root_stm, stm.data(), G, cudaMemcpyHostToDevice));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->n_moves, n_moves.data(), G * 4, cudaMemcpyHostToDevice));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->moves, moves.data(), moves.size() * 2, cudaMemcpyHostToDevice));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->rec_len, rec_len.data(), G * 4, cudaMemcpyHostToDevice));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->rec_samples, rec_samples.data(), G * 4, cudaMemcpyHostToDevice));
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->rec_buf, rec.data(), rec.size(), cudaMemcpyHostToDevice));
+		// prepare_search for every game: empty trees, fresh hashes (the solver tables stay, like the reference's)
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
+		const Params p = make_params(e);
+		reset_games_kernel<<<static_cast<unsigned>((G + 127) / 128), 128, 0, e->stream>>>(p, 1);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));

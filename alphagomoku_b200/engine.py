@@ -222,6 +222,18 @@ class Engine:
                                         _ptr(flags)))
         return scores, n_actions, moves, action_scores, flags
 
+    def save_games(self):
+        """GeneratorManager::saveState: positions, move lists and samples of the games in flight, as bytes."""
+        used = ctypes.c_size_t()
+        self._lib.agb_save_games(self._h, None, 0, ctypes.byref(used))
+        buf = np.zeros(used.value, np.uint8)
+        self._check(self._lib.agb_save_games(self._h, _ptr(buf), buf.size, ctypes.byref(used)))
+        return buf.tobytes()
+
+    def load_games(self, blob):
+        buf = np.frombuffer(blob, np.uint8)
+        self._check(self._lib.agb_load_games(self._h, _ptr(buf), buf.size))
+
     def set_solver_keys(self, keys):
         """Zobrist words of the solver's transposition tables: uint64 [2 * cells, 2] (FastZobristHashing::m_keys)."""
         k = np.ascontiguousarray(keys, np.uint64).reshape(-1)

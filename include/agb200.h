@@ -166,6 +166,12 @@ int agb_selfplay_reset(AgbEngine *engine, const int8_t *boards_host, const int8_
  * SearchTask::getEdges / getActionScores); flags[n]: bit 0 must-defend, bits 8.. positions visited. */
 int agb_solve(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, int max_positions, uint16_t *scores_host,
 		int32_t *n_actions_host, uint16_t *moves_host, uint16_t *action_scores_host, int32_t *flags_host);
+/* games in flight (GeneratorManager::saveState / loadState, src/selfplay/GeneratorManager.cpp:240-290): every game's position, move
+ * list and the samples recorded so far. *used receives the size; AGB_ENOMEM when capacity is too small (call once with NULL to size the
+ * buffer). Loading needs an engine with the same games / board / rules; the search trees start empty, as after the reference's
+ * GameGenerator::load -> prepare_search. */
+int agb_save_games(AgbEngine *engine, void *blob_host, size_t capacity, size_t *used);
+int agb_load_games(AgbEngine *engine, const void *blob_host, size_t bytes);
 /* replace the Zobrist words of the solver's transposition tables: keys[2 * rows * cols][2] = (low, high) 64-bit word of
  * (cell, CROSS) then (cell, CIRCLE), i.e. FastZobristHashing::m_keys (include/alphagomoku/search/ZobristHashing.hpp:111-127).
  * The words only decide which bucket a position maps to; parity tests pass the reference's own so that bucket replacement

@@ -164,3 +164,44 @@ def test_random_evaluation_symmetries():
     assert eng.stats()["overflow_flags"] == 0
     eng.close()
     shard.close()
+
+
+def test_save_and_resume_games_in_flight():
+    """GeneratorManager::saveState / loadState: positions, move lists and recorded samples survive; trees are rebuilt. A resumed engine
+    writes the same blob back, continues, and its finished records start with the samples recorded before the save."""
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob, dataset
+    size, games, blocks, filters = 15, 12, 2, 64
+    blob = netblob.pack(netblob.random_tensors(size, size, blocks, filters, False, seed=4), size, size, blocks, filters, False)
+    rng = np.random.default_rng(5)
+    boards, stm = _openings(rng, size, games)
+
+    def make():
+        eng = agb.Engine(agb.GameConfig(agb.GameRules.FREESTYLE, size, size, 20), max_boards=games * 4, blocks=blocks, filters=filters, games=games,
+                         max_batch_size=4, max_simulations=50, solver_max_positions=20)
+        eng.load_weights(blob)
+        return eng
+
+    a = make()
+    a.selfplay_reset(boards, stm)
+    a.step(70)
+    a.pop_finished()
+    saved = a.save_games()
+    positions = [a.get_board(g) for g in range(games)]
+    b = make()
+    b.selfplay_reset(boards, stm)
+    b.load_games(saved)
+    assert b.save_games() == saved
+    for g in range(games):
+        board, to_move, _ = b.get_board(g)
+        assert (board == positions[g][0]).all() and to_move == positions[g][1]
+        assert b.get_root(g)[4] == 0  # empty tree
+    with pytest.raises(agb.AgbError):
+        b.load_games(saved[:len(saved) // 2])
+    b.step(250)
+    records, n = b.pop_finished()
+    assert n >= 1 and b.stats()["overflow_flags"] == 0
+    for rec in dataset.split_records(records, n):
+        assert len(dataset.parse_record(rec)["moves"]) >= 1
+    a.close()
+    b.close()
