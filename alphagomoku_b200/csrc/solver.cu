@@ -44,8 +44,10 @@ namespace agb
 				const int slot = st.game_slots[static_cast<size_t>(g) * st.batch + k];
 				const size_t cbase = static_cast<size_t>(slot) * kCellPitch;
 				int stones = 0;
-				for (int i = 0; i < cells; i++)
+				for (int i = threadIdx.x & 31; i < cells; i += 32) // the lanes count interleaved cells
 					stones += (store.board[cbase + i] != NONE);
+				for (int o = 16; o > 0; o >>= 1)
+					stones += __shfl_xor_sync(0xFFFFFFFFu, stones, o);
 				solver::DynState d;
 				d.board = store.board + cbase;
 				d.lines = store.lines + static_cast<size_t>(slot) * kLinePitch;
@@ -60,11 +62,12 @@ namespace agb
 				const solver::SearchOutput res = solver::solve_position(d, tt, mem, max_nodes, 100);
 				uint16_t *om = out.moves + static_cast<size_t>(slot) * out.pitch;
 				uint16_t *os = out.scores + static_cast<size_t>(slot) * out.pitch;
-				for (int i = 0; i < res.n_actions; i++)
+				for (int i = threadIdx.x & 31; i < res.n_actions; i += 32)
 				{
 					om[i] = mem.stack_moves[i];
 					os[i] = mem.stack_scores[i];
 				}
+				__syncwarp();
 				out.n_actions[slot] = res.n_actions;
 				out.score[slot] = res.score;
 				out.must_defend[slot] = res.must_defend ? 1 : 0;

@@ -511,6 +511,37 @@ namespace agb
 				// 7x7 stencils around stones (MoveGenerator.cpp:1011-1125); `sign` 0: around every stone (box-and-star), else star around `sign`
 				AGB_HD_NOINLINE void stencil_mask(uint32_t *mask, int sign) const
 				{
+#ifdef __CUDA_ARCH__
+					// lockstep warp (solver_search.cuh): lane r builds row r of the mask from the stones of rows r-3..r+3, then every lane
+					// collects all rows
+					const unsigned long long box = 0x493E3E773E3E49ull, star = 0x492A1C771C2A49ull; // the 7 stencil rows, one byte each
+					const int lane = threadIdx.x & 31;
+					uint32_t mine = 0;
+					if (lane < v.S)
+					{
+						uint32_t legal = 0;
+						for (int c = 0; c < v.S; c++)
+							legal |= static_cast<uint32_t>(v.board[lane * v.S + c] == NONE) << c;
+						for (int i = 0; i < 7; i++)
+						{
+							const int sr = lane + 3 - i; // a stone in row sr puts stencil row i on this row
+							if (sr < 0 or sr >= v.S)
+								continue;
+							const uint32_t m = static_cast<uint32_t>(((sign == 0) ? box : star) >> (8 * i)) << 25 & 0xFE000000u;
+							for (int c = 0; c < v.S; c++)
+							{
+								const int s = v.board[sr * v.S + c];
+								if ((sign == 0) ? (s != NONE) : (s == sign))
+									mine |= m >> (28 - c);
+							}
+						}
+						if (sign == 0 and v.stones == 0 and lane == v.S / 2)
+							mine |= 1u << (v.S / 2);
+						mine &= legal;
+					}
+					for (int r = 0; r < v.S; r++)
+						mask[r] = __shfl_sync(0xFFFFFFFFu, mine, r);
+#else
 					const uint32_t box[7] = { 73u, 62u, 62u, 119u, 62u, 62u, 73u };
 					const uint32_t star[7] = { 73u, 42u, 28u, 119u, 28u, 42u, 73u };
 					uint32_t rows[kMaxSize + 7];
@@ -533,6 +564,7 @@ namespace agb
 					legal_mask(legal);
 					for (int r = 0; r < v.S; r++)
 						mask[r] = rows[3 + r] & legal[r];
+#endif
 				}
 
 				// ---- stages -----------------------------------------------------------------------------------------------------
