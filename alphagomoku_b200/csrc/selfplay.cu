@@ -121,7 +121,7 @@ namespace agb
 			int32_t path_edge[kMaxPath];
 	};
 
-	constexpr int kMaxGroups = 2;
+	constexpr int kMaxGroups = 4;
 	struct SelfplayState
 	{
 			int games = 0, batch = 0, cells = 0, S = 0;
@@ -154,9 +154,9 @@ namespace agb
 			// pipeline groups: the games are split into `groups` independent halves that advance on their own streams, so that the
 			// solver / tree kernels of one half overlap the network kernel of the other (the network launches share one stream)
 			int groups = 1;
-			cudaStream_t group_stream[2] = { nullptr, nullptr };
+			cudaStream_t group_stream[kMaxGroups] = { };
 			cudaStream_t nn_stream = nullptr;
-			cudaEvent_t ready[2] = { nullptr, nullptr }, evaluated[2] = { nullptr, nullptr }, joined = nullptr;
+			cudaEvent_t ready[kMaxGroups] = { }, evaluated[kMaxGroups] = { }, joined = nullptr;
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
 			// SelfplayConfig::use_symmetries: every evaluation goes through a random board symmetry (NNEvaluator.cpp:134-146, 244-286)
@@ -1386,7 +1386,7 @@ namespace agb
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
 		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : 1;
 		if (s->groups > kMaxGroups or s->groups > c.games)
-			return e->fail(AGB_EINVAL, "pipeline_groups must be 1 or 2 and not exceed the number of games");
+			return e->fail(AGB_EINVAL, "pipeline_groups must be 1..4 and not exceed the number of games");
 		if (s->groups > 1)
 		{
 			for (int k = 0; k < s->groups; k++)

@@ -20,9 +20,9 @@ namespace agb
 {
 	namespace
 	{
-		constexpr int kSolverWarpsPerBlock = 4;
+		constexpr int kSolverWarpsPerBlock = 1; // one game per block: the block scheduler can then fit solver warps next to a resident K4 CTA
 
-		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32, 7) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int game_begin, int games, int S, int rules,
+		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32, 28) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int game_begin, int games, int S, int rules,
 				int draw_after, int max_nodes, SolverOutputs out, const uint8_t *__restrict__ slot_is_root, int *__restrict__ nn_list, int *__restrict__ nn_count,
 				uint32_t *__restrict__ status)
 		{

@@ -83,8 +83,8 @@ typedef struct AgbConfig
 	int32_t first_game_id; /* global id of this engine's game 0 (rank * games when sharded) */
 	int32_t solver_table_entries; /* entries of each game's solver transposition table (power of two; 0 = 65536; the reference uses 4 Mi,
 	                                 AlphaBetaSearch.cpp:55) */
-	int32_t pipeline_groups; /* 1: all games advance together; 2: two halves on their own streams, so that one half's solver and tree
-	                            kernels can overlap the other half's network kernel; 0 = 1. Per-game results do not depend on it */
+	int32_t pipeline_groups; /* 1: all games advance together; 2..4: that many groups of games on their own streams, so that one group's solver and tree
+	                            kernels can overlap another group's network kernel; 0 = 1. Per-game results do not depend on it */
 	int32_t reserved[5];
 } AgbConfig;
 
