@@ -20,9 +20,12 @@ namespace agb
 {
 	namespace
 	{
-		constexpr int kSolverWarpsPerBlock = 1; // one game per block: the block scheduler can then fit solver warps next to a resident K4 CTA
 
-		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32, 28) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int game_begin, int games, int S, int rules,
+		// Two builds of the same kernel: <1, 28> keeps 72 registers per thread and holds 28 games per SM (enough for 4144 games in one
+		// wave); <2, 28> is capped at 32 registers and holds 56, for launches with more games than that (the kernel is latency-bound, so
+		// resident warps matter more than spills: 16384 games x 2 leaves take 26 ms where 4096 x 8 take 43).
+		template<int kSolverWarpsPerBlock, int kMinBlocks>
+		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32, kMinBlocks) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int game_begin, int games, int S, int rules,
 				int draw_after, int max_nodes, SolverOutputs out, const uint8_t *__restrict__ slot_is_root, int *__restrict__ nn_list, int *__restrict__ nn_count,
 				uint32_t *__restrict__ status)
 		{
@@ -173,8 +176,15 @@ namespace agb
 			int *nn_count, cudaStream_t stream)
 	{
 		const int draw_after = e->cfg.draw_after > 0 ? e->cfg.draw_after : e->cells;
-		solve_games_kernel<<<(game_count + kSolverWarpsPerBlock - 1) / kSolverWarpsPerBlock, kSolverWarpsPerBlock * 32, 0, stream>>>(e->store, e->tables, st,
-				game_begin, game_count, e->cfg.rows, e->cfg.rules, draw_after, e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
+		static const bool force_dense = getenv("AGB_SOLVER_DENSE") != nullptr; // tests: exercise the low-register build with few games
+		if (game_count <= 28 * sms and not force_dense)
+			solve_games_kernel<1, 28><<<game_count, 32, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows, e->cfg.rules, draw_after,
+					e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		else
+			solve_games_kernel<2, 28><<<(game_count + 1) / 2, 64, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows, e->cfg.rules, draw_after,
+					e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

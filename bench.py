@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--games", type=int, default=GAMES)
+    ap.add_argument("--batch", type=int, default=BATCH, help="SearchConfig::max_batch_size (leaves per game and step)")
     ap.add_argument("--groups", type=int, default=0, help="pipeline groups (0 = engine default)")
     ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -194,8 +195,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     games = args.games
-    eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * BATCH, device=local_rank, blocks=BLOCKS, filters=FILTERS,
-                     q_head=False, games=games, max_batch_size=BATCH, max_simulations=SIMS, init_to="parent", max_nodes_per_game=1536,
+    eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * args.batch, device=local_rank, blocks=BLOCKS, filters=FILTERS,
+                     q_head=False, games=games, max_batch_size=args.batch, max_simulations=SIMS, init_to="parent", max_nodes_per_game=1536,
                      max_edges_per_game=1536 * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
                      solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups, use_symmetries=True)
     # C1: rank 0 owns the weights and broadcasts them over NCCL (NetworkLoader::get per thread in the reference)
@@ -232,9 +233,9 @@ def main():
     nn_positions = st1["nn_positions"] - st0["nn_positions"]
 
     # e2e: NNEvaluator drop-in through host buffers (pinned), copies inside the timed region
-    n_e2e = games * BATCH
-    e_boards = torch.from_numpy(np.repeat(boards, BATCH, axis=0)).pin_memory()
-    e_stm = torch.from_numpy(np.repeat(stm, BATCH)).pin_memory()
+    n_e2e = games * args.batch
+    e_boards = torch.from_numpy(np.repeat(boards, args.batch, axis=0)).pin_memory()
+    e_stm = torch.from_numpy(np.repeat(stm, args.batch)).pin_memory()
     e_policy = torch.empty((n_e2e, SIZE * SIZE), dtype=torch.float32).pin_memory()
     e_value = torch.empty((n_e2e, 3), dtype=torch.float32).pin_memory()
     lib = eng._lib

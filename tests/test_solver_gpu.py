@@ -79,3 +79,10 @@ def test_generate_openings(ref):
     again, _ = eng.generate_openings(48)
     assert (again == boards).all()
     eng.close()
+
+
+def test_low_register_solver_build_matches_reference(ref, monkeypatch):
+    """Launches with more than 28 games per SM use a build of the solver kernel capped at 32 registers (56 resident games per SM);
+    AGB_SOLVER_DENSE forces it here so that it is checked against the reference as well."""
+    monkeypatch.setenv("AGB_SOLVER_DENSE", "1")
+    test_agb_solve_matches_reference(ref, None, 1, 15, 100, 0.3)
