@@ -398,4 +398,26 @@ extern "C"
 		solver->solver.clear();
 		return run_solver(solver->solver, solver->gc, board, sign_to_move, max_nodes, moves, scores, result_score, flags);
 	}
+	// MoveGenerator::generate in a given MoveGeneratorMode on a fresh PatternCalculator, like MoveGenWrapper of the reference's
+	// test/search/alpha_beta/test_move_generator.cpp:22-43. flags: bit0 must_defend, bit1 has_initiative; returns the list size
+	int agref_generate(int rules, int rows, int cols, const int8_t *board, int sign_to_move, int mode, uint16_t *moves, uint16_t *scores, int32_t *flags)
+	{
+		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
+		matrix<Sign> b(rows, cols);
+		for (int i = 0; i < rows * cols; i++)
+			b[i] = static_cast<Sign>(board[i]);
+		PatternCalculator calc(gc);
+		MoveGenerator generator(gc, calc);
+		ActionStack stack(1024 + rows * cols);
+		calc.setBoard(b, static_cast<Sign>(sign_to_move));
+		ActionList list(stack);
+		generator.generate(list, static_cast<MoveGeneratorMode>(mode));
+		for (int i = 0; i < list.size(); i++)
+		{
+			moves[i] = list[i].move.toShort();
+			scores[i] = Score::to_short(list[i].score);
+		}
+		*flags = static_cast<int>(list.must_defend) | (static_cast<int>(list.has_initiative) << 1);
+		return list.size();
+	}
 }

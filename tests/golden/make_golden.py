@@ -7,7 +7,8 @@ the GPU box, which has neither, can still check against the reference's known an
 Two kinds of vectors:
  * known answers hand-written by the reference's authors, transcribed mechanically from test/game/test_renju.cpp
    (EXPECT_TRUE/FALSE(is_forbidden(...)), getOutcome expectations), test_freestyle/standard/caro.cpp (getOutcome)
-   and test/networks/test_NNInputFeatures.cpp (feature bits at named cells);
+   test/networks/test_NNInputFeatures.cpp (feature bits at named cells) and test/search/alpha_beta/test_move_generator.cpp
+   (action-list size, flags, members and scores per generator mode);
  * outputs of the reference itself (libagref.so) on every board literal found in those files and in
    test/search/alpha_beta/test_move_generator.cpp + src/utils/selfcheck.cpp, plus seeded random boards.
 """
@@ -135,6 +136,52 @@ def transcribe_feature_bits(known, boards):
                           "source": "test/networks/test_NNInputFeatures.cpp"})
 
 
+SCORES = {"loss_in": 0, "draw_in": 1, "win_in": 3}
+
+
+def transcribe_move_generator(known):
+    """test/search/alpha_beta/test_move_generator.cpp: per TEST one board, MoveGenWrapper objects (rules, side to move), action lists
+    generated in a MoveGeneratorMode, and EXPECT_* on size / must_defend / has_initiative / contains(Move) / getScoreOf(Move)."""
+    board, wrappers, lists = None, {}, {}
+    for kind, val in walk_source(f"{REF}/test/search/alpha_beta/test_move_generator.cpp"):
+        if kind == "board":
+            board, wrappers, lists = val.copy(), {}, {}
+            continue
+        line = val.strip()
+        if line.startswith("//") or board is None:
+            continue
+        m = re.match(r"MoveGenWrapper (\w+)\(GameRules::(\w+), board, Sign::(\w+)\);", line)
+        if m:
+            wrappers[m.group(1)] = (RULES[m.group(2)], 1 if m.group(3) == "CROSS" else 2)
+            continue
+        m = re.match(r"(?:const )?ActionList (\w+) = (\w+)\(MoveGeneratorMode::(\w+)\);", line)
+        if m and m.group(2) in wrappers:
+            rules, stm = wrappers[m.group(2)]
+            entry = {"kind": "movegen", "rules": rules, "board": board.flatten().tolist(), "size": board.shape[0], "stm": stm, "mode": m.group(3),
+                     "contains": [], "scores": [], "source": "test/search/alpha_beta/test_move_generator.cpp"}
+            lists[m.group(1)] = entry
+            known.append(entry)
+            continue
+        m = re.match(r"EXPECT_(EQ|GE)\((\w+)\.size\(\), (\d+)\);", line)
+        if m and m.group(2) in lists:
+            lists[m.group(2)]["size_eq" if m.group(1) == "EQ" else "size_ge"] = int(m.group(3))
+            continue
+        m = re.match(r"EXPECT_(TRUE|FALSE)\((\w+)\.(must_defend|has_initiative)\);", line)
+        if m and m.group(2) in lists:
+            lists[m.group(2)][m.group(3)] = m.group(1) == "TRUE"
+            continue
+        m = re.match(r'EXPECT_TRUE\((\w+)\.contains\(Move\("(\w+)"\)\)\);', line)
+        if m and m.group(1) in lists:
+            r, c, _ = parse_move(m.group(2))
+            lists[m.group(1)]["contains"].append([r, c])
+            continue
+        m = re.match(r'EXPECT_EQ\((\w+)\.getScoreOf\(Move\("(\w+)"\)\), Score::(\w+)\((\d+)\)\);', line)
+        if m and m.group(1) in lists:
+            r, c, _ = parse_move(m.group(2))
+            pv, n = SCORES[m.group(3)], int(m.group(4))
+            lists[m.group(1)]["scores"].append([r, c, (pv << 13) | (4000 + (-n if pv == 3 else n))])
+
+
 def collect_boards(path, rules_list, boards):
     for kind, val in walk_source(path):
         if kind == "board":
@@ -161,6 +208,7 @@ def main():
     for fname in ("test_freestyle.cpp", "test_standard.cpp", "test_caro.cpp"):
         transcribe_outcomes(fname, known, boards)
     transcribe_feature_bits(known, boards)
+    transcribe_move_generator(known)
     collect_boards(f"{REF}/test/search/alpha_beta/test_move_generator.cpp", [0, 1, 2, 3, 4], boards)
     collect_boards(f"{REF}/src/utils/selfcheck.cpp", [0, 2], boards)
     rng = np.random.default_rng(20261017)

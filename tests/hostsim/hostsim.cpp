@@ -279,3 +279,50 @@ extern "C" int hostsim_prepare_opening(void *p, int rules, int S, int min_moves,
 	std::copy(result.begin(), result.end(), moves);
 	return static_cast<int>(result.size());
 }
+
+// MoveGenerator::generate(THREATS or OPTIMAL) on a position set up like PatternCalculator::setBoard; flags: bit0 must_defend, bit1 has_initiative
+extern "C" int hostsim_generate(int rules, int S, const int8_t *board_in, int stm, int mode, const uint8_t *pattern_table, const uint8_t *threat_table,
+		const uint16_t *def_table, uint16_t *moves, uint16_t *scores, int32_t *flags)
+{
+	using namespace agb::solver;
+	const int cells = S * S;
+	std::vector<int8_t> board(board_in, board_in + cells);
+	std::vector<uint64_t> lines(kMaxLines);
+	for (int l = 0; l < line_count(S); l++)
+		lines[l] = build_line(board.data(), S, l);
+	std::vector<uint32_t> ptypes(cells, 0);
+	std::vector<uint8_t> threats(cells, 0);
+	std::vector<int32_t> hist_count(2 * kHistTypes, 0);
+	std::vector<uint16_t> hist_cells(2 * kHistTypes * cells, 0);
+	int stones = 0;
+	for (int r = 0; r < S; r++)
+		for (int c = 0; c < S; c++)
+		{
+			const int idx = r * S + c;
+			stones += (board[idx] != NONE);
+			if (board[idx] != NONE)
+				continue;
+			ptypes[idx] = classify_cell(lines.data(), pattern_table, r, c, S);
+			threats[idx] = threat_of_cell(ptypes[idx], threat_table);
+			for (int colour = 0; colour < 2; colour++)
+			{
+				const int t = (threats[idx] >> (4 * colour)) & 15;
+				if (t != TT_NONE)
+					hist_cells[(colour * kHistTypes + t) * cells + hist_count[colour * kHistTypes + t]++] = mk_loc(r, c);
+			}
+		}
+	DynState d;
+	d.v = View { S, cells, rules, stm, stones, cells, cells, board.data(), lines.data(), ptypes.data(), threats.data(), nullptr, hist_count.data(), hist_cells.data(),
+			pattern_table, def_table, &d };
+	d.board = board.data();
+	d.lines = lines.data();
+	d.ptypes = ptypes.data();
+	d.threats = threats.data();
+	d.hist_count = hist_count.data();
+	d.hist_cells = hist_cells.data();
+	d.threat_table = threat_table;
+	MoveGenerator gen(d.v, moves, scores);
+	gen.generate(mode);
+	*flags = static_cast<int>(gen.out.must_defend) | (static_cast<int>(gen.out.has_initiative) << 1);
+	return gen.out.n_actions;
+}

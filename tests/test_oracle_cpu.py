@@ -346,3 +346,61 @@ def test_alpha_beta_solver_matches_reference(ref, ref_fast, hostsim, rules, size
     assert total_nodes > 150 or max_nodes == 1
     lib.agref_solver_destroy(rh)
     hostsim.hostsim_solver_destroy(hh)
+
+
+# ---- the reference's own move generator tests (test/search/alpha_beta/test_move_generator.cpp) --------------------------------------
+MODES = {"BASIC": 0, "THREATS": 1, "OPTIMAL": 2, "REDUCED": 3, "LEGAL": 4}
+
+
+def _check_movegen_expectations(entry, moves, scores, flags):
+    cells = {((int(m) >> 2) & 127, (int(m) >> 9) & 127): int(s) for m, s in zip(moves, scores)}
+    if "size_eq" in entry:
+        assert len(moves) == entry["size_eq"], (entry["size_eq"], len(moves))
+    if "size_ge" in entry:
+        assert len(moves) >= entry["size_ge"]
+    if "must_defend" in entry:
+        assert bool(flags & 1) == entry["must_defend"]
+    if "has_initiative" in entry:
+        assert bool(flags & 2) == entry["has_initiative"]
+    for r, c in entry["contains"]:
+        assert (r, c) in cells, (r, c, sorted(cells))
+    for r, c, s in entry["scores"]:
+        assert cells.get((r, c)) == s, (r, c, hex(s), cells.get((r, c)))
+
+
+def _movegen_entries(golden, modes):
+    return [e for e in golden[0] if e["kind"] == "movegen" and e["mode"] in modes]
+
+
+def test_reference_move_generator_known_answers_pin_the_oracle(ref, golden):
+    """The hand-written expectations of the reference's move generator tests (list size, must_defend, has_initiative, members, scores in
+    every MoveGeneratorMode) hold for oracle/_ref: the build used as the K5 oracle behaves like the reference's authors say it must."""
+    entries = _movegen_entries(golden, MODES)
+    assert len(entries) >= 50
+    for e in entries:
+        cells = e["size"] ** 2
+        moves, scores, flags = np.zeros(cells, np.uint16), np.zeros(cells, np.uint16), np.zeros(1, np.int32)
+        board = np.array(e["board"], np.int8)
+        n = ref.lib.agref_generate(e["rules"], e["size"], e["size"], _p(board), e["stm"], MODES[e["mode"]], _p(moves), _p(scores), _p(flags))
+        _check_movegen_expectations(e, moves[:n], scores[:n], int(flags[0]))
+
+
+def test_kernel_logic_move_generator_known_answers(ref, hostsim, golden):
+    """The same expectations for the host-compiled K5 generator (THREATS and OPTIMAL, the modes the solver uses), plus equality with the
+    reference's list, order included."""
+    entries = _movegen_entries(golden, ("THREATS", "OPTIMAL"))
+    assert len(entries) >= 45
+    tables = {}
+    for e in entries:
+        if e["rules"] not in tables:
+            tables[e["rules"]] = _solver_tables(hostsim, e["rules"])
+        t = tables[e["rules"]]
+        cells = e["size"] ** 2
+        board = np.array(e["board"], np.int8)
+        moves, scores, flags = np.zeros(cells, np.uint16), np.zeros(cells, np.uint16), np.zeros(1, np.int32)
+        n = hostsim.hostsim_generate(e["rules"], e["size"], _p(board), e["stm"], MODES[e["mode"]], _p(t[0]), _p(t[1]), _p(t[2]), _p(moves), _p(scores),
+                                     _p(flags))
+        _check_movegen_expectations(e, moves[:n], scores[:n], int(flags[0]))
+        rm, rs, rf = np.zeros(cells, np.uint16), np.zeros(cells, np.uint16), np.zeros(1, np.int32)
+        rn = ref.lib.agref_generate(e["rules"], e["size"], e["size"], _p(board), e["stm"], MODES[e["mode"]], _p(rm), _p(rs), _p(rf))
+        assert rn == n and (rm[:n] == moves[:n]).all() and (rs[:n] == scores[:n]).all() and rf[0] == flags[0]

@@ -86,3 +86,33 @@ def test_low_register_solver_build_matches_reference(ref, monkeypatch):
     AGB_SOLVER_DENSE forces it here so that it is checked against the reference as well."""
     monkeypatch.setenv("AGB_SOLVER_DENSE", "1")
     test_agb_solve_matches_reference(ref, None, 1, 15, 100, 0.3)
+
+
+def test_move_generator_known_answers_on_the_device(golden):
+    """The reference's own move generator tests (test/search/alpha_beta/test_move_generator.cpp, OPTIMAL mode) through agb_solve with a
+    budget of one position, i.e. K5's root generation on the device: list size, must-defend flag, members and scores as the reference's
+    authors wrote them down."""
+    import alphagomoku_b200 as agb
+    entries = [e for e in golden[0] if e["kind"] == "movegen" and e["mode"] == "OPTIMAL"]
+    assert len(entries) >= 45
+    engines = {}
+    for e in entries:
+        key = (e["rules"], e["size"])
+        if key not in engines:
+            engines[key] = agb.Engine(agb.GameConfig(agb.GameRules(e["rules"]), e["size"], e["size"]), max_boards=8)
+        board = np.array(e["board"], np.int8)
+        _, n_actions, moves, action_scores, flags = engines[key].solve(board[None], np.array([e["stm"]], np.int8), 1)
+        n = int(n_actions[0])
+        cells = {((int(m) >> 2) & 127, (int(m) >> 9) & 127): int(s) for m, s in zip(moves[0, :n], action_scores[0, :n])}
+        if "size_eq" in e:
+            assert n == e["size_eq"], (e["size_eq"], n)
+        if "size_ge" in e:
+            assert n >= e["size_ge"]
+        if "must_defend" in e:
+            assert bool(flags[0] & 1) == e["must_defend"]
+        for r, c in e["contains"]:
+            assert (r, c) in cells
+        for r, c, s in e["scores"]:
+            assert cells.get((r, c)) == s
+    for eng in engines.values():
+        eng.close()
