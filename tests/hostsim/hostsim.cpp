@@ -326,3 +326,17 @@ extern "C" int hostsim_generate(int rules, int S, const int8_t *board_in, int st
 	*flags = static_cast<int>(gen.out.must_defend) | (static_cast<int>(gen.out.has_initiative) << 1);
 	return gen.out.n_actions;
 }
+
+// Score arithmetic of the search (search/Score.hpp) as the device uses it
+extern "C" uint16_t hostsim_score_negate(uint16_t s)
+{
+	return agb::solver::sc_negate(s);
+}
+extern "C" uint16_t hostsim_score_invert(uint16_t s, int delta)
+{
+	return agb::solver::sc_invert(s, delta);
+}
+extern "C" int hostsim_score_is_proven(uint16_t s)
+{
+	return agb::solver::sc_is_proven(s) ? 1 : 0;
+}

@@ -404,3 +404,29 @@ def test_kernel_logic_move_generator_known_answers(ref, hostsim, golden):
         rm, rs, rf = np.zeros(cells, np.uint16), np.zeros(cells, np.uint16), np.zeros(1, np.int32)
         rn = ref.lib.agref_generate(e["rules"], e["size"], e["size"], _p(board), e["stm"], MODES[e["mode"]], _p(rm), _p(rs), _p(rf))
         assert rn == n and (rm[:n] == moves[:n]).all() and (rs[:n] == scores[:n]).all() and rf[0] == flags[0]
+
+
+def test_score_arithmetic_known_answers(hostsim):
+    """test/search/test_Score.cpp:14-111 restated on the 16-bit wire form the device works with (3-bit proven value, 13-bit eval + 4000,
+    Score.hpp:47-68): ordering is the ordering of the raw words, unary minus, invert_up / invert_down, the two infinities."""
+    win_in = lambda n: (3 << 13) | (4000 - n)  # noqa: E731
+    loss_in = lambda n: (0 << 13) | (4000 + n)  # noqa: E731
+    draw_in = lambda n: (1 << 13) | (4000 + n)  # noqa: E731
+    ev = lambda e: (2 << 13) | (4000 + e)  # noqa: E731
+    minus_inf, plus_inf = 0x0000, 0xFFFF
+    for f in (hostsim.hostsim_score_negate, hostsim.hostsim_score_invert):
+        f.restype = ctypes.c_uint16
+    neg = lambda s: hostsim.hostsim_score_negate(ctypes.c_uint16(s))  # noqa: E731
+    inv = lambda s, d: hostsim.hostsim_score_invert(ctypes.c_uint16(s), d)  # noqa: E731
+    # comparison (test_Score.cpp:16-28)
+    assert win_in(4) > win_in(5) and win_in(4) > draw_in(5) and win_in(4) > ev(4000) and win_in(4) > loss_in(5)
+    assert ev(123) > ev(-123) and ev(-4000) > draw_in(5) and ev(-4000) > loss_in(5)
+    assert draw_in(4) > draw_in(3) and draw_in(4) > loss_in(5) and loss_in(4) > loss_in(3)
+    # unary minus (:58-72), invert_up (:77-91), invert_down (:96-110) on s1 = win_in(5), s2 = loss_in(5), s3 = draw_in(5), s4 = 123, s5 = -123
+    s = [win_in(5), loss_in(5), draw_in(5), ev(123), ev(-123), minus_inf, plus_inf]
+    assert [neg(x) for x in s] == [loss_in(5), win_in(5), draw_in(5), ev(-123), ev(123), plus_inf, minus_inf]
+    assert [inv(x, +1) for x in s] == [loss_in(6), win_in(6), draw_in(6), ev(-123), ev(123), plus_inf, minus_inf]
+    assert [inv(x, -1) for x in s] == [loss_in(4), win_in(4), draw_in(4), ev(-123), ev(123), plus_inf, minus_inf]
+    # infinities are not proven scores (:36-43)
+    assert hostsim.hostsim_score_is_proven(ctypes.c_uint16(minus_inf)) == 0 and hostsim.hostsim_score_is_proven(ctypes.c_uint16(plus_inf)) == 0
+    assert hostsim.hostsim_score_is_proven(ctypes.c_uint16(win_in(3))) == 1 and hostsim.hostsim_score_is_proven(ctypes.c_uint16(ev(5))) == 0
