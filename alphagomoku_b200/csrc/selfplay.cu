@@ -204,6 +204,8 @@ namespace agb
 				int game_begin, game_count, slot_base;
 				int32_t *eval_count; // this group's slot counter
 				int use_symmetries, first_game_id;
+				int max_children; // MCTSConfig::max_children (0: unlimited)
+				float expansion_threshold; // MCTSConfig::policy_expansion_threshold
 				unsigned long long sym_seed;
 				Tables tables;
 				BoardStore store;
@@ -556,6 +558,70 @@ namespace agb
 				p.s.solver.game_slot_count[g] = n_slots;
 		}
 
+		// ---- std::partial_sort as libstdc++ runs it (bits/stl_algo.h __partial_sort -> __heap_select + __sort_heap, bits/stl_heap.h),
+		// with EdgeComparator<MaxPolicyPrior> (Edge.hpp:156-171). The order of equal elements is decided by these heap moves, so
+		// prune_weak_moves (EdgeGenerator.cpp:69-84) is reproduced move for move. Single thread.
+		__device__ inline bool edge_before(const EdgeD &a, const EdgeD &b)
+		{
+			if ((score::is_proven(a.score) or score::is_proven(b.score)) and a.score != b.score)
+				return a.score > b.score;
+			return a.prior > b.prior;
+		}
+		__device__ void heap_push(EdgeD *first, int hole, int top, const EdgeD &value)
+		{
+			int parent = (hole - 1) / 2;
+			while (hole > top and edge_before(first[parent], value))
+			{
+				first[hole] = first[parent];
+				hole = parent;
+				parent = (hole - 1) / 2;
+			}
+			first[hole] = value;
+		}
+		__device__ void heap_adjust(EdgeD *first, int hole, int len, const EdgeD &value)
+		{
+			const int top = hole;
+			int child = hole;
+			while (child < (len - 1) / 2)
+			{
+				child = 2 * (child + 1);
+				if (edge_before(first[child], first[child - 1]))
+					child--;
+				first[hole] = first[child];
+				hole = child;
+			}
+			if ((len & 1) == 0 and child == (len - 2) / 2)
+			{
+				child = 2 * (child + 1);
+				first[hole] = first[child - 1];
+				hole = child - 1;
+			}
+			heap_push(first, hole, top, value);
+		}
+		__device__ void partial_sort_edges(EdgeD *first, int middle, int last)
+		{
+			if (middle >= 2)
+				for (int parent = (middle - 2) / 2; parent >= 0; parent--)
+				{ // __make_heap
+					const EdgeD value = first[parent];
+					heap_adjust(first, parent, middle, value);
+				}
+			for (int i = middle; i < last; i++)
+				if (edge_before(first[i], first[0]))
+				{ // __pop_heap(first, middle, i)
+					const EdgeD value = first[i];
+					first[i] = first[0];
+					heap_adjust(first, 0, middle, value);
+				}
+			for (int end = middle; end > 1;)
+			{ // __sort_heap
+				end--;
+				const EdgeD value = first[end];
+				first[end] = first[0];
+				heap_adjust(first, 0, end, value);
+			}
+		}
+
 		// ---- K7: edge generation + expand + backup ------------------------------------------------------------------------
 		__device__ void node_update_value(NodeD &n, float win, float draw)
 		{ // Node::updateValue (Node.hpp:268-274): 1.0 / visits in double, narrowed to float
@@ -780,6 +846,25 @@ namespace agb
 						__syncwarp();
 					}
 					count = kept;
+				}
+				else if (not is_root_task and p.max_children > 0 and count > p.max_children and not must_defend)
+				{ // prune_weak_moves, unproven position: the max_children best edges, then those above the expansion threshold
+					if (lane == 0)
+					{
+						EdgeD *first = edges + n_edges;
+						partial_sort_edges(first, p.max_children, count);
+						float sum_policy = 0.0f;
+						for (int i = 0; i < p.max_children; i++)
+							sum_policy += first[i].prior;
+						const float threshold = p.expansion_threshold * sum_policy;
+						int kept = 0;
+						for (int i = 0; i < p.max_children; i++)
+							if (first[i].prior >= threshold)
+								kept++;
+						count = kept;
+					}
+					count = __shfl_sync(kFullMask, count, 0);
+					__syncwarp();
 				}
 				// renormalize_policy: sequential float sum in edge order (EdgeGenerator.cpp:23-40)
 				if (lane == 0 and count > 0)
@@ -1281,6 +1366,8 @@ namespace agb
 			p.slot_base = 0;
 			p.eval_count = e->selfplay->eval_count;
 			p.use_symmetries = e->cfg.use_symmetries != 0;
+			p.max_children = e->cfg.max_children > 0 ? e->cfg.max_children : 0;
+			p.expansion_threshold = e->cfg.policy_expansion_threshold;
 			p.first_game_id = e->cfg.first_game_id;
 			p.sym_seed = e->cfg.seed * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull;
 			p.tables = e->tables;
@@ -1298,8 +1385,6 @@ namespace agb
 		const AgbConfig &c = e->cfg;
 		if (c.blocks <= 0)
 			return e->fail(AGB_EINVAL, "self-play needs a network (blocks > 0)");
-		if (c.max_children > 0 and c.max_children < e->cells)
-			return e->fail(AGB_EINVAL, "max_children below the board size (policy pruning of unproven positions) is not on the device yet: use 0 (unlimited, the reference default)");
 		if (c.max_batch_size <= 0 or c.games * c.max_batch_size > c.max_boards)
 			return e->fail(AGB_EINVAL, "games * max_batch_size must fit in max_boards");
 		SelfplayState *s = new SelfplayState();

@@ -93,7 +93,8 @@ namespace
 extern "C"
 {
 	void* agref_sp_create(int rules, int rows, int cols, int draw_after, int max_batch_size, int max_simulations, const char *init_to,
-			float exploration_constant, float information_leak_threshold, int use_solver, int solver_max_positions, agref_eval_fn eval_fn, void *ctx)
+			float exploration_constant, float information_leak_threshold, int use_solver, int solver_max_positions, agref_eval_fn eval_fn, void *ctx,
+			int max_children, float policy_expansion_threshold)
 	{
 		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
 		if (draw_after > 0)
@@ -111,6 +112,11 @@ extern "C"
 		sc.search_config.mcts_config.edge_selector_config.init_to = init_to;
 		sc.search_config.mcts_config.edge_selector_config.exploration_constant = exploration_constant;
 		sc.search_config.tss_config.max_positions = solver_max_positions;
+		if (max_children > 0)
+		{ // MCTSConfig: prune_weak_moves keeps at most this many edges of an unproven position (EdgeGenerator.cpp:69-84)
+			sc.search_config.mcts_config.max_children = max_children;
+			sc.search_config.mcts_config.policy_expansion_threshold = policy_expansion_threshold;
+		}
 		agref::g_game_config = gc;
 		agref::g_eval_fn = eval_fn;
 		agref::g_eval_ctx = ctx;

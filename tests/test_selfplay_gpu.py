@@ -45,7 +45,14 @@ def test_lockstep_engine_caro_20x20(ref, rules, q_head, init_to, batch, sims, so
     _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=20)
 
 
-def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15):
+@pytest.mark.parametrize("rules,q_head,solver,max_children,threshold", [(0, False, 0, 12, 1.0e-4), (1, True, 50, 20, 0.02), (4, False, 1, 6, 0.1)])
+def test_lockstep_engine_with_policy_pruning(ref, rules, q_head, solver, max_children, threshold):
+    """MCTSConfig::max_children / policy_expansion_threshold: prune_weak_moves on unproven positions (std::partial_sort by prior, then the
+    threshold on the kept priors), EdgeGenerator.cpp:69-84."""
+    _run_case(ref, rules, q_head, "parent", 4, 60, solver, max_children=max_children, threshold=threshold)
+
+
+def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_children=0, threshold=1.0e-4):
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import refapi
@@ -55,7 +62,8 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15):
     draw_after = 14 if solver == 0 else 28
     eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
                      games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver,
-                     solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0, pipeline_groups=2 if solver > 0 else 1)  # the reference's table size (AlphaBetaSearch.cpp:55)
+                     solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0, pipeline_groups=2 if solver > 0 else 1, max_children=max_children,
+                     policy_expansion_threshold=threshold)  # the reference's table size (AlphaBetaSearch.cpp:55)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
     def evaluate(features):
@@ -69,7 +77,8 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15):
     fast = solver > 0 and rules == 2
     for g in range(games):
         r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=solver > 0,
-                                solver_max_positions=max(solver, 1), draw_after=draw_after, fast=fast)
+                                solver_max_positions=max(solver, 1), draw_after=draw_after, fast=fast, max_children=max_children,
+                                policy_expansion_threshold=threshold)
         refs.append(r)
     if solver > 0:
         eng.set_solver_keys(np.stack([r.solver_keys() for r in refs]))
