@@ -348,6 +348,15 @@ namespace agb
 				entries[2 * i + 1] = kEmptyEntryData;
 			}
 		}
+		AGB_HD inline void tt_prefetch(const HashTable &t, uint64_t lo)
+		{ // SharedHashTable::prefetch (SharedHashTable.hpp:183-186): the bucket is on its way while the move is being added
+#ifdef __CUDA_ARCH__
+			asm volatile("prefetch.global.L2 [%0];" :: "l"(t.entries + 8 * (lo & t.bucket_mask)));
+#else
+			(void) t;
+			(void) lo;
+#endif
+		}
 		AGB_HD_NOINLINE inline uint64_t tt_seek(const HashTable &t, uint64_t lo, uint64_t hi)
 		{
 			const uint64_t *bucket = t.entries + 8 * (lo & t.bucket_mask);
@@ -875,6 +884,7 @@ namespace agb
 							{
 								const uint16_t mv = am[i];
 								hash_toggle(tt, key_lo, key_hi, d.v.S, mv);
+								tt_prefetch(tt, key_lo);
 								Frame &child = frames[top + 1];
 								child.list_begin = stack_offset;
 								child.list_size = 0;
