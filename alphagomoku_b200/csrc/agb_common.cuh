@@ -4,7 +4,11 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define AGB_HD __host__ __device__
-#define AGB_HD_NOINLINE __host__ __device__ __noinline__ // keeps the single-lane solver's code small enough for the instruction cache
+#ifdef __CUDA_ARCH__
+#define AGB_HD_NOINLINE __host__ __device__ __noinline__ // device pass: keeps the solver's code small enough for the instruction cache
+#else
+#define AGB_HD_NOINLINE __host__ __device__
+#endif
 #else
 #define AGB_HD
 #define AGB_HD_NOINLINE

@@ -89,11 +89,6 @@ namespace agb
 		{
 			asm volatile("bar.sync 1, 256;" ::: "memory");
 		}
-		__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
-		{
-			const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-			return *reinterpret_cast<const uint32_t*>(&v);
-		}
 		__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
 		{ // cvt.rn.relu.bf16x2.f32: max(x, 0) folded into the rounding conversion
 			uint32_t r;
@@ -663,7 +658,7 @@ namespace agb
 			{
 				const int nb = min(kValueBoards, n - b0);
 				if (threadIdx.x < kValueBoards)
-					slot[threadIdx.x] = (threadIdx.x < nb) ? (gather ? gather[b0 + threadIdx.x] : b0 + threadIdx.x + slot_base) : -1;
+					slot[threadIdx.x] = (static_cast<int>(threadIdx.x) < nb) ? (gather ? gather[b0 + threadIdx.x] : b0 + static_cast<int>(threadIdx.x) + slot_base) : -1;
 				__syncthreads();
 				for (int k = 0; k < kValueBoards; k++)
 				{

@@ -216,10 +216,6 @@ namespace agb
 		{
 			return win + 0.5f * draw;
 		}
-		__device__ inline int lowest_lane(unsigned mask)
-		{
-			return __ffs(mask) - 1;
-		}
 
 		// ---- transposition table ---------------------------------------------------------------------------------
 		__device__ int table_seek(const Params &p, int g, uint64_t hash, const uint64_t *bits, int stm, int lane)
@@ -1191,7 +1187,6 @@ namespace agb
 					next_stm = p.s.opening_stm[k];
 				}
 				uint64_t h = 0;
-				uint64_t nb[2] = { 0, 0 }; // lanes 0..3: cross words, via shuffles below
 				__syncwarp();
 				for (int i = lane; i < cells; i += 32)
 					board[i] = src ? src[i] : 0;
@@ -1208,7 +1203,6 @@ namespace agb
 						}
 					bits[lane] = w;
 				}
-				(void) nb;
 				for (int o = 8; o > 0; o >>= 1) // lanes kBitWords..15 contribute zero
 					h ^= __shfl_xor_sync(kFullMask, h, o);
 				if (lane == 0)

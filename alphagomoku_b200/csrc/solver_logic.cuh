@@ -224,7 +224,7 @@ namespace agb
 
 		// ---- view of one analysed position ---------------------------------------------------------------------------------------
 		struct DynState;
-		AGB_HD inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c); // solver_search.cuh: live state, reference side effects
+		AGB_HD_NOINLINE inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c); // solver_search.cuh: live state, reference side effects
 		enum : int { GEN_BASIC = 0, GEN_THREATS = 1, GEN_OPTIMAL = 2, GEN_REDUCED = 3, GEN_LEGAL = 4 }; // MoveGeneratorMode (MoveGenerator.hpp)
 		struct View
 		{
