@@ -430,3 +430,15 @@ def test_score_arithmetic_known_answers(hostsim):
     # infinities are not proven scores (:36-43)
     assert hostsim.hostsim_score_is_proven(ctypes.c_uint16(minus_inf)) == 0 and hostsim.hostsim_score_is_proven(ctypes.c_uint16(plus_inf)) == 0
     assert hostsim.hostsim_score_is_proven(ctypes.c_uint16(win_in(3))) == 1 and hostsim.hostsim_score_is_proven(ctypes.c_uint16(ev(5))) == 0
+
+
+def test_reference_side_shims_compile_against_the_reference_headers(tmp_path):
+    """integration/agb200_shims.hpp (the NNEvaluator drop-in and the batched AlphaBetaSearch::solve of INTEGRATION.md) must compile against the
+    reference's own headers: SearchTask accessors, Score / Value / Move constructors and the C ABI agree."""
+    if not os.path.isdir("/root/reference/include"):
+        pytest.skip("/root/reference absent")
+    import subprocess
+    tu = tmp_path / "shim_tu.cpp"
+    tu.write_text('#include "integration/agb200_shims.hpp"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I/root/reference/include", "-I" + os.path.join(ROOT, "oracle", "ref_stub"),
+                           "-I" + os.path.join(ROOT, "include"), "-I" + ROOT, str(tu)])
