@@ -255,6 +255,10 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    # C2 (outside the timed regions): finished-game records of every rank, all-gathered like the reference's shared GameDataBuffer
+    records, n_finished = eng.pop_finished()
+    gathered = sharding.gather_records(records)
+    c2_bytes = sum(len(g) for g in gathered)
     # whole-job totals: sum of the units every rank processed, max of the device times
     sums, maxes = sharding.reduce_counters([float(evals), ms, float(n_e2e * e2e_steps), e2e_s, float(launches)])
     if rank == 0:
@@ -282,6 +286,7 @@ def main():
                              "positions_per_launch": nn_positions / max(nn_launches, 1), "ms_per_launch": nn_ns / max(nn_launches, 1) * 1e-6,
                              "share_of_step": (nn_ns * 1e-6) / ms, "solver_share_of_step": (st1["solver_kernel_ns"] - st0["solver_kernel_ns"]) * 1e-6 / ms,
                              "leaf_positions_per_step": (st1["nb_node_count"] - st0["nb_node_count"]) / args.steps},
+                "sharding": {"c1_weight_bytes_broadcast": int(blob.nbytes), "c2_record_bytes_gathered": int(c2_bytes), "ranks": world},
                 "clocks": clocks.summary()}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, _ = run_reference(args.cpu_seconds)
