@@ -20,7 +20,8 @@ class AgbConfig(ctypes.Structure):
         ("policy_expansion_threshold", ctypes.c_float), ("max_children", ctypes.c_int32),
         ("solver_max_positions", ctypes.c_int32), ("use_symmetries", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("solver_table_entries", ctypes.c_int32),
-        ("pipeline_groups", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
+        ("pipeline_groups", ctypes.c_int32), ("final_selector", ctypes.c_int32), ("final_exploration_constant", ctypes.c_float),
+        ("reserved", ctypes.c_int32 * 3),
     ]
 
 

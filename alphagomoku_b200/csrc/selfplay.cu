@@ -205,6 +205,8 @@ namespace agb
 				int32_t *eval_count; // this group's slot counter
 				int use_symmetries, first_game_id;
 				int max_children; // MCTSConfig::max_children (0: unlimited)
+				int final_selector; // SelfplayConfig::final_selector.policy (AGB_FINAL_*)
+				float final_exploration; // its exploration_constant (lcb)
 				float expansion_threshold; // MCTSConfig::policy_expansion_threshold
 				unsigned long long sym_seed;
 				Tables tables;
@@ -1009,6 +1011,50 @@ namespace agb
 			return n;
 		}
 
+		// ---- final move selectors (EdgeSelector.cpp:426-536, 1340-1433): the value find_best_edge maximises, first maximum wins -----------------
+		__device__ float final_selector_value(const Params &p, const EdgeD &e, const NodeD &parent, float parent_log_visit)
+		{
+			const int proven = score::pv(e.score);
+			const float distance = static_cast<float>(score::distance(e.score));
+			const float expectation = e.win + 0.5f * e.draw;
+			const int vloss = e.vloss_flag & 0x7FFF;
+			switch (p.final_selector)
+			{
+				default:
+				case AGB_FINAL_MAX_VISIT:
+					return static_cast<float>(e.visits);
+				case AGB_FINAL_MIN_VISIT:
+					return static_cast<float>(-e.visits);
+				case AGB_FINAL_MAX_POLICY:
+					return e.prior;
+				case AGB_FINAL_MAX_VALUE:
+					if (proven == score::LOSS)
+						return -1000.0f + distance;
+					if (proven == score::DRAW)
+						return 0.5f;
+					if (proven == score::WIN)
+						return +1000.0f - distance;
+					return expectation;
+				case AGB_FINAL_BEST:
+					if (proven == score::LOSS)
+						return -1.0e8f + distance;
+					if (proven == score::WIN)
+						return +1.0e8f - distance;
+					return static_cast<float>(e.visits) + expectation * static_cast<float>(parent.visits) + 0.001f * e.prior;
+				case AGB_FINAL_LCB:
+				{
+					if (proven == score::LOSS)
+						return -1.0e6f + distance + e.prior;
+					if (proven == score::WIN)
+						return +1.0e6f - distance + e.prior;
+					const float q = (e.visits > 0) ? expectation : (parent.win + 0.5f * parent.draw);
+					const float u = p.final_exploration * sqrtf(parent_log_visit / (1.0f + static_cast<float>(e.visits) + static_cast<float>(vloss)));
+					const float visits = 1.0e-8f + static_cast<float>(e.visits); // getVirtualLoss(edge), EdgeSelector.cpp:26-31
+					return q * (visits / (visits + static_cast<float>(vloss))) - u;
+				}
+			}
+		}
+
 		// ---- per-ply driver: final move, record, game end, subtree reuse ------------------------------------------------------
 		__global__ void __launch_bounds__(128) make_move_kernel(const __grid_constant__ Params p)
 		{
@@ -1029,12 +1075,13 @@ namespace agb
 			const int simulations = static_cast<int>(p.max_simulations - reduction * (p.max_simulations - 50));
 			if (not (R.visits > simulations or score::is_proven(R.score)))
 				return;
-			// final selector "max_visit": first edge with the most visits (EdgeSelector.cpp:1403-1406)
+			// final selector: the first edge with the largest value (find_best_edge_impl, EdgeSelector.cpp:561-586)
+			const float parent_log_visit = static_cast<float>(log(static_cast<double>(R.visits + R.vloss)));
 			float best_v = -FLT_MAX;
 			int best_i = 0x7FFFFFFF;
 			for (int i = lane; i < R.n_edges; i += 32)
 			{
-				const float v = static_cast<float>(edges[R.edge_begin + i].visits);
+				const float v = final_selector_value(p, edges[R.edge_begin + i], R, parent_log_visit);
 				if (v > best_v)
 				{
 					best_v = v;
@@ -1361,6 +1408,8 @@ namespace agb
 			p.eval_count = e->selfplay->eval_count;
 			p.use_symmetries = e->cfg.use_symmetries != 0;
 			p.max_children = e->cfg.max_children > 0 ? e->cfg.max_children : 0;
+			p.final_selector = e->cfg.final_selector;
+			p.final_exploration = e->cfg.final_exploration_constant;
 			p.expansion_threshold = e->cfg.policy_expansion_threshold;
 			p.first_game_id = e->cfg.first_game_id;
 			p.sym_seed = e->cfg.seed * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull;

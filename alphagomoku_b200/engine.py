@@ -60,7 +60,8 @@ class Engine:
     def __init__(self, game: GameConfig, max_boards=1024, device=0, blocks=0, filters=0, q_head=False, games=0, max_batch_size=1,
                  max_simulations=400, max_nodes_per_game=0, max_edges_per_game=0, init_to="parent", exploration_constant=1.25,
                  information_leak_threshold=0.01, policy_expansion_threshold=1.0e-4, max_children=0, solver_max_positions=0,
-                 use_symmetries=False, seed=0, first_game_id=0, solver_table_entries=0, pipeline_groups=0):
+                 use_symmetries=False, seed=0, first_game_id=0, solver_table_entries=0, pipeline_groups=0, final_selector="max_visit",
+                 final_exploration_constant=1.25):
         self._lib = _lib.load()
         self.game = game
         self.cells = game.rows * game.cols
@@ -78,6 +79,8 @@ class Engine:
         cfg.use_symmetries, cfg.seed, cfg.first_game_id = int(use_symmetries), seed, first_game_id
         cfg.solver_table_entries = solver_table_entries
         cfg.pipeline_groups = pipeline_groups
+        cfg.final_selector = {"max_visit": 0, "best": 1, "max_value": 2, "max_policy": 3, "min_visit": 4, "lcb": 5}[final_selector]
+        cfg.final_exploration_constant = final_exploration_constant
         self.config = cfg
         self.max_boards = max_boards
         handle = ctypes.c_void_p()

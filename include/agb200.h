@@ -54,6 +54,12 @@ enum
 
 typedef struct AgbEngine AgbEngine;
 
+/* final move selectors of the self-play loop */
+enum
+{
+	AGB_FINAL_MAX_VISIT = 0, AGB_FINAL_BEST = 1, AGB_FINAL_MAX_VALUE = 2, AGB_FINAL_MAX_POLICY = 3, AGB_FINAL_MIN_VISIT = 4, AGB_FINAL_LCB = 5
+};
+
 /* GameConfig + the parts of SelfplayConfig / SearchConfig the device engine honours
  * (include/alphagomoku/utils/configs.hpp:23-255). */
 typedef struct AgbConfig
@@ -85,7 +91,9 @@ typedef struct AgbConfig
 	                                 AlphaBetaSearch.cpp:55) */
 	int32_t pipeline_groups; /* 1: all games advance together; 2..4: that many groups of games on their own streams, so that one group's solver and tree
 	                            kernels can overlap another group's network kernel; 0 = 1. Per-game results do not depend on it */
-	int32_t reserved[5];
+	int32_t final_selector; /* SelfplayConfig::final_selector.policy: AGB_FINAL_* (EdgeSelector::create, EdgeSelector.cpp:680-711) */
+	float final_exploration_constant; /* its exploration_constant (used by AGB_FINAL_LCB) */
+	int32_t reserved[3];
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */

@@ -52,7 +52,13 @@ def test_lockstep_engine_with_policy_pruning(ref, rules, q_head, solver, max_chi
     _run_case(ref, rules, q_head, "parent", 4, 60, solver, max_children=max_children, threshold=threshold)
 
 
-def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_children=0, threshold=1.0e-4):
+@pytest.mark.parametrize("selector,rules,solver", [("best", 0, 0), ("max_value", 1, 20), ("lcb", 0, 1), ("max_policy", 4, 0), ("min_visit", 0, 0)])
+def test_lockstep_engine_final_selectors(ref, selector, rules, solver):
+    """SelfplayConfig::final_selector: the move actually played is chosen by another EdgeSelector (EdgeSelector.cpp:426-536, 680-711)."""
+    _run_case(ref, rules, True, "parent", 4, 60, solver, final_selector=selector)
+
+
+def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_children=0, threshold=1.0e-4, final_selector="max_visit"):
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import refapi
@@ -63,7 +69,7 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_chi
     eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
                      games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver,
                      solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0, pipeline_groups=2 if solver > 0 else 1, max_children=max_children,
-                     policy_expansion_threshold=threshold)  # the reference's table size (AlphaBetaSearch.cpp:55)
+                     policy_expansion_threshold=threshold, final_selector=final_selector)  # the reference's table size (AlphaBetaSearch.cpp:55)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
     def evaluate(features):
@@ -78,7 +84,7 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_chi
     for g in range(games):
         r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=solver > 0,
                                 solver_max_positions=max(solver, 1), draw_after=draw_after, fast=fast, max_children=max_children,
-                                policy_expansion_threshold=threshold)
+                                policy_expansion_threshold=threshold, final_selector=final_selector)
         refs.append(r)
     if solver > 0:
         eng.set_solver_keys(np.stack([r.solver_keys() for r in refs]))
