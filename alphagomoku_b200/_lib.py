@@ -21,7 +21,7 @@ class AgbConfig(ctypes.Structure):
         ("solver_max_positions", ctypes.c_int32), ("use_symmetries", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("solver_table_entries", ctypes.c_int32),
         ("pipeline_groups", ctypes.c_int32), ("final_selector", ctypes.c_int32), ("final_exploration_constant", ctypes.c_float),
-        ("reserved", ctypes.c_int32 * 3),
+        ("noise_type", ctypes.c_int32), ("noise_weight", ctypes.c_float), ("reserved", ctypes.c_int32 * 1),
     ]
 
 
@@ -70,6 +70,7 @@ SYMBOLS = {
     "agb_pop_finished": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I)]),
     "agb_get_stats": (_I, [_VP, ctypes.POINTER(AgbStats)]),
     "agb_get_root": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "agb_get_root_noise": (_I, [_VP, _I, _VP]),
     "agb_get_board": (_I, [_VP, _I, _VP, _VP, _VP]),
     "agb_synchronize": (_I, [_VP]),
     "agb_stream": (_VP, [_VP]),

@@ -160,6 +160,10 @@ namespace agb
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
 			// SelfplayConfig::use_symmetries: every evaluation goes through a random board symmetry (NNEvaluator.cpp:134-146, 244-286)
+			// EdgeSelectorConfig::noise_type / noise_weight: the root's priors as the tree selector sees them (PUCTSelector::noisy_policy)
+			float *root_noise = nullptr; // [games][cells], indexed by the root's edge index
+			uint8_t *noise_ready = nullptr; // [games] drawn for the current search
+			uint32_t *noise_counter = nullptr; // [games] searches drawn so far
 			int8_t *task_sym = nullptr; // [games*batch] symmetry of the slot's evaluation
 			uint32_t *sym_counter = nullptr; // [games] evaluations drawn so far (the random stream is keyed by the global game id)
 			uint32_t *features_aug = nullptr; // [games*batch][cells] augmented feature words
@@ -206,6 +210,8 @@ namespace agb
 				int use_symmetries, first_game_id;
 				int max_children; // MCTSConfig::max_children (0: unlimited)
 				int final_selector; // SelfplayConfig::final_selector.policy (AGB_FINAL_*)
+				int noise_type; // AGB_NOISE_*
+				float noise_weight;
 				float final_exploration; // its exploration_constant (lcb)
 				float expansion_threshold; // MCTSConfig::policy_expansion_threshold
 				unsigned long long sym_seed;
@@ -314,6 +320,89 @@ namespace agb
 			}
 		}
 
+		// ---- root noise (EdgeSelector.cpp:602-623, random.cpp:89-123). The reference draws from a thread-local std::mt19937; here a counter-based
+		// stream keyed by (seed, global game id, search number) gives the same distributions independently of how games are sharded. ----
+		__device__ inline float noise_uniform(unsigned long long key, unsigned int index)
+		{ // (0, 1)
+			unsigned long long z = key + 0x9E3779B97F4A7C15ull * (index + 1ull);
+			z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+			z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+			z ^= z >> 31;
+			return (static_cast<float>(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+		}
+		__device__ void draw_root_noise(const Params &p, int g, const NodeD &root, const EdgeD *edges)
+		{ // single thread; fills p.s.root_noise[g][0 .. n_edges) with PUCTSelector::noisy_policy
+			float *noisy = p.s.root_noise + static_cast<size_t>(g) * p.s.cells;
+			const int n = root.n_edges;
+			const float w = p.noise_weight;
+			const unsigned long long key = (p.sym_seed ^ 0x6E6F697365ull) + (static_cast<unsigned long long>(p.first_game_id + g) << 32) + p.s.noise_counter[g]++;
+			unsigned int draw = 0;
+			if (p.noise_type == AGB_NOISE_CUSTOM)
+			{ // createCustomNoise: u^4 of what is left, then a uniform shuffle
+				float sum = 0.0f;
+				for (int i = 0; i < n; i++)
+				{
+					const float u = noise_uniform(key, draw++);
+					noisy[i] = static_cast<float>(pow(static_cast<double>(u), 4.0) * (1.0f - sum));
+					sum += noisy[i];
+				}
+				for (int i = n - 1; i > 0; i--)
+				{ // Fisher-Yates
+					const int j = min(i, static_cast<int>(noise_uniform(key, draw++) * (i + 1)));
+					const float t = noisy[i];
+					noisy[i] = noisy[j];
+					noisy[j] = t;
+				}
+				for (int i = 0; i < n; i++)
+					noisy[i] = (1.0f - w) * edges[root.edge_begin + i].prior + w * noisy[i];
+			}
+			else if (p.noise_type == AGB_NOISE_DIRICHLET)
+			{ // createDirichletNoise(size, 0.05): normalised gamma(0.05) draws (Marsaglia-Tsang on shape + 1, boosted by u^(1/shape))
+				const double shape = 0.05, d = shape + 1.0 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+				float sum = 0.0f;
+				for (int i = 0; i < n; i++)
+				{
+					double sample = 0.0;
+					for (int attempt = 0; attempt < 64; attempt++)
+					{
+						const double u1 = noise_uniform(key, draw++), u2 = noise_uniform(key, draw++), u3 = noise_uniform(key, draw++);
+						const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); // standard normal
+						const double v = (1.0 + c * x) * (1.0 + c * x) * (1.0 + c * x);
+						if (v > 0.0 and log(u3) < 0.5 * x * x + d - d * v + d * log(v))
+						{
+							sample = d * v;
+							break;
+						}
+					}
+					sample *= pow(static_cast<double>(noise_uniform(key, draw++)), 1.0 / shape);
+					noisy[i] = static_cast<float>(sample);
+					sum += noisy[i];
+				}
+				const float inv = (sum > 0.0f) ? 1.0f / sum : 0.0f;
+				for (int i = 0; i < n; i++)
+					noisy[i] = (1.0f - w) * edges[root.edge_begin + i].prior + w * (sum > 0.0f ? noisy[i] * inv : 1.0f / n);
+			}
+			else
+			{ // gumbel: softmax(log_eps(prior) + w * g), g = -log_eps(-log_eps(u))
+				const float eps = 1.1920929e-07f;
+				float m = -FLT_MAX;
+				for (int i = 0; i < n; i++)
+				{
+					const float gum = -logf(eps - logf(eps + noise_uniform(key, draw++)));
+					noisy[i] = logf(eps + edges[root.edge_begin + i].prior) + w * gum;
+					m = fmaxf(m, noisy[i]);
+				}
+				float sum = 0.0f;
+				for (int i = 0; i < n; i++)
+				{
+					noisy[i] = expf(noisy[i] - m);
+					sum += noisy[i];
+				}
+				for (int i = 0; i < n; i++)
+					noisy[i] /= sum;
+			}
+		}
+
 		// ---- K6: select ------------------------------------------------------------------------------------------------
 		__global__ void __launch_bounds__(128) select_kernel(const __grid_constant__ Params p)
 		{
@@ -361,12 +450,25 @@ namespace agb
 						initial_q = expectation(N.win, N.draw);
 					else if (p.init_to == 2)
 						initial_q = 0.5f;
+					// root noise: drawn once per search, then used instead of the priors at the root (PUCTSelector::select)
+					const bool use_noise = p.noise_type != 0 and (N.flags & 1) != 0;
+					const float *noisy = p.s.root_noise + static_cast<size_t>(g) * cells;
+					if (use_noise)
+					{
+						if (lane == 0 and p.s.noise_ready[g] == 0)
+						{
+							draw_root_noise(p, g, N, edges);
+							p.s.noise_ready[g] = 1;
+						}
+						__syncwarp();
+					}
 					float best_v = -FLT_MAX;
 					int best_i = 0x7FFFFFFF;
 					for (int i = lane; i < N.n_edges; i += 32)
 					{
 						const EdgeD e = edges[N.edge_begin + i];
 						const int vl = e.vloss_flag & 0x7FFF;
+						const float prior = use_noise ? noisy[i] : e.prior;
 						float v;
 						switch (score::is_proven(e.score) ? score::pv(e.score) : static_cast<int>(score::UNKNOWN))
 						{
@@ -390,7 +492,7 @@ namespace agb
 									Q = expectation(e.win, e.draw) * vloss_scale;
 								else
 									Q = initial_q;
-								const float U = e.prior * psv / (1.0f + e.visits + vl);
+								const float U = prior * psv / (1.0f + e.visits + vl);
 								v = Q + U;
 								break;
 							}
@@ -1262,6 +1364,8 @@ namespace agb
 					p.s.n_edges[g] = 0;
 					p.s.rec_len[g] = 4;
 					p.s.rec_samples[g] = 0;
+					if (p.s.noise_ready != nullptr)
+						p.s.noise_ready[g] = 0;
 					if (p.solver_mode != 0)
 						p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64;
 				}
@@ -1270,6 +1374,8 @@ namespace agb
 					table[i] = -1;
 				return;
 			}
+			if (lane == 0 and p.s.noise_ready != nullptr)
+				p.s.noise_ready[g] = 0; // prepare_search makes a new EdgeSelector: the next search draws new noise
 			// prepare_search -> Search::setBoard: the solver's table enters a new generation
 			if (lane == 0 and p.solver_mode != 0)
 				p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64;
@@ -1373,6 +1479,8 @@ namespace agb
 			p.s.n_edges[g] = 0;
 			p.s.n_stored[g] = 0;
 			p.s.outcome[g] = 0;
+			if (p.s.noise_ready != nullptr)
+				p.s.noise_ready[g] = 0;
 			if (not keep_history)
 			{
 				p.s.n_moves[g] = opening_moves(p.s.root_board + static_cast<size_t>(g) * cells, cells, p.s.S, p.s.moves + static_cast<size_t>(g) * cells);
@@ -1409,6 +1517,8 @@ namespace agb
 			p.use_symmetries = e->cfg.use_symmetries != 0;
 			p.max_children = e->cfg.max_children > 0 ? e->cfg.max_children : 0;
 			p.final_selector = e->cfg.final_selector;
+			p.noise_type = (e->cfg.noise_weight > 0.0f) ? e->cfg.noise_type : 0;
+			p.noise_weight = e->cfg.noise_weight;
 			p.final_exploration = e->cfg.final_exploration_constant;
 			p.expansion_threshold = e->cfg.policy_expansion_threshold;
 			p.first_game_id = e->cfg.first_game_id;
@@ -1482,6 +1592,12 @@ namespace agb
 		alloc(&s->policy, T * cells);
 		alloc(&s->value, T * 3);
 		alloc(&s->q, T * cells * 3);
+		if (c.noise_type != 0 and c.noise_weight > 0.0f)
+		{
+			alloc(&s->root_noise, G * cells);
+			alloc(&s->noise_ready, G);
+			alloc(&s->noise_counter, G);
+		}
 		if (c.use_symmetries)
 		{
 			alloc(&s->task_sym, T);
@@ -1551,7 +1667,7 @@ namespace agb
 			return;
 		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
-				s->value, s->q, s->task_sym, s->sym_counter, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
+				s->value, s->q, s->root_noise, s->noise_ready, s->noise_counter, s->task_sym, s->sym_counter, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
 				s->sample_root, s->sample_draw, s->sample_score, s->slot_is_root, s->nn_list, s->nn_count, s->solver_out.moves, s->solver_out.scores,
 				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->solver_out.nodes, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
@@ -1609,6 +1725,8 @@ extern "C"
 			s->n_openings = 0;
 		}
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
+		if (s->noise_counter != nullptr)
+			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->noise_counter, 0, G * sizeof(uint32_t), e->stream));
 		if (s->sym_counter != nullptr)
 		{
 			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->sym_counter, 0, G * sizeof(uint32_t), e->stream));
@@ -2000,6 +2118,32 @@ extern "C"
 		}
 		if (root_visits)
 			*root_visits = node.visits;
+		return AGB_OK;
+	}
+	int agb_get_root_noise(AgbEngine *e, int game, float *noisy_policy_host)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or game < 0 or game >= s->games or noisy_policy_host == nullptr)
+			return e->fail(AGB_EINVAL, "bad game index or null pointer");
+		if (s->root_noise == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without root noise");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		const int cells = s->cells;
+		std::memset(noisy_policy_host, 0, cells * sizeof(float));
+		int32_t root = -1;
+		uint8_t ready = 0;
+		AGB_CUDA_CHECK(e, cudaMemcpy(&root, s->root_node + game, 4, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(&ready, s->noise_ready + game, 1, cudaMemcpyDeviceToHost));
+		if (root < 0 or not ready)
+			return AGB_OK;
+		NodeD node;
+		AGB_CUDA_CHECK(e, cudaMemcpy(&node, s->nodes + static_cast<size_t>(game) * s->max_nodes + root, sizeof(NodeD), cudaMemcpyDeviceToHost));
+		std::vector<EdgeD> edges(node.n_edges);
+		std::vector<float> noisy(node.n_edges);
+		AGB_CUDA_CHECK(e, cudaMemcpy(edges.data(), s->edges + static_cast<size_t>(game) * s->max_edges + node.edge_begin, sizeof(EdgeD) * node.n_edges, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(noisy.data(), s->root_noise + static_cast<size_t>(game) * cells, sizeof(float) * node.n_edges, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < node.n_edges; i++)
+			noisy_policy_host[((edges[i].move >> 2) & 127) * s->S + ((edges[i].move >> 9) & 127)] = noisy[i];
 		return AGB_OK;
 	}
 	int agb_get_board(AgbEngine *e, int game, int8_t *board_host, int8_t *sign_to_move, int32_t *move_number)

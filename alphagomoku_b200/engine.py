@@ -61,7 +61,7 @@ class Engine:
                  max_simulations=400, max_nodes_per_game=0, max_edges_per_game=0, init_to="parent", exploration_constant=1.25,
                  information_leak_threshold=0.01, policy_expansion_threshold=1.0e-4, max_children=0, solver_max_positions=0,
                  use_symmetries=False, seed=0, first_game_id=0, solver_table_entries=0, pipeline_groups=0, final_selector="max_visit",
-                 final_exploration_constant=1.25):
+                 final_exploration_constant=1.25, noise_type="none", noise_weight=0.0):
         self._lib = _lib.load()
         self.game = game
         self.cells = game.rows * game.cols
@@ -81,6 +81,8 @@ class Engine:
         cfg.pipeline_groups = pipeline_groups
         cfg.final_selector = {"max_visit": 0, "best": 1, "max_value": 2, "max_policy": 3, "min_visit": 4, "lcb": 5}[final_selector]
         cfg.final_exploration_constant = final_exploration_constant
+        cfg.noise_type = {"none": 0, "custom": 1, "dirichlet": 2, "gumbel": 3}[noise_type]
+        cfg.noise_weight = noise_weight
         self.config = cfg
         self.max_boards = max_boards
         handle = ctypes.c_void_p()
@@ -258,6 +260,12 @@ class Engine:
         rv = ctypes.c_int32(0)
         self._check(self._lib.agb_get_root(self._h, game, _ptr(visits), _ptr(priors), _ptr(q), _ptr(value), ctypes.byref(rv)))
         return visits, priors, q, value, rv.value
+
+    def get_root_noise(self, game):
+        """PUCTSelector::noisy_policy of game's current search, per cell (zeros before it is drawn)."""
+        out = np.zeros(self.cells, np.float32)
+        self._check(self._lib.agb_get_root_noise(self._h, game, _ptr(out)))
+        return out
 
     def get_board(self, game):
         board = np.zeros(self.cells, np.int8)

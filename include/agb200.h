@@ -54,6 +54,12 @@ enum
 
 typedef struct AgbEngine AgbEngine;
 
+/* root noise of the tree selector */
+enum
+{
+	AGB_NOISE_NONE = 0, AGB_NOISE_CUSTOM = 1, AGB_NOISE_DIRICHLET = 2, AGB_NOISE_GUMBEL = 3
+};
+
 /* final move selectors of the self-play loop */
 enum
 {
@@ -93,7 +99,9 @@ typedef struct AgbConfig
 	                            kernels can overlap another group's network kernel; 0 = 1. Per-game results do not depend on it */
 	int32_t final_selector; /* SelfplayConfig::final_selector.policy: AGB_FINAL_* (EdgeSelector::create, EdgeSelector.cpp:680-711) */
 	float final_exploration_constant; /* its exploration_constant (used by AGB_FINAL_LCB) */
-	int32_t reserved[3];
+	int32_t noise_type; /* EdgeSelectorConfig::noise_type of the tree selector: AGB_NOISE_* (applied at the root, EdgeSelector.cpp:1127-1137) */
+	float noise_weight; /* EdgeSelectorConfig::noise_weight; 0 = no noise */
+	int32_t reserved[1];
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -219,6 +227,9 @@ int agb_get_stats(AgbEngine *engine, AgbStats *stats);
 int agb_get_root(AgbEngine *engine, int game, int32_t *visits_host, float *priors_host, float *q_host, float *root_value3_host,
 		int32_t *root_visits);
 int agb_get_board(AgbEngine *engine, int game, int8_t *board_host, int8_t *sign_to_move, int32_t *move_number);
+/* the root priors as the tree selector currently sees them (PUCTSelector::noisy_policy), noisy_policy[cells]; zeros until the search
+ * of the current move has drawn its noise */
+int agb_get_root_noise(AgbEngine *engine, int game, float *noisy_policy_host);
 
 int agb_synchronize(AgbEngine *engine);
 /* CUDA stream (cudaStream_t) the engine launches on, for callers that time with events */

@@ -220,3 +220,56 @@ def test_save_and_resume_games_in_flight():
         assert len(dataset.parse_record(rec)["moves"]) >= 1
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("noise_type", ["custom", "dirichlet", "gumbel"])
+def test_root_noise(noise_type):
+    """EdgeSelectorConfig::noise_type / noise_weight (EdgeSelector.cpp:602-623, 1127-1137; random.cpp:89-123): the root's priors are
+    mixed with noise drawn once per search. The random stream differs from the reference's thread-local mt19937 by design (keyed by seed
+    and global game id), so the checks are on what the mixture must look like, on determinism and on shard invariance."""
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob
+    size, games, blocks, filters, w = 15, 32, 2, 64, 0.25
+    blob = netblob.pack(netblob.random_tensors(size, size, blocks, filters, False, seed=2), size, size, blocks, filters, False)
+    rng = np.random.default_rng(8)
+    boards, stm = _openings(rng, size, games)
+
+    def make(n_games, first, weight=w):
+        eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD, size, size), max_boards=n_games * 4, blocks=blocks, filters=filters, games=n_games,
+                         max_batch_size=4, max_simulations=80, noise_type=noise_type, noise_weight=weight, seed=31, first_game_id=first)
+        eng.load_weights(blob)
+        eng.selfplay_reset(boards[first:first + n_games], stm[first:first + n_games])
+        return eng
+
+    eng = make(games, 0)
+    eng.step(3)  # the root is expanded in step 1; step 2 selects at the root for the first time and draws the noise
+    mixtures, top5, sizeable = [], [], []
+    for g in range(games):
+        _, priors, _, _, visits = eng.get_root(g)
+        noisy = eng.get_root_noise(g)
+        legal = boards[g] == 0
+        assert visits > 1 and (noisy[~legal] == 0).all() and (noisy[legal] >= 0).all()
+        if noise_type == "gumbel":
+            assert abs(float(noisy.sum()) - 1.0) < 1e-4
+        else:
+            noise = (noisy - (1.0 - w) * priors) / w  # what was mixed in
+            assert (noise[legal] > -1e-6).all()
+            total = float(noise[legal].sum())
+            assert (abs(total - 1.0) < 1e-3) if noise_type == "dirichlet" else (0.3 < total <= 1.0 + 1e-4), total
+            if noise_type == "dirichlet":
+                top5.append(float(np.sort(noise[legal])[-5:].sum()))
+                sizeable.append(int((noise[legal] > 0.01).sum()))
+        assert np.abs(noisy - priors).max() > 1e-4
+        mixtures.append(noisy)
+    assert len({m.tobytes() for m in mixtures}) == games  # every game has its own draw
+    if noise_type == "dirichlet":  # Dirichlet(0.05) over ~215 moves (numpy: top-5 share median 0.55, ~19 components above 0.01)
+        assert 0.42 < np.median(top5) < 0.68 and 12 <= np.median(sizeable) <= 27, (np.median(top5), np.median(sizeable))
+    eng.step(30)
+    shard = make(8, 16)
+    shard.step(33)
+    for g in range(8):
+        a, b = eng.get_root(16 + g), shard.get_root(g)
+        assert (a[0] == b[0]).all() and a[4] == b[4], g
+        assert (eng.get_root_noise(16 + g) == shard.get_root_noise(g)).all()
+    eng.close()
+    shard.close()
