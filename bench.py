@@ -164,6 +164,20 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def reference_integer_path(seconds=1.0):
+    """rates of the pure reference code on ONE host core (no network involved)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refapi
+    ref = refapi.RefOracle(fast=True)
+    rng = np.random.default_rng(0)
+    boards, _ = random_openings(rng, 256)
+    rates = np.zeros(3)
+    ref.lib.agref_bench_integer_path.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+    ref.lib.agref_bench_integer_path(RULES, SIZE, SIZE, refapi._p(boards), 256, seconds, 100, refapi._p(rates))
+    return {"set_board_and_encode_per_s": float(rates[0]), "add_undo_pairs_per_s": float(rates[1]), "solve_100_positions_per_s": float(rates[2]),
+            "cores": 1, "note": "oracle/_ref (reference sources, -O3 -DNDEBUG), opening positions of this bench"}
+
+
 # ---- our arm -------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -255,6 +269,24 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    # device rates of the integer path alone (no network): K1+K3 on the e2e boards, K5 from the solver kernel's event times
+    d_boards, d_stm = torch.from_numpy(np.repeat(boards, args.batch, axis=0)).cuda(), torch.from_numpy(np.repeat(stm, args.batch)).cuda()
+    d_feat = torch.empty((n_e2e, SIZE * SIZE), dtype=torch.int32, device="cuda")
+
+    def k1():
+        assert lib.agb_set_boards_dev(eng._h, ctypes.c_void_p(d_boards.data_ptr()), ctypes.c_void_p(d_stm.data_ptr()), n_e2e, ctypes.c_void_p(d_feat.data_ptr())) == 0
+
+    k1()
+    k1_start, k1_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1_start.record(stream)
+    for _ in range(5):
+        k1()
+    k1_end.record(stream)
+    k1_end.synchronize()
+    solver_ns = st1["solver_kernel_ns"] - st0["solver_kernel_ns"]
+    device_integer_path = {"set_board_and_encode_per_s": 5 * n_e2e / (k1_start.elapsed_time(k1_end) * 1e-3),
+                           "solve_100_positions_per_s": ((st1["nb_node_count"] - st0["nb_node_count"]) / (solver_ns * 1e-9)) if solver_ns else None,
+                           "note": "one GPU; leaf positions solved per second of K5 kernel time, K1+K3 on 32 k boards per launch"}
     # C2 (outside the timed regions): finished-game records of every rank, all-gathered like the reference's shared GameDataBuffer
     records, n_finished = eng.pop_finished()
     gathered = sharding.gather_records(records)
@@ -292,7 +324,8 @@ def main():
             v, cores, _ = run_reference(args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                                     "sample": f"{args.cpu_seconds:.0f} s of reference self-play on the host cores (oracle/_ref Tree/Search/AlphaBetaSearch, "
-                                              f"8 games x batch 8 per core, solver on; NN = torch-CPU fp32 stand-in for MinML)"}
+                                              f"8 games x batch 8 per core, solver on; NN = torch-CPU fp32 stand-in for MinML)",
+                                    "integer_path_one_core": reference_integer_path(), "integer_path_device": device_integer_path}
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -427,4 +427,67 @@ extern "C"
 		*flags = static_cast<int>(list.must_defend) | (static_cast<int>(list.has_initiative) << 1);
 		return list.size();
 	}
+	// Integer-path rates of the pure reference code on one host core: setBoard + encode per second, addMove +
+	// undoMove pairs per second, AlphaBetaSearch::solve(max_nodes) per second, each over the given boards for about `seconds` seconds.
+	void agref_bench_integer_path(int rules, int rows, int cols, const int8_t *boards, int n_boards, double seconds, int max_nodes, double *rates)
+	{
+		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
+		const int cells = rows * cols;
+		std::vector<matrix<Sign>> bs;
+		std::vector<Sign> stm;
+		std::vector<Move> moves;
+		for (int i = 0; i < n_boards; i++)
+		{
+			matrix<Sign> b(rows, cols);
+			int stones = 0, first_empty = -1;
+			for (int j = 0; j < cells; j++)
+			{
+				b[j] = static_cast<Sign>(boards[static_cast<size_t>(i) * cells + j]);
+				stones += (b[j] != Sign::NONE);
+				if (b[j] == Sign::NONE and first_empty < 0 and j >= cells / 3)
+					first_empty = j;
+			}
+			bs.push_back(b);
+			stm.push_back((stones % 2 == 0) ? Sign::CROSS : Sign::CIRCLE);
+			moves.push_back(Move(first_empty / cols, first_empty % cols, stm.back()));
+		}
+		PatternCalculator calc(gc);
+		NNInputFeatures features(rows, cols);
+		double t0 = getTime();
+		long count = 0;
+		while (getTime() - t0 < seconds)
+			for (int i = 0; i < n_boards; i++, count++)
+			{
+				calc.setBoard(bs[i], stm[i]);
+				features.encode(calc);
+			}
+		rates[0] = count / (getTime() - t0);
+		t0 = getTime();
+		count = 0;
+		while (getTime() - t0 < seconds)
+			for (int i = 0; i < n_boards; i++)
+			{
+				calc.setBoard(bs[i], stm[i]); // inside the timed region: one per 200 pairs
+				for (int k = 0; k < 200; k++, count++)
+				{
+					calc.addMove(moves[i]);
+					calc.undoMove(moves[i]);
+				}
+			}
+		rates[1] = count / (getTime() - t0);
+		AlphaBetaSearch solver(gc);
+		solver.setDepthLimit(100);
+		solver.setNodeLimit(max_nodes);
+		solver.setTimeLimit(std::numeric_limits<double>::max());
+		t0 = getTime();
+		count = 0;
+		while (getTime() - t0 < seconds)
+			for (int i = 0; i < n_boards and getTime() - t0 < seconds; i++, count++)
+			{
+				SearchTask task(gc);
+				task.set(bs[i], stm[i]);
+				solver.solve(task);
+			}
+		rates[2] = count / (getTime() - t0);
+	}
 }
