@@ -62,6 +62,7 @@ SYMBOLS = {
     "agb_prepare_opening": (_I, [_VP, _I, _VP, _VP]),
     "agb_generate_openings": (_I, [_VP, _I, _VP, _VP]),
     "agb_selfplay_reset": (_I, [_VP, _VP, _VP]),
+    "agb_think": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I]),
     "agb_save_games": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "agb_load_games": (_I, [_VP, _VP, ctypes.c_size_t]),
     "agb_set_solver_keys": (_I, [_VP, _VP, ctypes.c_size_t]),

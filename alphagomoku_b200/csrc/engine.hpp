@@ -47,6 +47,7 @@ struct AgbEngine
 		agb::SolveScratch *solve_scratch = nullptr; // agb_solve: solver memory for positions outside the lockstep engine
 		std::vector<uint64_t> solver_keys_host; // Zobrist words given through agb_set_solver_keys (applied to every solver state)
 		void *opening_rng = nullptr; // std::mt19937 of the opening generator (openings.cu)
+		bool think_mode = false; // agb_think in progress: games stop at their decision
 
 		int fail(int code, const std::string &msg)
 		{

@@ -161,6 +161,9 @@ namespace agb
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
 			// SelfplayConfig::use_symmetries: every evaluation goes through a random board symmetry (NNEvaluator.cpp:134-146, 244-286)
 			// EdgeSelectorConfig::noise_type / noise_weight: the root's priors as the tree selector sees them (PUCTSelector::noisy_policy)
+			// agb_think: games search one move and then wait for the host (evaluation games between two engines, Player::getMove)
+			uint8_t *paused = nullptr; // [games] 1: this game takes no part in the lockstep iterations
+			uint16_t *decision = nullptr; // [games] the move chosen by the last search (Move::toShort), 0 = none yet
 			float *root_noise = nullptr; // [games][cells], indexed by the root's edge index
 			uint8_t *noise_ready = nullptr; // [games] drawn for the current search
 			uint32_t *noise_counter = nullptr; // [games] searches drawn so far
@@ -210,6 +213,7 @@ namespace agb
 				int use_symmetries, first_game_id;
 				int max_children; // MCTSConfig::max_children (0: unlimited)
 				int final_selector; // SelfplayConfig::final_selector.policy (AGB_FINAL_*)
+				int single_move; // agb_think: a game stops at its decision instead of playing on
 				int noise_type; // AGB_NOISE_*
 				float noise_weight;
 				float final_exploration; // its exploration_constant (lcb)
@@ -414,6 +418,16 @@ namespace agb
 			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
 			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
 			TaskD *tasks = p.s.tasks + static_cast<size_t>(g) * p.s.batch;
+			if (p.s.paused[g])
+			{ // waiting for the host (agb_think): no tasks, nothing to solve or evaluate
+				if (lane == 0)
+				{
+					p.s.n_stored[g] = 0;
+					if (p.solver_mode != 0)
+						p.s.solver.game_slot_count[g] = 0;
+				}
+				return;
+			}
 			const int root = p.s.root_node[g];
 			const int root_visits = (root >= 0) ? nodes[root].visits : 0;
 			int stored = 0;
@@ -1169,7 +1183,7 @@ namespace agb
 			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
 			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
 			const int root = p.s.root_node[g];
-			if (root < 0)
+			if (root < 0 or p.s.paused[g])
 				return;
 			const NodeD R = nodes[root];
 			// GameGenerator.cpp:95-101: fewer simulations when the root is drawish
@@ -1201,6 +1215,19 @@ namespace agb
 				}
 			}
 			const EdgeD chosen = edges[R.edge_begin + best_i];
+			if (p.single_move)
+			{ // Player::getMove: report the move and the root's value, leave the position to the host
+				if (lane == 0)
+				{
+					p.s.decision[g] = chosen.move;
+					p.s.sample_root[g * 4 + 0] = R.win;
+					p.s.sample_root[g * 4 + 1] = R.draw;
+					p.s.sample_root[g * 4 + 2] = static_cast<float>(R.visits);
+					p.s.sample_root[g * 4 + 3] = static_cast<float>(chosen.move);
+					p.s.paused[g] = 1;
+				}
+				return;
+			}
 			// SearchDataPack(rootNode, board) (dataset/data_packs.cpp:24-43), kept dense for the record writer
 			for (int i = lane; i < cells; i += 32)
 			{
@@ -1516,6 +1543,7 @@ namespace agb
 			p.eval_count = e->selfplay->eval_count;
 			p.use_symmetries = e->cfg.use_symmetries != 0;
 			p.max_children = e->cfg.max_children > 0 ? e->cfg.max_children : 0;
+			p.single_move = e->think_mode ? 1 : 0;
 			p.final_selector = e->cfg.final_selector;
 			p.noise_type = (e->cfg.noise_weight > 0.0f) ? e->cfg.noise_type : 0;
 			p.noise_weight = e->cfg.noise_weight;
@@ -1592,6 +1620,8 @@ namespace agb
 		alloc(&s->policy, T * cells);
 		alloc(&s->value, T * 3);
 		alloc(&s->q, T * cells * 3);
+		alloc(&s->paused, G);
+		alloc(&s->decision, G);
 		if (c.noise_type != 0 and c.noise_weight > 0.0f)
 		{
 			alloc(&s->root_noise, G * cells);
@@ -1655,6 +1685,8 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->zobrist, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->opening_cursor, 0, 4, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->paused, 0, G, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->decision, 0, G * sizeof(uint16_t), e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_used, 0, 8, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_games, 0, 4, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
@@ -1667,7 +1699,7 @@ namespace agb
 			return;
 		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
-				s->value, s->q, s->root_noise, s->noise_ready, s->noise_counter, s->task_sym, s->sym_counter, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
+				s->value, s->q, s->paused, s->decision, s->root_noise, s->noise_ready, s->noise_counter, s->task_sym, s->sym_counter, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
 				s->sample_root, s->sample_draw, s->sample_score, s->slot_is_root, s->nn_list, s->nn_count, s->solver_out.moves, s->solver_out.scores,
 				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->solver_out.nodes, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
@@ -1725,6 +1757,8 @@ extern "C"
 			s->n_openings = 0;
 		}
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->paused, 0, G, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->decision, 0, G * sizeof(uint16_t), e->stream));
 		if (s->noise_counter != nullptr)
 			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->noise_counter, 0, G * sizeof(uint32_t), e->stream));
 		if (s->sym_counter != nullptr)
@@ -1851,6 +1885,65 @@ extern "C"
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		return AGB_OK;
+	}
+
+	// Player::setBoard + search until isSearchOver + getMove (src/evaluation/Player.cpp) for many games at once: every active game
+	// searches the given position with a fresh tree and stops at its decision; the host plays the moves (evaluation games between two
+	// engines, alphagomoku_b200/arena.py). moves[games]: Move::toShort, 0 for inactive games; root_values[games][2]: win and draw rate
+	// of the root after the search.
+	int agb_think(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *active_host, uint16_t *moves_host,
+			float *root_values_host, int max_steps)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games");
+		if (boards_host == nullptr or sign_to_move_host == nullptr or active_host == nullptr or moves_host == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		int rc = agb_selfplay_reset(e, boards_host, sign_to_move_host);
+		if (rc != AGB_OK)
+			return rc;
+		const int G = s->games;
+		std::vector<uint8_t> paused(G);
+		int remaining = 0;
+		for (int g = 0; g < G; g++)
+		{
+			paused[g] = active_host[g] ? 0 : 1;
+			remaining += active_host[g] ? 1 : 0;
+		}
+		AGB_CUDA_CHECK(e, cudaMemcpy(s->paused, paused.data(), G, cudaMemcpyHostToDevice));
+		e->think_mode = true;
+		int steps = 0;
+		while (remaining > 0)
+		{
+			rc = agb_step(e, 4);
+			if (rc != AGB_OK)
+				break;
+			steps += 4;
+			AGB_CUDA_CHECK(e, cudaMemcpy(paused.data(), s->paused, G, cudaMemcpyDeviceToHost));
+			remaining = 0;
+			for (int g = 0; g < G; g++)
+				remaining += paused[g] ? 0 : 1;
+			if (remaining > 0 and max_steps > 0 and steps >= max_steps)
+			{
+				rc = e->fail(AGB_ESTATE, "agb_think: " + std::to_string(remaining) + " games have not decided after " + std::to_string(steps) + " steps");
+				break;
+			}
+		}
+		e->think_mode = false;
+		if (rc != AGB_OK)
+			return rc;
+		AGB_CUDA_CHECK(e, cudaMemcpy(moves_host, s->decision, G * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+		if (root_values_host != nullptr)
+		{
+			std::vector<float> roots(static_cast<size_t>(G) * 4);
+			AGB_CUDA_CHECK(e, cudaMemcpy(roots.data(), s->sample_root, roots.size() * sizeof(float), cudaMemcpyDeviceToHost));
+			for (int g = 0; g < G; g++)
+			{
+				root_values_host[2 * g + 0] = active_host[g] ? roots[4 * g + 0] : 0.0f;
+				root_values_host[2 * g + 1] = active_host[g] ? roots[4 * g + 1] : 0.0f;
+			}
+		}
 		return AGB_OK;
 	}
 

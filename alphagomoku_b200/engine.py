@@ -227,6 +227,15 @@ class Engine:
                                         _ptr(flags)))
         return scores, n_actions, moves, action_scores, flags
 
+    def think(self, boards, sign_to_move, active=None, max_steps=0):
+        """Player::getMove for every active game: search boards[g] from a fresh tree, return (moves uint16 [games], root values [games, 2])."""
+        b = np.ascontiguousarray(boards, np.int8).reshape(-1, self.cells)
+        s = np.ascontiguousarray(sign_to_move, np.int8)
+        a = np.ones(b.shape[0], np.int8) if active is None else np.ascontiguousarray(active, np.int8)
+        moves, values = np.zeros(b.shape[0], np.uint16), np.zeros((b.shape[0], 2), np.float32)
+        self._check(self._lib.agb_think(self._h, _ptr(b), _ptr(s), _ptr(a), _ptr(moves), _ptr(values), max_steps))
+        return moves, values
+
     def save_games(self):
         """GeneratorManager::saveState: positions, move lists and samples of the games in flight, as bytes."""
         used = ctypes.c_size_t()

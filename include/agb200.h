@@ -182,6 +182,14 @@ int agb_selfplay_reset(AgbEngine *engine, const int8_t *boards_host, const int8_
  * SearchTask::getEdges / getActionScores); flags[n]: bit 0 must-defend, bits 8.. positions visited. */
 int agb_solve(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, int max_positions, uint16_t *scores_host,
 		int32_t *n_actions_host, uint16_t *moves_host, uint16_t *action_scores_host, int32_t *flags_host);
+/* ---- one move per game on request (Player::setBoard / selectSolveEvaluate / expandBackup / isSearchOver / getMove,
+ * src/evaluation/Player.cpp:93-238): every game with active[g] != 0 searches boards[g] from a fresh tree with the engine's search
+ * settings and stops at its decision. moves[games]: the chosen Move::toShort (0 for inactive games); root_values[games][2] (optional):
+ * win and draw rate of the root. max_steps > 0 bounds the lockstep iterations. The building block of evaluation games between two
+ * engines (alphagomoku_b200/arena.py). */
+int agb_think(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *active_host, uint16_t *moves_host,
+		float *root_values_host, int max_steps);
+
 /* games in flight (GeneratorManager::saveState / loadState, src/selfplay/GeneratorManager.cpp:240-290): every game's position, move
  * list and the samples recorded so far. *used receives the size; AGB_ENOMEM when capacity is too small (call once with NULL to size the
  * buffer). Loading needs an engine with the same games / board / rules; the search trees start empty, as after the reference's
