@@ -442,3 +442,63 @@ def test_reference_side_shims_compile_against_the_reference_headers(tmp_path):
     tu.write_text('#include "integration/agb200_shims.hpp"\nint main() { return 0; }\n')
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I/root/reference/include", "-I" + os.path.join(ROOT, "oracle", "ref_stub"),
                            "-I" + os.path.join(ROOT, "include"), "-I" + ROOT, str(tu)])
+
+
+def test_trainer_side_reader_matches_the_reference(ref, tmp_path):
+    """Records (format 201) -> GameDataBuffer file -> what the reference's trainer reads: GameDataStorage::getSample and
+    SamplerVisits::prepare_training_data through oracle/_ref, against alphagomoku_b200.dataset.decode_sample / training_targets_visits on
+    the same bytes. The games are played by the reference's own search with a synthetic evaluator, so every record field is exercised."""
+    import refapi
+    from alphagomoku_b200 import dataset
+    size, cells = 15, 225
+    rng = np.random.default_rng(77)
+
+    def evaluate(features):
+        n = features.shape[0]
+        policy = rng.random((n, cells)).astype(np.float32) ** 4
+        policy /= policy.sum(1, keepdims=True)
+        win = rng.random(n).astype(np.float32)
+        draw = ((1 - win) * rng.random(n)).astype(np.float32)
+        return policy, np.stack([win, draw, 1 - win - draw], 1), None
+
+    records = []
+    for g in range(3):
+        sp = refapi.RefSelfplay(1, size, evaluate, max_batch_size=4, max_simulations=60, use_solver=True, solver_max_positions=50, draw_after=18)
+        board = np.zeros(cells, np.int8)
+        board[[7 * 15 + 7, 7 * 15 + 8 + g, 8 * 15 + 7]] = [1, 2, 1]
+        sp.set_position(board, 2)
+        for _ in range(4000):
+            if sp.step() == 2:
+                break
+        records.append(sp.record())
+        sp.close()
+    buf = dataset.GameDataBuffer(1, size, size, 18)
+    buf.add_records(b"".join(records), len(records))
+    path = str(tmp_path / "buffer.bin")
+    buf.save(path)
+    lib = ref.lib
+    checked = 0
+    for g, rec in enumerate(records):
+        game = dataset.parse_record(rec)
+        assert len(game["samples"]) >= 3
+        for k in range(len(game["samples"])):
+            board, visits, prior = np.zeros(cells, np.int8), np.zeros(cells, np.int32), np.zeros(cells, np.float32)
+            values, scores, scalars = np.zeros((cells, 2), np.float32), np.zeros(cells, np.uint16), np.zeros(8, np.float32)
+            policy_t, value_t, visits_t, scalars_t = np.zeros(cells, np.float32), np.zeros((cells, 2), np.float32), np.zeros(cells, np.float32), np.zeros(6, np.float32)
+            rc = lib.agref_buffer_sample(path.encode(), g, k, _p(board), _p(visits), _p(prior), _p(values), _p(scores), _p(scalars), _p(policy_t), _p(value_t),
+                                         _p(visits_t), _p(scalars_t))
+            assert rc == 0
+            mine = dataset.decode_sample(game, k, size, size)
+            assert (mine["board"] == board).all() and (mine["visit_count"] == visits).all() and (mine["action_scores"] == scores).all()
+            assert (mine["policy_prior"].view(np.uint32) == prior.view(np.uint32)).all()
+            assert (mine["action_values"].view(np.uint32) == values.view(np.uint32)).all()
+            assert np.float32(mine["minimax_value"][0]) == scalars[0] and np.float32(mine["minimax_value"][1]) == scalars[1]
+            assert (mine["minimax_score"], mine["moves_left"], mine["game_outcome"], mine["played_move"], mine["flags"]) == tuple(int(x) for x in scalars[2:7])
+            targets = dataset.training_targets_visits(mine)
+            assert (targets["policy_target"].view(np.uint32) == policy_t.view(np.uint32)).all()
+            assert (targets["action_values_target"].view(np.uint32) == value_t.view(np.uint32)).all()
+            assert (targets["visit_count"] == visits_t.astype(np.int32)).all()
+            assert np.float32(targets["value_target"][0]) == scalars_t[0] and np.float32(targets["value_target"][1]) == scalars_t[1]
+            assert targets["moves_left"] == scalars_t[4] and targets["sign_to_move"] == int(scalars_t[5])
+            checked += 1
+    assert checked >= 10
