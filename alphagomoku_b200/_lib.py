@@ -21,7 +21,7 @@ class AgbConfig(ctypes.Structure):
         ("solver_max_positions", ctypes.c_int32), ("use_symmetries", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("solver_table_entries", ctypes.c_int32),
         ("pipeline_groups", ctypes.c_int32), ("final_selector", ctypes.c_int32), ("final_exploration_constant", ctypes.c_float),
-        ("noise_type", ctypes.c_int32), ("noise_weight", ctypes.c_float), ("reserved", ctypes.c_int32 * 1),
+        ("noise_type", ctypes.c_int32), ("noise_weight", ctypes.c_float), ("policy_temperature", ctypes.c_float),
     ]
 
 

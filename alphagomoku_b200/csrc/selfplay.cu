@@ -214,6 +214,7 @@ namespace agb
 				int max_children; // MCTSConfig::max_children (0: unlimited)
 				int final_selector; // SelfplayConfig::final_selector.policy (AGB_FINAL_*)
 				int single_move; // agb_think: a game stops at its decision instead of playing on
+				float policy_temperature; // MCTSConfig::policy_temperature (initialize_edges, EdgeGenerator.cpp:88-127)
 				int noise_type; // AGB_NOISE_*
 				float noise_weight;
 				float final_exploration; // its exploration_constant (lcb)
@@ -672,6 +673,16 @@ namespace agb
 				p.s.solver.game_slot_count[g] = n_slots;
 		}
 
+		// initialize_edges (EdgeGenerator.cpp:88-127): the prior an edge gets from the policy value of its cell
+		__device__ inline float tempered_prior(float policy_value, float temperature, float max_policy)
+		{
+			if (temperature == 1.0f)
+				return policy_value;
+			if (temperature == 0.0f)
+				return (policy_value == max_policy) ? 1.0f : 0.0f;
+			return powf(policy_value, 1.0f / temperature);
+		}
+
 		// ---- std::partial_sort as libstdc++ runs it (bits/stl_algo.h __partial_sort -> __heap_select + __sort_heap, bits/stl_heap.h),
 		// with EdgeComparator<MaxPolicyPrior> (Edge.hpp:156-171). The order of equal elements is decided by these heap moves, so
 		// prune_weak_moves (EdgeGenerator.cpp:69-84) is reproduced move for move. Single thread.
@@ -792,6 +803,15 @@ namespace agb
 					stones += (p.store.board[cbase + i] != NONE);
 				for (int o = 16; o > 0; o >>= 1)
 					stones += __shfl_xor_sync(kFullMask, stones, o);
+				float max_policy = 0.0f; // maxValue(task.getPolicy()) over the whole board, only needed at temperature 0
+				if (p.policy_temperature == 0.0f)
+				{
+					max_policy = -FLT_MAX;
+					for (int i = lane; i < cells; i += 32)
+						max_policy = fmaxf(max_policy, p.s.policy[static_cast<size_t>(slot) * cells + i]);
+					for (int o = 16; o > 0; o >>= 1)
+						max_policy = fmaxf(max_policy, __shfl_xor_sync(kFullMask, max_policy, o));
+				}
 				int count = 0;
 				uint16_t tscore = score::kDefault;
 				bool must_defend = false;
@@ -821,7 +841,7 @@ namespace agb
 						else if (draw_now)
 							kind = score::DRAW;
 						EdgeD e;
-						e.prior = p.s.policy[static_cast<size_t>(slot) * cells + i];
+						e.prior = tempered_prior(p.s.policy[static_cast<size_t>(slot) * cells + i], p.policy_temperature, max_policy);
 						e.win = p.q_head ? p.s.q[(static_cast<size_t>(slot) * cells + i) * 3 + 0] : 0.0f;
 						e.draw = p.q_head ? p.s.q[(static_cast<size_t>(slot) * cells + i) * 3 + 1] : 0.0f;
 						e.visits = 0;
@@ -911,7 +931,9 @@ namespace agb
 						e.visits = 0;
 						e.vloss_flag = 0;
 						e.pad = 0;
-						e.prior = went_to_nn ? p.s.policy[static_cast<size_t>(slot) * cells + cell] : 0.0f;
+						// a task that skipped the network has an all-zero policy (SearchTask::set clears it)
+						e.prior = went_to_nn ? tempered_prior(p.s.policy[static_cast<size_t>(slot) * cells + cell], p.policy_temperature, max_policy)
+								: tempered_prior(0.0f, p.policy_temperature, 0.0f);
 						e.win = 0.0f;
 						e.draw = 0.0f;
 						if (went_to_nn)
@@ -1544,6 +1566,8 @@ namespace agb
 			p.use_symmetries = e->cfg.use_symmetries != 0;
 			p.max_children = e->cfg.max_children > 0 ? e->cfg.max_children : 0;
 			p.single_move = e->think_mode ? 1 : 0;
+			// 0 in the (possibly zero-initialised) config means the default 1; a negative value asks for the reference's temperature 0
+			p.policy_temperature = (e->cfg.policy_temperature == 0.0f) ? 1.0f : ((e->cfg.policy_temperature < 0.0f) ? 0.0f : e->cfg.policy_temperature);
 			p.final_selector = e->cfg.final_selector;
 			p.noise_type = (e->cfg.noise_weight > 0.0f) ? e->cfg.noise_type : 0;
 			p.noise_weight = e->cfg.noise_weight;

@@ -61,7 +61,7 @@ class Engine:
                  max_simulations=400, max_nodes_per_game=0, max_edges_per_game=0, init_to="parent", exploration_constant=1.25,
                  information_leak_threshold=0.01, policy_expansion_threshold=1.0e-4, max_children=0, solver_max_positions=0,
                  use_symmetries=False, seed=0, first_game_id=0, solver_table_entries=0, pipeline_groups=0, final_selector="max_visit",
-                 final_exploration_constant=1.25, noise_type="none", noise_weight=0.0):
+                 final_exploration_constant=1.25, noise_type="none", noise_weight=0.0, policy_temperature=1.0):
         self._lib = _lib.load()
         self.game = game
         self.cells = game.rows * game.cols
@@ -83,6 +83,7 @@ class Engine:
         cfg.final_exploration_constant = final_exploration_constant
         cfg.noise_type = {"none": 0, "custom": 1, "dirichlet": 2, "gumbel": 3}[noise_type]
         cfg.noise_weight = noise_weight
+        cfg.policy_temperature = -1.0 if policy_temperature == 0 else policy_temperature  # 0 in the C struct means "default"
         self.config = cfg
         self.max_boards = max_boards
         handle = ctypes.c_void_p()

@@ -101,7 +101,8 @@ typedef struct AgbConfig
 	float final_exploration_constant; /* its exploration_constant (used by AGB_FINAL_LCB) */
 	int32_t noise_type; /* EdgeSelectorConfig::noise_type of the tree selector: AGB_NOISE_* (applied at the root, EdgeSelector.cpp:1127-1137) */
 	float noise_weight; /* EdgeSelectorConfig::noise_weight; 0 = no noise */
-	int32_t reserved[1];
+	float policy_temperature; /* MCTSConfig::policy_temperature: 0 or 1 = priors as the network gives them (the default), t > 0 = prior^(1/t),
+	                             negative = the reference's temperature 0 (one-hot on the best move) */
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */

@@ -94,7 +94,8 @@ extern "C"
 {
 	void* agref_sp_create(int rules, int rows, int cols, int draw_after, int max_batch_size, int max_simulations, const char *init_to,
 			float exploration_constant, float information_leak_threshold, int use_solver, int solver_max_positions, agref_eval_fn eval_fn, void *ctx,
-			int max_children, float policy_expansion_threshold, const char *final_policy, float final_exploration_constant)
+			int max_children, float policy_expansion_threshold, const char *final_policy, float final_exploration_constant,
+			float policy_temperature)
 	{
 		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
 		if (draw_after > 0)
@@ -105,6 +106,7 @@ extern "C"
 		sc.constraints.max_simulations = max_simulations;
 		sc.final_selector.policy = (final_policy != nullptr and final_policy[0] != 0) ? final_policy : "max_visit";
 		sc.final_selector.exploration_constant = final_exploration_constant;
+		sc.search_config.mcts_config.policy_temperature = policy_temperature;
 		sc.device_config = { DeviceConfig() };
 		sc.device_config[0].batch_size = max_batch_size;
 		sc.search_config.max_batch_size = max_batch_size;

@@ -99,7 +99,8 @@ class RefSelfplay:
 
     def __init__(self, rules, size, evaluate, max_batch_size=8, max_simulations=100, init_to="parent", exploration_constant=1.25,
                  information_leak_threshold=0.01, use_solver=False, solver_max_positions=100, draw_after=0, fast=False, max_children=0,
-                 policy_expansion_threshold=1.0e-4, final_selector="max_visit", final_exploration_constant=1.25):
+                 policy_expansion_threshold=1.0e-4, final_selector="max_visit", final_exploration_constant=1.25,
+                 policy_temperature=1.0):
         # fast=True: the reference's Release flags (-O3 -DNDEBUG), for timing only (its RNG is then seeded from the clock)
         self.lib = ctypes.CDLL(REF_LIB_FAST if fast and os.path.exists(REF_LIB_FAST) else REF_LIB)
         self.size, self.cells = size, size * size
@@ -118,11 +119,11 @@ class RefSelfplay:
         self._cb = EVAL_FN(callback)
         self.lib.agref_sp_create.restype = ctypes.c_void_p
         self.lib.agref_sp_create.argtypes = [ctypes.c_int] * 6 + [ctypes.c_char_p, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
-                                             EVAL_FN, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p, ctypes.c_float]
+                                             EVAL_FN, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p, ctypes.c_float, ctypes.c_float]
         self.h = ctypes.c_void_p(self.lib.agref_sp_create(rules, size, size, draw_after, max_batch_size, max_simulations, init_to.encode(),
                                                           exploration_constant, information_leak_threshold, int(use_solver),
                                                           solver_max_positions, self._cb, None, max_children, policy_expansion_threshold,
-                                                          final_selector.encode(), final_exploration_constant))
+                                                          final_selector.encode(), final_exploration_constant, policy_temperature))
 
     def set_position(self, board, stm):
         board = np.ascontiguousarray(board, np.int8)

@@ -58,7 +58,14 @@ def test_lockstep_engine_final_selectors(ref, selector, rules, solver):
     _run_case(ref, rules, True, "parent", 4, 60, solver, final_selector=selector)
 
 
-def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_children=0, threshold=1.0e-4, final_selector="max_visit"):
+@pytest.mark.parametrize("rules,solver", [(0, 0), (1, 30)])
+def test_lockstep_engine_policy_temperature_zero(ref, rules, solver):
+    """MCTSConfig::policy_temperature = 0: initialize_edges gives prior 1 to the cells with the largest policy value and 0 to the rest
+    (EdgeGenerator.cpp:90-101); positions that skipped the network have an all-zero policy, hence prior 1 everywhere."""
+    _run_case(ref, rules, False, "parent", 4, 60, solver, temperature=0.0)
+
+
+def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_children=0, threshold=1.0e-4, final_selector="max_visit", temperature=1.0):
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import refapi
@@ -69,7 +76,7 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_chi
     eng = agb.Engine(agb.GameConfig(agb.GameRules(rules), size, size, draw_after), max_boards=256, blocks=blocks, filters=filters, q_head=q_head,
                      games=games, max_batch_size=batch, max_simulations=sims, init_to=init_to, max_nodes_per_game=1024, solver_max_positions=solver,
                      solver_table_entries=4 * 1024 * 1024 if solver > 1 else 0, pipeline_groups=2 if solver > 0 else 1, max_children=max_children,
-                     policy_expansion_threshold=threshold, final_selector=final_selector)  # the reference's table size (AlphaBetaSearch.cpp:55)
+                     policy_expansion_threshold=threshold, final_selector=final_selector, policy_temperature=temperature)  # the reference's table size (AlphaBetaSearch.cpp:55)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, q_head, seed=5), size, size, blocks, filters, q_head))
 
     def evaluate(features):
@@ -84,7 +91,7 @@ def _run_case(ref, rules, q_head, init_to, batch, sims, solver, size=15, max_chi
     for g in range(games):
         r = refapi.RefSelfplay(rules, size, evaluate, max_batch_size=batch, max_simulations=sims, init_to=init_to, use_solver=solver > 0,
                                 solver_max_positions=max(solver, 1), draw_after=draw_after, fast=fast, max_children=max_children,
-                                policy_expansion_threshold=threshold, final_selector=final_selector)
+                                policy_expansion_threshold=threshold, final_selector=final_selector, policy_temperature=temperature)
         refs.append(r)
     if solver > 0:
         eng.set_solver_keys(np.stack([r.solver_keys() for r in refs]))
