@@ -38,6 +38,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         extra = ["-fmad=false"] if src == "selfplay.cu" else []  # tree arithmetic follows the reference op by op (no FMA contraction)
+        if src == "resnet.cu" and os.environ.get("AGB_NET_FLAGS"):
+            extra = os.environ["AGB_NET_FLAGS"].split()  # experiments with the network kernel's code generation
         if src == "solver.cu" and os.environ.get("AGB_SOLVER_FLAGS"):
             extra = os.environ["AGB_SOLVER_FLAGS"].split()  # experiments with the solver kernel's code generation
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]

@@ -153,7 +153,12 @@ namespace agb
 		// owns the upper rows, rank 1 the lower ones; after every layer each CTA writes its boundary row into the other's halo row through
 		// distributed shared memory, so the tensor-core schedule is the same as for two independent boards.
 		template<int F, bool SPLIT>
+#ifdef AGB_NET_MAXNREG
+		// experiment: a register cap leaves room for solver warps of another pipeline group next to the resident CTA
+		__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(AGB_NET_MAXNREG) resnet_board_kernel(const __grid_constant__ NetParams prm)
+#else
 		__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) resnet_board_kernel(const __grid_constant__ NetParams prm)
+#endif
 		{
 			extern __shared__ __align__(1024) uint8_t smem[];
 			const int S = prm.S, P = prm.P;

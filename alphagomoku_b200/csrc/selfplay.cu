@@ -20,6 +20,8 @@
 #include "records.cuh"
 
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -2122,6 +2124,20 @@ extern "C"
 				e->nn_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
 			if (e->cfg.solver_max_positions > 0 and cudaEventElapsedTime(&ms, e->events[4 * i], e->events[4 * i + 1]) == cudaSuccess)
 				e->solver_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
+		}
+		if (const char *trace = getenv("AGB_STEP_TRACE"))
+		{ // diagnostics: when each group's solver and network phases ran, in ms from the first event of the call
+			if (FILE *f = fopen(trace, "a"))
+			{
+				for (int i = 0; i < n_steps * groups; i++)
+				{
+					float t[4] = { 0, 0, 0, 0 };
+					for (int k = 0; k < 4; k++)
+						cudaEventElapsedTime(&t[k], e->events[0], e->events[4 * i + k]);
+					fprintf(f, "step %d group %d: solver %.2f-%.2f network %.2f-%.2f\n", i / groups, i % groups, t[0], t[1], t[2], t[3]);
+				}
+				fclose(f);
+			}
 		}
 		e->nn_kernel_launches += static_cast<uint64_t>(n_steps) * groups;
 		e->nn_positions += evals_after - evals_before;
