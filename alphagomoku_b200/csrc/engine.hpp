@@ -86,6 +86,9 @@ namespace agb
 			void *frames = nullptr; // [games][kMaxFrames] solver::Frame
 			void *children = nullptr; // [games][cells] solver::ChildInfo (previews of the root actions)
 			unsigned long long *game_cycles = nullptr; // [games][2] SM clocks and positions visited by the last launch (load-balance diagnostics)
+			uint32_t *game_work = nullptr; // [games] estimated cost of the game in the last launch (next launch's priorities)
+			int32_t *order = nullptr; // [games] games of a launch, most expensive (by the previous launch's clocks) first
+			int32_t *next = nullptr; // [games] work-queue heads, one per launch range (indexed by its first game)
 			const uint16_t *def_table = nullptr;
 	};
 	// solver.cu

@@ -21,23 +21,51 @@ namespace agb
 	namespace
 	{
 
-		// Two builds of the same kernel: <1, 28> keeps 72 registers per thread and holds 28 games per SM (enough for 4144 games in one
-		// wave); <2, 28> is capped at 32 registers and holds 56, for launches with more games than that (the kernel is latency-bound, so
-		// resident warps matter more than spills: 16384 games x 2 leaves take 26 ms where 4096 x 8 take 43).
+		// Two builds of the same kernel: <1, 28> keeps 72 registers per thread (28 warps fit an SM); <2, 28> is capped at 32 registers and
+		// holds 56, for launches with many more games than that (resident warps matter more than spills there: 16384 games x 2 leaves
+		// take 26 ms where 4096 x 8 take 43).
+		//
+		// Scheduling: the kernel is bound by the SM's instruction supply, which saturates at 8-16 unrelated warps, and
+		// a game's cost is heavy-tailed, so "every game resident from the start" ends in a long tail of a few expensive games per SM
+		// crawling at an equal share. Instead fewer warps are resident and each pulls games from a queue ordered by the cost the game
+		// had in the previous launch (longest first; a game's cost correlates 0.9 from one step to the next): expensive games start at once and get a larger share, cheap ones fill the end.
+		constexpr int kResidentWarps = 10; // per SM, 72-register build: measured best of 4..28 (throughput is flat above ~8, the tail shorter below 28)
+		__global__ void order_games_kernel(const uint32_t *__restrict__ game_work, int game_begin, int games, int32_t *__restrict__ order, int32_t *__restrict__ next)
+		{ // rank by counting: games <= 16384, so n^2 comparisons are a few hundred microseconds at worst
+			const int i = blockIdx.x * blockDim.x + threadIdx.x;
+			if (i == 0)
+				*next = 0;
+			if (i >= games)
+				return;
+			const uint32_t mine = game_work[game_begin + i];
+			int rank = 0;
+			for (int j = 0; j < games; j++)
+			{
+				const uint32_t other = game_work[game_begin + j];
+				rank += (other > mine or (other == mine and j < i)) ? 1 : 0;
+			}
+			order[game_begin + rank] = i;
+		}
 		template<int kSolverWarpsPerBlock, int kMinBlocks>
 		__global__ void __launch_bounds__(kSolverWarpsPerBlock * 32, kMinBlocks) solve_games_kernel(BoardStore store, Tables tables, SolverState st, int game_begin, int games, int S, int rules,
 				int draw_after, int max_nodes, SolverOutputs out, const uint8_t *__restrict__ slot_is_root, int *__restrict__ nn_list, int *__restrict__ nn_count,
 				uint32_t *__restrict__ status)
 		{
-			const int local = blockIdx.x * kSolverWarpsPerBlock + (threadIdx.x >> 5);
-			if (local >= games)
+		  for (;;)
+		  {
+			int ticket = 0;
+			if ((threadIdx.x & 31) == 0)
+				ticket = atomicAdd(st.next + game_begin, 1);
+			ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+			if (ticket >= games)
 				return;
+			const int local = st.order[game_begin + ticket];
 			const int g = game_begin + local;
 			const bool leader = (threadIdx.x & 31) == 0; // all lanes run the solver in lockstep (solver_search.cuh); one of them publishes
 			const int cells = S * S;
 			const int n_slots = st.game_slot_count[g];
 			const long long t_begin = clock64();
-			unsigned long long nodes_total = 0;
+			unsigned long long nodes_total = 0, n_adds = 0, n_quiet = 0, n_gen = 0;
 			solver::HashTable tt { st.table + static_cast<size_t>(g) * st.table_entries * 2, st.table_entries / 4 - 1, st.generation[g], st.keys + static_cast<size_t>(g) * st.keys_stride };
 			solver::SearchMemory mem { st.stack_moves + static_cast<size_t>(g) * st.stack_capacity, st.stack_scores + static_cast<size_t>(g) * st.stack_capacity,
 					st.stack_capacity, reinterpret_cast<solver::Frame*>(st.frames) + static_cast<size_t>(g) * solver::kMaxFrames,
@@ -76,6 +104,9 @@ namespace agb
 				out.must_defend[slot] = res.must_defend ? 1 : 0;
 				out.nodes[slot] = res.node_counter;
 				nodes_total += res.node_counter;
+				n_adds += d.n_adds;
+				n_quiet += d.n_quiet;
+				n_gen += d.n_gen_actions;
 				if (leader and res.overflow)
 					atomicOr(status, res.overflow << 8); // bits 8..11, see AgbStats::overflow_flags
 				if (leader and (slot_is_root[slot] or not solver::sc_is_proven(res.score)))
@@ -86,7 +117,10 @@ namespace agb
 			{
 				st.game_cycles[2 * g] = static_cast<unsigned long long>(clock64() - t_begin);
 				st.game_cycles[2 * g + 1] = nodes_total;
+				// cost estimate in kilo-clocks of an undisturbed warp: least-squares fit on one-game-per-SM runs (tools/solver_work_fit.py, R^2 0.97)
+				st.game_work[g] = static_cast<uint32_t>(24 * n_adds + 6 * n_quiet + 4 * n_gen);
 			}
+		  }
 		}
 		__global__ void clear_tables_kernel(uint64_t *table, size_t n_entries)
 		{
@@ -139,6 +173,10 @@ namespace agb
 		AGB_CUDA_CHECK(e, cudaMalloc(&st->game_cycles, static_cast<size_t>(games) * 2 * sizeof(unsigned long long)));
 		AGB_CUDA_CHECK(e, cudaMemset(st->game_cycles, 0, static_cast<size_t>(games) * 2 * sizeof(unsigned long long)));
 		AGB_CUDA_CHECK(e, cudaMalloc(&st->children, static_cast<size_t>(games) * e->cells * sizeof(solver::ChildInfo)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->game_work, games * sizeof(uint32_t)));
+		AGB_CUDA_CHECK(e, cudaMemset(st->game_work, 0, games * sizeof(uint32_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->order, games * sizeof(int32_t)));
+		AGB_CUDA_CHECK(e, cudaMalloc(&st->next, games * sizeof(int32_t)));
 		AGB_CUDA_CHECK(e, cudaMemset(st->generation, 0, games * sizeof(int32_t)));
 		AGB_CUDA_CHECK(e, cudaMemset(st->game_slot_count, 0, games * sizeof(int32_t)));
 		st->def_table = e->d_def_table;
@@ -170,6 +208,9 @@ namespace agb
 		cudaFree(st->frames);
 		cudaFree(st->children);
 		cudaFree(st->game_cycles);
+		cudaFree(st->game_work);
+		cudaFree(st->order);
+		cudaFree(st->next);
 		*st = SolverState { };
 	}
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
@@ -179,12 +220,21 @@ namespace agb
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
 		static const bool force_dense = getenv("AGB_SOLVER_DENSE") != nullptr; // tests: exercise the low-register build with few games
-		if (game_count <= 28 * sms and not force_dense)
-			solve_games_kernel<1, 28><<<game_count, 32, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows, e->cfg.rules, draw_after,
-					e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		static const int resident_env = getenv("AGB_SOLVER_RESIDENT") != nullptr ? atoi(getenv("AGB_SOLVER_RESIDENT")) : 0; // warps per SM (tuning)
+		order_games_kernel<<<(game_count + 127) / 128, 128, 0, stream>>>(st.game_work, game_begin, game_count, st.order, st.next + game_begin);
+		e->launches++;
+		if (game_count <= 56 * sms and not force_dense)
+		{
+			const int resident = std::min(28, resident_env > 0 ? resident_env : kResidentWarps);
+			solve_games_kernel<1, 28> <<<std::min(game_count, resident * sms), 32, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows, e->cfg.rules,
+					draw_after, e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		}
 		else
-			solve_games_kernel<2, 28><<<(game_count + 1) / 2, 64, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows, e->cfg.rules, draw_after,
-					e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		{
+			const int resident = std::min(56, resident_env > 0 ? resident_env : 56);
+			solve_games_kernel<2, 28> <<<std::min((game_count + 1) / 2, resident / 2 * sms), 64, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows,
+					e->cfg.rules, draw_after, e->cfg.solver_max_positions, out, slot_is_root, nn_list, nn_count, e->d_status);
+		}
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

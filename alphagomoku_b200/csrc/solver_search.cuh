@@ -35,6 +35,7 @@ namespace agb
 				uint8_t cache_val[48];
 				int cache_size = 0;
 				uint32_t overflow = 0; // 1: forbidden-move recursion too deep, 2: forbidden cache full
+				uint32_t n_adds = 0, n_quiet = 0, n_gen = 0, n_gen_actions = 0; // work counters (scheduling weights, solver.cu)
 		};
 
 		AGB_HD_NOINLINE inline void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
@@ -175,6 +176,7 @@ namespace agb
 		}
 		AGB_HD_NOINLINE inline void dyn_add_move(DynState &d, int r, int c, int sign)
 		{ // PatternCalculator::addMove (PatternCalculator.cpp:68-86)
+			d.n_adds++;
 			const int S = d.v.S;
 			uint64_t line4[4];
 			int pos4[4];
@@ -651,6 +653,7 @@ namespace agb
 			const ChildInfo &info = mem.children[((mv >> 2) & 127) * d.v.S + ((mv >> 9) & 127)];
 			if (info.quiet == 0 or info.n_ops == 255)
 				return false;
+			d.n_quiet++;
 			const int depth = f.depth_remaining - 1;
 			const uint16_t alpha = sc_invert(f.beta, -1), beta = sc_invert(f.alpha, -1);
 			hash_toggle(tt, key_lo, key_hi, d.v.S, mv);
@@ -755,6 +758,8 @@ namespace agb
 									d.cache_size = 0;
 									MoveGenerator gen(d.v, mem.stack_moves + f.list_begin, mem.stack_scores + f.list_begin);
 									gen.generate(top == 0 ? GEN_OPTIMAL : GEN_THREATS);
+									d.n_gen++;
+									d.n_gen_actions += gen.out.n_actions;
 									f.list_size = static_cast<int16_t>(gen.out.n_actions);
 									f.is_fully_expanded = gen.out.is_fully_expanded ? 1 : 0;
 									stack_offset += gen.out.n_actions;
