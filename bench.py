@@ -35,9 +35,23 @@ SOLVER_POSITIONS, SOLVER_TABLE_ENTRIES = 100, 65536  # tss max_positions as in t
 FLOP_PER_POSITION = 2 * 1383.70e6  # BASELINE.md section 3 (algorithmic, ResNet 20x128 @ 15x15, heads p+v)
 
 
+# --workload: the headline is configs[1]; configs[2] and configs[3] of BASELINE.json can be measured with the same harness (extra lines,
+# e.g. profiles/r01_bench_renju15.json), name -> (label, rules, size, simulations, algorithmic FLOP per position from BASELINE.md section 3)
+WORKLOADS = {"standard15": ("configs[1]: standard 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", 1, 15, 400, 2 * 1383.70e6),
+             "renju15": ("configs[2]: renju 15x15 self-play with forbidden-move detection and the solver in the loop, ResNet 20x128 bf16", 2, 15, 400, 2 * 1383.70e6),
+             "caro20": ("configs[3]: caro 20x20 self-play, ResNet 20x128 bf16, 800 playouts/move", 3, 20, 800, 2 * 2459.90e6)}
+WORKLOAD = WORKLOADS["standard15"][0]
+RULE_NAMES = ["FREESTYLE", "STANDARD", "RENJU", "CARO5", "CARO6"]
+
+
+def select_workload(name):
+    global WORKLOAD, RULES, SIZE, SIMS, FLOP_PER_POSITION
+    WORKLOAD, RULES, SIZE, SIMS, FLOP_PER_POSITION = WORKLOADS[name]
+
+
 def workload_config(n_gpus, impl="ours", solver=0):
-    return {"workload": "configs[1]: standard 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", "rules": "STANDARD",
-            "board": "15x15", "network": "ResnetPV 20x128", "games_per_gpu": GAMES, "max_batch_size": BATCH, "max_simulations": SIMS, "use_symmetries": True,
+    return {"workload": WORKLOAD, "rules": RULE_NAMES[RULES],
+            "board": f"{SIZE}x{SIZE}", "network": "ResnetPV 20x128", "games_per_gpu": GAMES, "max_batch_size": BATCH, "max_simulations": SIMS, "use_symmetries": True,
             "solver": ("on (AlphaBetaSearch, max_positions 100, 4 Mi-entry table per game)" if impl == "reference" else
                        f"on (K5 alpha-beta, max_positions {solver}, {SOLVER_TABLE_ENTRIES}-entry table per game)" if solver > 0 else "off"),
             "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
@@ -189,9 +203,11 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="SearchConfig::max_batch_size (leaves per game and step)")
     ap.add_argument("--groups", type=int, default=0, help="pipeline groups (0 = engine default)")
     ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
+    ap.add_argument("--workload", default="standard15", choices=sorted(WORKLOADS), help="standard15 = BASELINE.json configs[1] (the headline)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -209,9 +225,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     games = args.games
+    nodes_per_game = 1536 * SIMS // 400  # the tree of one move plus the subtree kept from the previous one
     eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * args.batch, device=local_rank, blocks=BLOCKS, filters=FILTERS,
-                     q_head=False, games=games, max_batch_size=args.batch, max_simulations=SIMS, init_to="parent", max_nodes_per_game=1536,
-                     max_edges_per_game=1536 * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
+                     q_head=False, games=games, max_batch_size=args.batch, max_simulations=SIMS, init_to="parent", max_nodes_per_game=nodes_per_game,
+                     max_edges_per_game=nodes_per_game * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
                      solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups, use_symmetries=True)
     # C1: rank 0 owns the weights and broadcasts them over NCCL (NetworkLoader::get per thread in the reference)
     blob = netblob.pack(netblob.random_tensors(SIZE, SIZE, BLOCKS, FILTERS, False), SIZE, SIZE, BLOCKS, FILTERS, False) if rank == 0 else None
@@ -312,7 +329,7 @@ def main():
                 "config": workload_config(world, solver=args.solver),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * (SIZE * SIZE + 1)), "d2h_bytes_per_step": int(n_e2e * (SIZE * SIZE + 3) * 4),
                         "api": "agb_evaluate (NNEvaluator::evaluateGraph drop-in): pinned host boards -> K1+K3+K4 -> host policy/value"},
-                "gpu_launches": int(sums[4]),
+                "gpu_launches": int(sums[4]), "overflow_flags": int(st1["overflow_flags"]),
                 "roofline": {"bound": "tensor", "kernel": "resnet_board_kernel (+ value head)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                              "positions_per_launch": nn_positions / max(nn_launches, 1), "ms_per_launch": nn_ns / max(nn_launches, 1) * 1e-6,
