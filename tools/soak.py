@@ -11,10 +11,13 @@ import bench
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
 games = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-eng = agb.Engine(agb.GameConfig(agb.GameRules(bench.RULES), 15, 15), max_boards=games * 8, blocks=bench.BLOCKS, filters=bench.FILTERS, games=games,
-                 max_batch_size=8, max_simulations=bench.SIMS, max_nodes_per_game=1536, max_edges_per_game=1536 * 200, solver_max_positions=100,
+bench.select_workload(sys.argv[3] if len(sys.argv) > 3 else "standard15")
+S, nodes = bench.SIZE, 1536 * bench.SIMS // 400
+eng = agb.Engine(agb.GameConfig(agb.GameRules(bench.RULES), S, S), max_boards=games * 8, blocks=bench.BLOCKS, filters=bench.FILTERS, games=games,
+                 max_batch_size=8, max_simulations=bench.SIMS, max_nodes_per_game=nodes, max_edges_per_game=nodes * 200, solver_max_positions=100,
                  solver_table_entries=65536, seed=1, use_symmetries=True)
-eng.load_weights(netblob.pack(netblob.random_tensors(15, 15, bench.BLOCKS, bench.FILTERS, False), 15, 15, bench.BLOCKS, bench.FILTERS, False))
+eng.load_weights(netblob.pack(netblob.random_tensors(S, S, bench.BLOCKS, bench.FILTERS, False), S, S, bench.BLOCKS, bench.FILTERS, False))
+print("workload:", bench.WORKLOAD)
 boards, stm = eng.generate_openings(games)
 print("openings:", games, "stones per opening mean", float((boards != 0).sum(1).mean()))
 eng.selfplay_reset(boards, stm)
