@@ -22,6 +22,7 @@ class AgbConfig(ctypes.Structure):
         ("seed", ctypes.c_uint64), ("first_game_id", ctypes.c_int32), ("solver_table_entries", ctypes.c_int32),
         ("pipeline_groups", ctypes.c_int32), ("final_selector", ctypes.c_int32), ("final_exploration_constant", ctypes.c_float),
         ("noise_type", ctypes.c_int32), ("noise_weight", ctypes.c_float), ("policy_temperature", ctypes.c_float),
+        ("solver_sms", ctypes.c_int32),
     ]
 
 

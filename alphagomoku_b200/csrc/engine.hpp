@@ -98,8 +98,9 @@ namespace agb
 	void solver_state_destroy(SolverState *st);
 	void solve_scratch_destroy(AgbEngine *e);
 	void openings_destroy(AgbEngine *e);
+	// solver_sms > 0: run on that many SMs only, in blocks that take whole SMs (side by side with the network kernel, see AgbConfig::solver_sms)
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
-			int *nn_count, cudaStream_t stream);
+			int *nn_count, cudaStream_t stream, int solver_sms = 0);
 	// tables.cu
 	int build_tables(AgbEngine *e);
 	// patterns.cu

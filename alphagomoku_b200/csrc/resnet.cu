@@ -898,7 +898,7 @@ namespace agb
 	}
 
 	int net_forward_impl(AgbEngine *e, const uint32_t *features_dev, int n_boards, const int *n_dev, const int *gather_dev, float *policy_dev, float *value_dev,
-			float *q_dev, int slot_base = 0, cudaStream_t stream = nullptr)
+			float *q_dev, int slot_base = 0, cudaStream_t stream = nullptr, int max_sms = 0)
 	{
 		if (stream == nullptr)
 			stream = e->stream;
@@ -920,6 +920,8 @@ namespace agb
 		p.trace = trace ? d_trace : nullptr;
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
+		if (max_sms > 0)
+			sms = std::min(sms, max_sms); // the other SMs are the solver's (AgbConfig::solver_sms)
 		const int pairs = std::min(n->split ? n_boards : (n_boards + 1) / 2, sms / 2);
 		const int grid = 2 * pairs; // clusters of two CTAs: one board each, or (large boards) one board per pair
 		if (n->split)
@@ -968,9 +970,9 @@ namespace agb
 		return net_forward_impl(e, features_dev, n_boards, nullptr, nullptr, policy_dev, value_dev, q_dev);
 	}
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
-			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream)
+			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms)
 	{
-		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev, slot_base, stream);
+		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev, slot_base, stream, max_sms);
 	}
 }
 

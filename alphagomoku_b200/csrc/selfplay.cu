@@ -156,6 +156,7 @@ namespace agb
 			// pipeline groups: the games are split into `groups` independent halves that advance on their own streams, so that the
 			// solver / tree kernels of one half overlap the network kernel of the other (the network launches share one stream)
 			int groups = 1;
+			int solver_sms = 0, net_sms = 0; // SM partition between K5 and K4 (AgbConfig::solver_sms; 0 = none)
 			cudaStream_t group_stream[kMaxGroups] = { };
 			cudaStream_t nn_stream = nullptr;
 			cudaEvent_t ready[kMaxGroups] = { }, evaluated[kMaxGroups] = { }, joined = nullptr;
@@ -1585,7 +1586,7 @@ namespace agb
 	}
 
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
-			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream);
+			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms);
 
 	int selfplay_create(AgbEngine *e)
 	{
@@ -1684,7 +1685,15 @@ namespace agb
 			ok = cudaMemset(s->tasks, 0, T * sizeof(TaskD)) == cudaSuccess; // sticky per-slot flags start cleared
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
-		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : 1;
+		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : ((c.solver_max_positions > 1 and c.games >= 1024) ? 2 : 1);
+		{ // AgbConfig::solver_sms
+			int sms = 148;
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+			s->solver_sms = 0;
+			if (s->groups > 1 and c.solver_max_positions > 1 and c.solver_sms >= 0)
+				s->solver_sms = (c.solver_sms > 0 ? std::min(c.solver_sms, sms - 2) : sms * 20 / 148) & ~1;
+			s->net_sms = s->solver_sms > 0 ? sms - s->solver_sms : 0;
+		}
 		if (s->groups > kMaxGroups or s->groups > c.games)
 			return e->fail(AGB_EINVAL, "pipeline_groups must be 1..4 and not exceed the number of games");
 		if (s->groups > 1)
@@ -2063,7 +2072,7 @@ extern "C"
 				if (p.solver_mode != 0)
 				{ // K5 on every leaf; only unproven positions (and roots) go on to the network
 					AGB_CUDA_CHECK(e, cudaMemsetAsync(nn_count, 0, sizeof(int32_t), gs));
-					rc = launch_solve_games(e, s->solver, p.game_begin, p.game_count, s->solver_out, s->slot_is_root, s->nn_list + p.slot_base, nn_count, gs);
+					rc = launch_solve_games(e, s->solver, p.game_begin, p.game_count, s->solver_out, s->slot_is_root, s->nn_list + p.slot_base, nn_count, gs, s->solver_sms);
 					if (rc != AGB_OK)
 						return rc;
 				}
@@ -2083,7 +2092,7 @@ extern "C"
 				}
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[2], ns));
 				rc = net_forward_dev_gather(e, sym ? s->features_aug : s->features, p.solver_mode != 0 ? nn_count : p.eval_count,
-						p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr, max_tasks, sym ? s->policy_raw : s->policy, s->value, sym ? s->q_raw : s->q, p.slot_base, ns);
+						p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr, max_tasks, sym ? s->policy_raw : s->policy, s->value, sym ? s->q_raw : s->q, p.slot_base, ns, s->net_sms);
 				if (rc != AGB_OK)
 					return rc;
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[3], ns));

@@ -214,7 +214,7 @@ namespace agb
 		*st = SolverState { };
 	}
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
-			int *nn_count, cudaStream_t stream)
+			int *nn_count, cudaStream_t stream, int solver_sms)
 	{
 		const int draw_after = e->cfg.draw_after > 0 ? e->cfg.draw_after : e->cells;
 		int sms = 148;
@@ -223,7 +223,26 @@ namespace agb
 		static const int resident_env = getenv("AGB_SOLVER_RESIDENT") != nullptr ? atoi(getenv("AGB_SOLVER_RESIDENT")) : 0; // warps per SM (tuning)
 		order_games_kernel<<<(game_count + 127) / 128, 128, 0, stream>>>(st.game_work, game_begin, game_count, st.order, st.next + game_begin);
 		e->launches++;
-		if (game_count <= 56 * sms and not force_dense)
+		if (solver_sms > 0)
+		{ // side by side with the network kernel (AgbConfig::solver_sms): blocks of 28 warps at 72 registers fill an SM's register file, so such a
+		  // block and a K4 CTA never share an SM, and they are launched as clusters of two so that they take whole TPCs and K4's CTA pairs find
+		  // whole TPCs among the rest. Nothing inside the kernel uses the cluster.
+			cudaLaunchConfig_t cfg = { };
+			cfg.gridDim = dim3(static_cast<unsigned>(std::max(2, solver_sms & ~1)));
+			cfg.blockDim = dim3(28 * 32);
+			cfg.dynamicSmemBytes = 0;
+			cfg.stream = stream;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeClusterDimension;
+			attr[0].val.clusterDim.x = 2;
+			attr[0].val.clusterDim.y = 1;
+			attr[0].val.clusterDim.z = 1;
+			cfg.attrs = attr;
+			cfg.numAttrs = 1;
+			AGB_CUDA_CHECK(e, cudaLaunchKernelEx(&cfg, solve_games_kernel<28, 1>, e->store, e->tables, st, game_begin, game_count, static_cast<int>(e->cfg.rows),
+					static_cast<int>(e->cfg.rules), draw_after, static_cast<int>(e->cfg.solver_max_positions), out, slot_is_root, nn_list, nn_count, e->d_status));
+		}
+		else if (game_count <= 56 * sms and not force_dense)
 		{
 			const int resident = std::min(28, resident_env > 0 ? resident_env : kResidentWarps);
 			solve_games_kernel<1, 28> <<<std::min(game_count, resident * sms), 32, 0, stream>>>(e->store, e->tables, st, game_begin, game_count, e->cfg.rows, e->cfg.rules,

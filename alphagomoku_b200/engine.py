@@ -60,7 +60,7 @@ class Engine:
     def __init__(self, game: GameConfig, max_boards=1024, device=0, blocks=0, filters=0, q_head=False, games=0, max_batch_size=1,
                  max_simulations=400, max_nodes_per_game=0, max_edges_per_game=0, init_to="parent", exploration_constant=1.25,
                  information_leak_threshold=0.01, policy_expansion_threshold=1.0e-4, max_children=0, solver_max_positions=0,
-                 use_symmetries=False, seed=0, first_game_id=0, solver_table_entries=0, pipeline_groups=0, final_selector="max_visit",
+                 use_symmetries=False, seed=0, first_game_id=0, solver_table_entries=0, pipeline_groups=0, solver_sms=0, final_selector="max_visit",
                  final_exploration_constant=1.25, noise_type="none", noise_weight=0.0, policy_temperature=1.0):
         self._lib = _lib.load()
         self.game = game
@@ -79,6 +79,7 @@ class Engine:
         cfg.use_symmetries, cfg.seed, cfg.first_game_id = int(use_symmetries), seed, first_game_id
         cfg.solver_table_entries = solver_table_entries
         cfg.pipeline_groups = pipeline_groups
+        cfg.solver_sms = solver_sms
         cfg.final_selector = {"max_visit": 0, "best": 1, "max_value": 2, "max_policy": 3, "min_visit": 4, "lcb": 5}[final_selector]
         cfg.final_exploration_constant = final_exploration_constant
         cfg.noise_type = {"none": 0, "custom": 1, "dirichlet": 2, "gumbel": 3}[noise_type]

@@ -201,7 +201,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--games", type=int, default=GAMES)
     ap.add_argument("--batch", type=int, default=BATCH, help="SearchConfig::max_batch_size (leaves per game and step)")
-    ap.add_argument("--groups", type=int, default=0, help="pipeline groups (0 = engine default)")
+    ap.add_argument("--groups", type=int, default=0, help="AgbConfig::pipeline_groups (0 = engine default: 2 with the alpha-beta solver on)")
+    ap.add_argument("--solver-sms", type=int, default=0, help="AgbConfig::solver_sms (0 = engine default: 20 of 148 SMs, -1 = no partition)")
     ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
     ap.add_argument("--workload", default="standard15", choices=sorted(WORKLOADS), help="standard15 = BASELINE.json configs[1] (the headline)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -229,7 +230,7 @@ def main():
     eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * args.batch, device=local_rank, blocks=BLOCKS, filters=FILTERS,
                      q_head=False, games=games, max_batch_size=args.batch, max_simulations=SIMS, init_to="parent", max_nodes_per_game=nodes_per_game,
                      max_edges_per_game=nodes_per_game * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
-                     solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups, use_symmetries=True)
+                     solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups, solver_sms=args.solver_sms, use_symmetries=True)
     # C1: rank 0 owns the weights and broadcasts them over NCCL (NetworkLoader::get per thread in the reference)
     blob = netblob.pack(netblob.random_tensors(SIZE, SIZE, BLOCKS, FILTERS, False), SIZE, SIZE, BLOCKS, FILTERS, False) if rank == 0 else None
     eng.load_weights(sharding.broadcast_weights(blob))
@@ -319,6 +320,9 @@ def main():
             peak, peak_src = json.load(open(peaks_path))["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         else:
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+        total_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        groups_eff = args.groups if args.groups > 0 else (2 if args.solver > 1 and games >= 1024 else 1)
+        partition_sms = 0 if (groups_eff < 2 or args.solver <= 1 or args.solver_sms < 0) else ((args.solver_sms or total_sms * 20 // 148) & ~1)
         achieved = (FLOP_PER_POSITION * nn_positions / max(nn_launches, 1)) / (nn_ns / max(nn_launches, 1) * 1e-9) / 1e12 if nn_ns else None
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r01_k4_ncu_summary.json")
@@ -326,12 +330,19 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": max_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(world, solver=args.solver),
+                "config": dict(workload_config(world, solver=args.solver),
+                               pipeline=("one group, K5 then K4 on all SMs" if groups_eff == 1 or args.solver <= 1 else
+                                         f"{groups_eff} groups of games; K5 on {partition_sms} SMs side by side with K4 on the others"
+                                         if partition_sms > 0 else f"{groups_eff} groups of games, no SM partition")),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * (SIZE * SIZE + 1)), "d2h_bytes_per_step": int(n_e2e * (SIZE * SIZE + 3) * 4),
                         "api": "agb_evaluate (NNEvaluator::evaluateGraph drop-in): pinned host boards -> K1+K3+K4 -> host policy/value"},
                 "gpu_launches": int(sums[4]), "overflow_flags": int(st1["overflow_flags"]),
                 "roofline": {"bound": "tensor", "kernel": "resnet_board_kernel (+ value head)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                             "note": ("K4 timed alone on all SMs" if partition_sms == 0 else
+                                      f"K4 runs on {total_sms - partition_sms} of {total_sms} SMs, side by side with K5 on the other {partition_sms}; frac is against the "
+                                      f"whole GPU's peak ({achieved / (peak * (total_sms - partition_sms) / total_sms):.3f} of its own SMs' share); "
+                                      f"alone on all SMs (--groups 1, profiles/r01_bench_n1_groups1.json) it reaches 0.85"),
                              "positions_per_launch": nn_positions / max(nn_launches, 1), "ms_per_launch": nn_ns / max(nn_launches, 1) * 1e-6,
                              "share_of_step": (nn_ns * 1e-6) / ms, "solver_share_of_step": (st1["solver_kernel_ns"] - st0["solver_kernel_ns"]) * 1e-6 / ms,
                              "leaf_positions_per_step": (st1["nb_node_count"] - st0["nb_node_count"]) / args.steps},

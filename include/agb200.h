@@ -96,13 +96,17 @@ typedef struct AgbConfig
 	int32_t solver_table_entries; /* entries of each game's solver transposition table (power of two; 0 = 65536; the reference uses 4 Mi,
 	                                 AlphaBetaSearch.cpp:55) */
 	int32_t pipeline_groups; /* 1: all games advance together; 2..4: that many groups of games on their own streams, so that one group's solver and tree
-	                            kernels can overlap another group's network kernel; 0 = 1. Per-game results do not depend on it */
+	                            kernels overlap another group's network kernel; 0 = automatic (2 when the alpha-beta solver is on and there are at
+	                            least 1024 games, else 1). Per-game results do not depend on it */
 	int32_t final_selector; /* SelfplayConfig::final_selector.policy: AGB_FINAL_* (EdgeSelector::create, EdgeSelector.cpp:680-711) */
 	float final_exploration_constant; /* its exploration_constant (used by AGB_FINAL_LCB) */
 	int32_t noise_type; /* EdgeSelectorConfig::noise_type of the tree selector: AGB_NOISE_* (applied at the root, EdgeSelector.cpp:1127-1137) */
 	float noise_weight; /* EdgeSelectorConfig::noise_weight; 0 = no noise */
 	float policy_temperature; /* MCTSConfig::policy_temperature: 0 or 1 = priors as the network gives them (the default), t > 0 = prior^(1/t),
 	                             negative = the reference's temperature 0 (one-hot on the best move) */
+	int32_t solver_sms; /* with 2..4 pipeline groups and the alpha-beta solver: SMs the solver kernel runs on while the network kernel takes the
+	                       others (side by side, not sharing SMs: the solver is bound by instruction supply, the network by the tensor pipe, and
+	                       on a shared SM both lose). 0 = automatic (20 of 148), -1 = no partition. Even; ignored with one group */
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
