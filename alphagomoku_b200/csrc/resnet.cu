@@ -898,7 +898,7 @@ namespace agb
 	}
 
 	int net_forward_impl(AgbEngine *e, const uint32_t *features_dev, int n_boards, const int *n_dev, const int *gather_dev, float *policy_dev, float *value_dev,
-			float *q_dev, int slot_base = 0, cudaStream_t stream = nullptr, int max_sms = 0)
+			float *q_dev, int slot_base = 0, cudaStream_t stream = nullptr, int max_sms = 0, cudaStream_t tail_stream = nullptr, cudaEvent_t trunk_done = nullptr)
 	{
 		if (stream == nullptr)
 			stream = e->stream;
@@ -955,6 +955,12 @@ namespace agb
 			}
 		}
 		const int cells = e->cells, D = n->dense_width;
+		if (tail_stream != nullptr and tail_stream != stream)
+		{ // pipeline groups: the dense value layers go on the group's own stream, so that the next group's K4 follows this one at once
+			AGB_CUDA_CHECK(e, cudaEventRecord(trunk_done, stream));
+			AGB_CUDA_CHECK(e, cudaStreamWaitEvent(tail_stream, trunk_done, 0));
+			stream = tail_stream;
+		}
 		value_head_kernel<<<std::min((n_boards + kValueBoards - 1) / kValueBoards, 4 * sms), 256, kValueBoards * (cells * 4 + D) * 4, stream>>>(n->d_value_hidden, n->d_wd1, n->d_bd1, n->d_wd2,
 				n->d_bd2, value_dev, n_boards, cells * 4, D, n_dev, gather_dev, slot_base);
 		e->launches++;
@@ -970,9 +976,9 @@ namespace agb
 		return net_forward_impl(e, features_dev, n_boards, nullptr, nullptr, policy_dev, value_dev, q_dev);
 	}
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
-			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms)
+			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms, cudaStream_t tail_stream, cudaEvent_t trunk_done)
 	{
-		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev, slot_base, stream, max_sms);
+		return net_forward_impl(e, features_dev, max_boards, count_dev, gather_dev, policy_dev, value_dev, q_dev, slot_base, stream, max_sms, tail_stream, trunk_done);
 	}
 }
 

@@ -1586,7 +1586,7 @@ namespace agb
 	}
 
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
-			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms);
+			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms, cudaStream_t tail_stream, cudaEvent_t trunk_done);
 
 	int selfplay_create(AgbEngine *e)
 	{
@@ -1691,7 +1691,7 @@ namespace agb
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
 			s->solver_sms = 0;
 			if (s->groups > 1 and c.solver_max_positions > 1 and c.solver_sms >= 0)
-				s->solver_sms = (c.solver_sms > 0 ? std::min(c.solver_sms, sms - 2) : sms * 20 / 148) & ~1;
+				s->solver_sms = (c.solver_sms > 0 ? std::min(c.solver_sms, sms - 2) : sms * 24 / 148) & ~1;
 			s->net_sms = s->solver_sms > 0 ? sms - s->solver_sms : 0;
 		}
 		if (s->groups > kMaxGroups or s->groups > c.games)
@@ -2077,37 +2077,35 @@ extern "C"
 						return rc;
 				}
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[1], gs));
+				const bool sym = p.use_symmetries != 0;
+				const size_t off = static_cast<size_t>(p.slot_base);
+				// Only K4 itself goes on the network stream; what surrounds it (augment before, dense value layers and inverse symmetries after)
+				// stays on the group's stream, so that with several groups one K4 launch follows the other without a gap.
+				if (sym)
+				{ // NNEvaluator::pack_to_network: features.augment(symmetry), over all slots of the group
+					rc = launch_augment(e, s->features + off * s->cells, s->features_aug + off * s->cells, s->task_sym + off, max_tasks, gs);
+					if (rc != AGB_OK)
+						return rc;
+				}
 				if (groups > 1)
 				{
 					AGB_CUDA_CHECK(e, cudaEventRecord(s->ready[k], gs));
 					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(ns, s->ready[k], 0));
 				}
-				const bool sym = p.use_symmetries != 0;
-				const size_t off = static_cast<size_t>(p.slot_base);
-				if (sym)
-				{ // NNEvaluator::pack_to_network: features.augment(symmetry), over all slots of the group
-					rc = launch_augment(e, s->features + off * s->cells, s->features_aug + off * s->cells, s->task_sym + off, max_tasks, ns);
-					if (rc != AGB_OK)
-						return rc;
-				}
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[2], ns));
 				rc = net_forward_dev_gather(e, sym ? s->features_aug : s->features, p.solver_mode != 0 ? nn_count : p.eval_count,
-						p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr, max_tasks, sym ? s->policy_raw : s->policy, s->value, sym ? s->q_raw : s->q, p.slot_base, ns, s->net_sms);
+						p.solver_mode != 0 ? s->nn_list + p.slot_base : nullptr, max_tasks, sym ? s->policy_raw : s->policy, s->value, sym ? s->q_raw : s->q, p.slot_base, ns, s->net_sms,
+						gs, s->evaluated[k]);
 				if (rc != AGB_OK)
 					return rc;
 				AGB_CUDA_CHECK(e, cudaEventRecord(ev[3], ns));
 				if (sym)
 				{ // unpack_from_network: the inverse symmetry on the policy and the action values
-					rc = launch_symmetry_f32(e, s->policy_raw + off * s->cells, s->policy + off * s->cells, s->task_sym + off, max_tasks, 1, true, ns);
+					rc = launch_symmetry_f32(e, s->policy_raw + off * s->cells, s->policy + off * s->cells, s->task_sym + off, max_tasks, 1, true, gs);
 					if (rc == AGB_OK and e->cfg.q_head)
-						rc = launch_symmetry_f32(e, s->q_raw + off * s->cells * 3, s->q + off * s->cells * 3, s->task_sym + off, max_tasks, 3, true, ns);
+						rc = launch_symmetry_f32(e, s->q_raw + off * s->cells * 3, s->q + off * s->cells * 3, s->task_sym + off, max_tasks, 3, true, gs);
 					if (rc != AGB_OK)
 						return rc;
-				}
-				if (groups > 1)
-				{
-					AGB_CUDA_CHECK(e, cudaEventRecord(s->evaluated[k], ns));
-					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(gs, s->evaluated[k], 0));
 				}
 				expand_backup_kernel<<<grid, 128, 0, gs>>>(p);
 				make_move_kernel<<<grid, 128, 0, gs>>>(p);

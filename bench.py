@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--games", type=int, default=GAMES)
     ap.add_argument("--batch", type=int, default=BATCH, help="SearchConfig::max_batch_size (leaves per game and step)")
     ap.add_argument("--groups", type=int, default=0, help="AgbConfig::pipeline_groups (0 = engine default: 2 with the alpha-beta solver on)")
-    ap.add_argument("--solver-sms", type=int, default=0, help="AgbConfig::solver_sms (0 = engine default: 20 of 148 SMs, -1 = no partition)")
+    ap.add_argument("--solver-sms", type=int, default=0, help="AgbConfig::solver_sms (0 = engine default: 24 of 148 SMs, -1 = no partition)")
     ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
     ap.add_argument("--workload", default="standard15", choices=sorted(WORKLOADS), help="standard15 = BASELINE.json configs[1] (the headline)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -322,7 +322,7 @@ def main():
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
         total_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         groups_eff = args.groups if args.groups > 0 else (2 if args.solver > 1 and games >= 1024 else 1)
-        partition_sms = 0 if (groups_eff < 2 or args.solver <= 1 or args.solver_sms < 0) else ((args.solver_sms or total_sms * 20 // 148) & ~1)
+        partition_sms = 0 if (groups_eff < 2 or args.solver <= 1 or args.solver_sms < 0) else ((args.solver_sms or total_sms * 24 // 148) & ~1)
         achieved = (FLOP_PER_POSITION * nn_positions / max(nn_launches, 1)) / (nn_ns / max(nn_launches, 1) * 1e-9) / 1e12 if nn_ns else None
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r01_k4_ncu_summary.json")

@@ -106,7 +106,7 @@ typedef struct AgbConfig
 	                             negative = the reference's temperature 0 (one-hot on the best move) */
 	int32_t solver_sms; /* with 2..4 pipeline groups and the alpha-beta solver: SMs the solver kernel runs on while the network kernel takes the
 	                       others (side by side, not sharing SMs: the solver is bound by instruction supply, the network by the tensor pipe, and
-	                       on a shared SM both lose). 0 = automatic (20 of 148), -1 = no partition. Even; ignored with one group */
+	                       on a shared SM both lose). 0 = automatic (24 of 148), -1 = no partition. Even; ignored with one group */
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
