@@ -188,6 +188,39 @@ def test_random_evaluation_symmetries():
     shard.close()
 
 
+def test_scheduling_of_solver_and_network_is_invisible():
+    """AgbConfig::pipeline_groups / solver_sms only decide where and when K5 and K4 run (groups of games on their own streams, the solver on
+    its own SMs beside the network kernel): roots, finished-game records and counters must not depend on them."""
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob, dataset
+    size, games, blocks, filters = 15, 96, 2, 64
+    blob = netblob.pack(netblob.random_tensors(size, size, blocks, filters, False, seed=21), size, size, blocks, filters, False)
+    rng = np.random.default_rng(321)
+    boards, stm = _openings(rng, size, games)
+    results = []
+    for kwargs in (dict(pipeline_groups=1), dict(pipeline_groups=2), dict(pipeline_groups=3, solver_sms=8), dict(pipeline_groups=2, solver_sms=-1),
+                   dict(pipeline_groups=4, solver_sms=146)):
+        eng = agb.Engine(agb.GameConfig(agb.GameRules.RENJU, size, size, 40), max_boards=games * 4, blocks=blocks, filters=filters, games=games,
+                         max_batch_size=4, max_simulations=40, solver_max_positions=60, use_symmetries=True, seed=3, **kwargs)
+        eng.load_weights(blob)
+        eng.selfplay_reset(boards, stm)
+        eng.step(60)
+        eng.step(45)
+        records, n = eng.pop_finished()
+        roots = [eng.get_root(g) for g in range(games)]
+        st = eng.stats()
+        assert st["overflow_flags"] == 0
+        records = sorted(dataset.split_records(records, n))  # games of different groups finish in any order
+        results.append((records, n, roots, {k: st[k] for k in ("nb_network_evaluations", "nb_node_count", "nb_proven_states", "nb_moves_played", "nb_games_finished")}))
+        eng.close()
+    base = results[0]
+    assert base[1] >= 1 and base[3]["nb_proven_states"] > 0
+    for other in results[1:]:
+        assert other[0] == base[0] and other[1] == base[1] and other[3] == base[3]
+        for a, b in zip(base[2], other[2]):
+            assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all() and a[4] == b[4]
+
+
 def test_save_and_resume_games_in_flight():
     """GeneratorManager::saveState / loadState: positions, move lists and recorded samples survive; trees are rebuilt. A resumed engine
     writes the same blob back, continues, and its finished records start with the samples recorded before the save."""
