@@ -32,7 +32,7 @@ class AgbStats(ctypes.Structure):
         ("nb_information_leaks", ctypes.c_uint64), ("nb_proven_states", ctypes.c_uint64), ("nb_wasted_expansions", ctypes.c_uint64),
         ("nb_moves_played", ctypes.c_uint64), ("nb_games_finished", ctypes.c_uint64), ("nb_kernel_launches", ctypes.c_uint64),
         ("overflow_flags", ctypes.c_uint64), ("nn_kernel_ns", ctypes.c_uint64), ("nn_kernel_launches", ctypes.c_uint64),
-        ("nn_positions", ctypes.c_uint64), ("solver_kernel_ns", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 2),
+        ("nn_positions", ctypes.c_uint64), ("solver_kernel_ns", ctypes.c_uint64), ("solver_sms", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 1),
     ]
 
 

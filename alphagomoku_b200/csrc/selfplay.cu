@@ -1691,7 +1691,7 @@ namespace agb
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
 			s->solver_sms = 0;
 			if (s->groups > 1 and c.solver_max_positions > 1 and c.solver_sms >= 0)
-				s->solver_sms = (c.solver_sms > 0 ? std::min(c.solver_sms, sms - 2) : sms * 24 / 148) & ~1;
+				s->solver_sms = (c.solver_sms > 0 ? std::min(c.solver_sms, sms - 2) : sms * 28 / 148) & ~1;
 			s->net_sms = s->solver_sms > 0 ? sms - s->solver_sms : 0;
 		}
 		if (s->groups > kMaxGroups or s->groups > c.games)
@@ -2124,13 +2124,31 @@ extern "C"
 		unsigned long long evals_after = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&evals_after, s->stats + ST_EVALS, 8, cudaMemcpyDeviceToHost, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		double call_nn_ms = 0.0, call_solver_ms = 0.0;
 		for (int i = 0; i < n_steps * groups; i++)
 		{ // device time of the network kernels (K4 + value head) and of the solver kernel (K5) of this call
 			float ms = 0.0f;
 			if (cudaEventElapsedTime(&ms, e->events[4 * i + 2], e->events[4 * i + 3]) == cudaSuccess)
+			{
 				e->nn_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
+				call_nn_ms += ms;
+			}
 			if (e->cfg.solver_max_positions > 0 and cudaEventElapsedTime(&ms, e->events[4 * i], e->events[4 * i + 1]) == cudaSuccess)
+			{
 				e->solver_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
+				call_solver_ms += ms;
+			}
+		}
+		if (s->solver_sms > 0 and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0)
+		{ // automatic partition: both kernels scale with their SMs, so split the SMs in proportion to the SM-time each needed in this
+		  // call (K5 and K4 launches then take equally long); move three quarters of the way, in whole TPCs. Results do not depend on it.
+			const int sms = s->solver_sms + s->net_sms;
+			const double solver_work = call_solver_ms * s->solver_sms, net_work = call_nn_ms * s->net_sms;
+			const double target = sms * solver_work / (solver_work + net_work);
+			int next = static_cast<int>(s->solver_sms + 0.75 * (target - s->solver_sms) + 0.5) & ~1;
+			next = std::max(8, std::min(next, sms / 2));
+			s->solver_sms = next;
+			s->net_sms = sms - next;
 		}
 		if (const char *trace = getenv("AGB_STEP_TRACE"))
 		{ // diagnostics: when each group's solver and network phases ran, in ms from the first event of the call
@@ -2190,6 +2208,7 @@ extern "C"
 		stats->nn_kernel_launches = e->nn_kernel_launches;
 		stats->nn_positions = e->nn_positions;
 		stats->solver_kernel_ns = e->solver_kernel_ns;
+		stats->solver_sms = (e->selfplay != nullptr) ? static_cast<uint64_t>(e->selfplay->solver_sms) : 0;
 		if (e->selfplay != nullptr)
 		{
 			unsigned long long h[16];

@@ -202,9 +202,10 @@ def main():
     ap.add_argument("--games", type=int, default=GAMES)
     ap.add_argument("--batch", type=int, default=BATCH, help="SearchConfig::max_batch_size (leaves per game and step)")
     ap.add_argument("--groups", type=int, default=0, help="AgbConfig::pipeline_groups (0 = engine default: 2 with the alpha-beta solver on)")
-    ap.add_argument("--solver-sms", type=int, default=0, help="AgbConfig::solver_sms (0 = engine default: 24 of 148 SMs, -1 = no partition)")
+    ap.add_argument("--solver-sms", type=int, default=0, help="AgbConfig::solver_sms (0 = engine default: 28 of 148 SMs, -1 = no partition)")
     ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
     ap.add_argument("--workload", default="standard15", choices=sorted(WORKLOADS), help="standard15 = BASELINE.json configs[1] (the headline)")
+    ap.add_argument("--shard", type=int, default=0, help="play the games rank SHARD of a larger job would play (openings, game ids); for variance checks")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -229,12 +230,12 @@ def main():
     nodes_per_game = 1536 * SIMS // 400  # the tree of one move plus the subtree kept from the previous one
     eng = agb.Engine(agb.GameConfig(agb.GameRules(RULES), SIZE, SIZE), max_boards=games * args.batch, device=local_rank, blocks=BLOCKS, filters=FILTERS,
                      q_head=False, games=games, max_batch_size=args.batch, max_simulations=SIMS, init_to="parent", max_nodes_per_game=nodes_per_game,
-                     max_edges_per_game=nodes_per_game * 200, seed=1234, first_game_id=rank * games, solver_max_positions=args.solver,
+                     max_edges_per_game=nodes_per_game * 200, seed=1234, first_game_id=(rank + args.shard) * games, solver_max_positions=args.solver,
                      solver_table_entries=SOLVER_TABLE_ENTRIES, pipeline_groups=args.groups, solver_sms=args.solver_sms, use_symmetries=True)
     # C1: rank 0 owns the weights and broadcasts them over NCCL (NetworkLoader::get per thread in the reference)
     blob = netblob.pack(netblob.random_tensors(SIZE, SIZE, BLOCKS, FILTERS, False), SIZE, SIZE, BLOCKS, FILTERS, False) if rank == 0 else None
     eng.load_weights(sharding.broadcast_weights(blob))
-    rng = np.random.default_rng(99 + rank)
+    rng = np.random.default_rng(99 + rank + args.shard)
     boards, stm = random_openings(rng, games)
     eng.selfplay_reset(boards, stm)
 
@@ -322,7 +323,7 @@ def main():
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
         total_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         groups_eff = args.groups if args.groups > 0 else (2 if args.solver > 1 and games >= 1024 else 1)
-        partition_sms = 0 if (groups_eff < 2 or args.solver <= 1 or args.solver_sms < 0) else ((args.solver_sms or total_sms * 24 // 148) & ~1)
+        partition_sms = int(st0["solver_sms"])  # as the timed call ran (the automatic mode re-balances after each agb_step call)
         achieved = (FLOP_PER_POSITION * nn_positions / max(nn_launches, 1)) / (nn_ns / max(nn_launches, 1) * 1e-9) / 1e12 if nn_ns else None
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r01_k4_ncu_summary.json")
@@ -336,7 +337,7 @@ def main():
                                          if partition_sms > 0 else f"{groups_eff} groups of games, no SM partition")),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * (SIZE * SIZE + 1)), "d2h_bytes_per_step": int(n_e2e * (SIZE * SIZE + 3) * 4),
                         "api": "agb_evaluate (NNEvaluator::evaluateGraph drop-in): pinned host boards -> K1+K3+K4 -> host policy/value"},
-                "gpu_launches": int(sums[4]), "overflow_flags": int(st1["overflow_flags"]),
+                "gpu_launches": int(sums[4]), "overflow_flags": int(st1["overflow_flags"]), "solver_sms_during_timed_steps": int(st0["solver_sms"]),
                 "roofline": {"bound": "tensor", "kernel": "resnet_board_kernel (+ value head)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                              "note": ("K4 timed alone on all SMs" if partition_sms == 0 else

@@ -106,7 +106,8 @@ typedef struct AgbConfig
 	                             negative = the reference's temperature 0 (one-hot on the best move) */
 	int32_t solver_sms; /* with 2..4 pipeline groups and the alpha-beta solver: SMs the solver kernel runs on while the network kernel takes the
 	                       others (side by side, not sharing SMs: the solver is bound by instruction supply, the network by the tensor pipe, and
-	                       on a shared SM both lose). 0 = automatic (24 of 148), -1 = no partition. Even; ignored with one group */
+	                       on a shared SM both lose). 0 = automatic (starts at 28 of 148 and follows the measured launch times of the two kernels),
+	                       -1 = no partition. Even; ignored with one group */
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -231,7 +232,9 @@ typedef struct AgbStats
 	uint64_t nn_kernel_launches;
 	uint64_t nn_positions; /* positions those launches evaluated */
 	uint64_t solver_kernel_ns; /* total CUDA-event time of the solver kernel (K5) launches issued by agb_step */
-	uint64_t reserved[2];
+	uint64_t solver_sms; /* SMs the solver kernel currently runs on (AgbConfig::solver_sms; 0 = no partition). In automatic mode the engine
+	                        re-balances it after every agb_step call from the measured K5 and K4 launch times */
+	uint64_t reserved[1];
 } AgbStats;
 int agb_get_stats(AgbEngine *engine, AgbStats *stats);
 
