@@ -302,6 +302,21 @@ def main():
         k1()
     k1_end.record(stream)
     k1_end.synchronize()
+    # K4 (+ value head) alone on all SMs, on the same boards: the kernel's own roofline point, measured live next to the in-step one
+    d_policy = torch.empty((n_e2e, SIZE * SIZE), dtype=torch.float32, device="cuda")
+    d_value = torch.empty((n_e2e, 3), dtype=torch.float32, device="cuda")
+
+    def k4():
+        assert lib.agb_forward_dev(eng._h, ctypes.c_void_p(d_feat.data_ptr()), n_e2e, ctypes.c_void_p(d_policy.data_ptr()), ctypes.c_void_p(d_value.data_ptr()), None) == 0
+
+    k4()
+    k4_start, k4_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k4_start.record(stream)
+    for _ in range(3):
+        k4()
+    k4_end.record(stream)
+    k4_end.synchronize()
+    k4_alone_ms = k4_start.elapsed_time(k4_end) / 3
     solver_ns = st1["solver_kernel_ns"] - st0["solver_kernel_ns"]
     device_integer_path = {"set_board_and_encode_per_s": 5 * n_e2e / (k1_start.elapsed_time(k1_end) * 1e-3),
                            "solve_100_positions_per_s": ((st1["nb_node_count"] - st0["nb_node_count"]) / (solver_ns * 1e-9)) if solver_ns else None,
@@ -343,8 +358,11 @@ def main():
                              "note": ("K4 timed alone on all SMs" if partition_sms == 0 else
                                       f"K4 runs on {total_sms - partition_sms} of {total_sms} SMs, side by side with K5 on the other {partition_sms}; frac is against the "
                                       f"whole GPU's peak ({achieved / (peak * (total_sms - partition_sms) / total_sms):.3f} of its own SMs' share); "
-                                      f"alone on all SMs (--groups 1, profiles/r01_bench_n1_groups1.json) it reaches 0.85"),
+                                      f"alone on all SMs it reaches the fraction under 'alone' (also --groups 1, profiles/r01_bench_n1_groups1.json)"),
                              "positions_per_launch": nn_positions / max(nn_launches, 1), "ms_per_launch": nn_ns / max(nn_launches, 1) * 1e-6,
+                             "alone": {"what": "the same kernel (+ value head) alone on all SMs, agb_forward_dev on device-resident features, CUDA events on its stream",
+                                       "positions_per_launch": n_e2e, "ms_per_launch": k4_alone_ms, "achieved": FLOP_PER_POSITION * n_e2e / (k4_alone_ms * 1e-3) / 1e12,
+                                       "frac": FLOP_PER_POSITION * n_e2e / (k4_alone_ms * 1e-3) / 1e12 / peak},
                              "share_of_step": (nn_ns * 1e-6) / ms, "solver_share_of_step": (st1["solver_kernel_ns"] - st0["solver_kernel_ns"]) * 1e-6 / ms,
                              "leaf_positions_per_step": (st1["nb_node_count"] - st0["nb_node_count"]) / args.steps},
                 "sharding": {"c1_weight_bytes_broadcast": int(blob.nbytes), "c2_record_bytes_gathered": int(c2_bytes), "ranks": world},
