@@ -188,12 +188,13 @@ def test_random_evaluation_symmetries():
     shard.close()
 
 
-def test_scheduling_of_solver_and_network_is_invisible():
+@pytest.mark.parametrize("games", [96, 50])
+def test_scheduling_of_solver_and_network_is_invisible(games):
     """AgbConfig::pipeline_groups / solver_sms only decide where and when K5 and K4 run (groups of games on their own streams, the solver on
     its own SMs beside the network kernel): roots, finished-game records and counters must not depend on them."""
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob, dataset
-    size, games, blocks, filters = 15, 96, 2, 64
+    size, blocks, filters = 15, 2, 64  # 50 games: groups of unequal size
     blob = netblob.pack(netblob.random_tensors(size, size, blocks, filters, False, seed=21), size, size, blocks, filters, False)
     rng = np.random.default_rng(321)
     boards, stm = _openings(rng, size, games)
@@ -214,7 +215,7 @@ def test_scheduling_of_solver_and_network_is_invisible():
         results.append((records, n, roots, {k: st[k] for k in ("nb_network_evaluations", "nb_node_count", "nb_proven_states", "nb_moves_played", "nb_games_finished")}))
         eng.close()
     base = results[0]
-    assert base[1] >= 1 and base[3]["nb_proven_states"] > 0
+    assert (base[1] >= 1 or games < 96) and base[3]["nb_proven_states"] > 0 and base[3]["nb_moves_played"] > games
     for other in results[1:]:
         assert other[0] == base[0] and other[1] == base[1] and other[3] == base[3]
         for a, b in zip(base[2], other[2]):
