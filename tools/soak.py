@@ -30,8 +30,13 @@ for chunk in range(steps // 100):
     total_bytes += len(blob)
     for rec in dataset.split_records(blob, n)[:50]:
         lengths.append(len(dataset.parse_record(rec)["moves"]))
+    prev = st if chunk > 0 else None
     st = eng.stats()
     assert st["overflow_flags"] == 0, st
+    if prev is not None:
+        print(f"  last 100 steps: K4 {(st['nn_kernel_ns'] - prev['nn_kernel_ns']) / 1e8:.1f} ms/step in {(st['nn_kernel_launches'] - prev['nn_kernel_launches']) / 100:.0f} launches, "
+              f"K5 {(st['solver_kernel_ns'] - prev['solver_kernel_ns']) / 1e8:.1f} ms/step, network positions {(st['nn_positions'] - prev['nn_positions']) / 100:.0f}/step, "
+              f"solver SMs now {st['solver_sms']}")
     print(f"step {(chunk + 1) * 100}: evals {st['nb_network_evaluations']} moves {st['nb_moves_played']} finished {st['nb_games_finished']} popped {total_games} "
           f"({total_bytes / 1e6:.1f} MB) proven {st['nb_proven_states']} leaks {st['nb_information_leaks']} t={time.time() - t0:.0f}s", flush=True)
 print("game length (sample): mean", np.mean(lengths) if lengths else None, "max", max(lengths) if lengths else None)
