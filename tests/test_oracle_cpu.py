@@ -142,6 +142,29 @@ def test_open_three_promotions_match_reference(ref, hostsim):
     assert checked > 100
 
 
+def test_ctypes_structures_match_the_header(tmp_path):
+    """The ctypes mirror of AgbConfig / AgbStats (alphagomoku_b200/_lib.py) has the size and the field offsets the C compiler gives the header."""
+    import ctypes
+    import subprocess
+    from alphagomoku_b200 import _lib
+    probes = [("AgbConfig", _lib.AgbConfig), ("AgbStats", _lib.AgbStats)]
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "agb200.h"', "int main(void) {"]
+    for cname, cls in probes:
+        src.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            src.append(f'printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    src += ["return 0; }"]
+    c_file = tmp_path / "abi.c"
+    c_file.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c_file), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in probes:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert int(out[f"{cname}.{field}"]) == getattr(cls, field).offset, (cname, field)
+
+
 def test_c_abi_exports_every_declared_symbol():
     from alphagomoku_b200 import _lib
     header = open(os.path.join(ROOT, "include", "agb200.h")).read()
