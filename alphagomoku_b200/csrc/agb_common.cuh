@@ -30,6 +30,9 @@ namespace agb
 	// ThreatType, ThreatTable.hpp:18-30
 	enum : int { TT_NONE = 0, TT_HALF_OPEN_3, TT_OPEN_3, TT_FORK_3x3, TT_HALF_OPEN_4, TT_FORK_4x3, TT_FORK_4x4, TT_OPEN_4, TT_FIVE, TT_OVERLINE };
 	enum : int { RULE_FREESTYLE = 0, RULE_STANDARD, RULE_RENJU, RULE_CARO5, RULE_CARO6 };
+	// bit of the device status word: a kernel met input it cannot use (a cell that is not a Sign, a move onto an occupied or off-board cell,
+	// an undo of a stone that is not there); the offending slot is left alone and the host call fails with AGB_EINVAL
+	constexpr uint32_t kStatusBadInput = 1u << 12;
 
 	// Device views of the static tables (built once per engine by tables.cu)
 	struct Tables

@@ -19,10 +19,36 @@ namespace
 	int check_status(AgbEngine *e)
 	{ // surfaces device-side overflows of bounded structures (never silent)
 		uint32_t status = 0;
-		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, sizeof(status), cudaMemcpyDeviceToHost, e->stream));
-		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		const int rc = agb::take_status(e, &status);
+		if (rc != AGB_OK)
+			return rc;
+		if (status & agb::kStatusBadInput)
+			return e->fail(AGB_EINVAL, "invalid input reached the device: a board cell outside 0..2, a sign to move outside 1..2, or a move that does not fit "
+					"its position (occupied or off-board cell, undo of an absent stone); the offending slots were left unchanged");
 		if (status != 0)
 			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status));
+		return AGB_OK;
+	}
+}
+
+namespace agb
+{
+	// host-side validation of caller buffers (the reference asserts on these; here a bad value would index device arrays out of range)
+	int validate_boards(AgbEngine *e, const int8_t *boards, const int8_t *sign_to_move, size_t n)
+	{
+		const size_t cells = static_cast<size_t>(e->cells);
+		unsigned bad = 0;
+		for (size_t i = 0; i < n * cells; i++)
+			bad |= static_cast<unsigned>(static_cast<uint8_t>(boards[i]) > 2u);
+		if (bad)
+			return e->fail(AGB_EINVAL, "board cells must be 0 (empty), 1 (cross) or 2 (circle)");
+		if (sign_to_move != nullptr)
+		{
+			for (size_t i = 0; i < n; i++)
+				bad |= static_cast<unsigned>(sign_to_move[i] != 1 and sign_to_move[i] != 2);
+			if (bad)
+				return e->fail(AGB_EINVAL, "sign_to_move must be 1 (cross) or 2 (circle)");
+		}
 		return AGB_OK;
 	}
 }
@@ -219,6 +245,7 @@ extern "C"
 		if (n == 0)
 			return AGB_OK;
 		const size_t cells = e->cells;
+		AGB_TRY(agb::validate_boards(e, boards_host, sign_to_move_host, n));
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8, boards_host, n * cells, cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8b, sign_to_move_host, n, cudaMemcpyHostToDevice, e->stream));
 		AGB_TRY(agb::launch_set_boards(e, e->d_io8, e->d_io8b, n, e->d_features));
@@ -231,10 +258,16 @@ extern "C"
 		AGB_REQUIRE(e, moves_host, "null pointer");
 		if (n == 0)
 			return AGB_OK;
+		for (int i = 0; i < n; i++)
+		{ // Move::toShort: sign | row << 2 | col << 9; sign 0 skips the slot
+			const int sign = moves_host[i] & 3, row = (moves_host[i] >> 2) & 127, col = (moves_host[i] >> 9) & 127;
+			if (sign == 3 or (sign != 0 and (row >= e->cfg.rows or col >= e->cfg.cols)))
+				return e->fail(AGB_EINVAL, "move " + std::to_string(i) + " is not on the board (sign " + std::to_string(sign) + ", row " + std::to_string(row)
+						+ ", col " + std::to_string(col) + ")");
+		}
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io16, moves_host, n * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
 		AGB_TRY(agb::launch_add_undo(e, e->d_io16, n, undo));
-		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
-		return AGB_OK;
+		return check_status(e); // occupied cell / absent stone is found on the device
 	}
 	int agb_add_moves(AgbEngine *e, const uint16_t *moves_host, int n)
 	{
@@ -331,6 +364,9 @@ extern "C"
 		AGB_REQUIRE(e, boards_host and last_moves_host and outcomes_host, "null pointer");
 		if (n == 0)
 			return AGB_OK;
+		AGB_TRY(agb::validate_boards(e, boards_host, nullptr, n));
+		for (int i = 0; i < n; i++)
+			AGB_REQUIRE(e, ((last_moves_host[i] >> 2) & 127) < e->cfg.rows and ((last_moves_host[i] >> 9) & 127) < e->cfg.cols, "last move is not on the board");
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8, boards_host, static_cast<size_t>(n) * e->cells, cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io16, last_moves_host, n * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
 		AGB_TRY(agb::launch_outcomes(e, e->d_io8, e->d_io16, n, e->d_io8b));

@@ -40,7 +40,8 @@ struct AgbEngine
 		int8_t *d_io8 = nullptr; // [max_boards][cells] staging
 		int8_t *d_io8b = nullptr; // [max_boards]
 		uint16_t *d_io16 = nullptr; // [max_boards]
-		uint32_t *d_status = nullptr; // device overflow / error word
+		uint32_t *d_status = nullptr; // device overflow / error word (cleared every time it is reported, see take_status)
+		uint32_t overflow_seen = 0; // every flag reported since creation or the last agb_selfplay_reset / agb_load_games (AgbStats::overflow_flags)
 
 		agb::NetWeights *net = nullptr;
 		agb::SelfplayState *selfplay = nullptr;
@@ -58,6 +59,21 @@ struct AgbEngine
 
 namespace agb
 {
+	// Reads the device status word on the engine's stream and clears it, so that one overflow is reported once and the engine stays
+	// usable afterwards (the flags stay visible in AgbStats::overflow_flags). Synchronises the stream.
+	inline int take_status(AgbEngine *e, uint32_t *status)
+	{
+		*status = 0;
+		cudaError_t err = cudaMemcpyAsync(status, e->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream);
+		if (err == cudaSuccess)
+			err = cudaMemsetAsync(e->d_status, 0, sizeof(uint32_t), e->stream);
+		if (err == cudaSuccess)
+			err = cudaStreamSynchronize(e->stream);
+		if (err != cudaSuccess)
+			return e->fail(AGB_ECUDA, std::string("status word: ") + cudaGetErrorString(err));
+		e->overflow_seen |= *status;
+		return AGB_OK;
+	}
 	// per-slot outputs of the solver (K5)
 	struct SolverOutputs
 	{
@@ -91,6 +107,8 @@ namespace agb
 			int32_t *next = nullptr; // [games] work-queue heads, one per launch range (indexed by its first game)
 			const uint16_t *def_table = nullptr;
 	};
+	// capi.cu: caller-supplied boards hold only Sign values 0..2 and sign_to_move (may be NULL) only 1..2, else AGB_EINVAL
+	int validate_boards(AgbEngine *e, const int8_t *boards, const int8_t *sign_to_move, size_t n);
 	// solver.cu
 	int solver_create(AgbEngine *e);
 	int solver_state_create(AgbEngine *e, int games, int batch, SolverState *st);

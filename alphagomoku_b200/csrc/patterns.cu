@@ -74,10 +74,17 @@ namespace agb
 				const size_t cell_base = static_cast<size_t>(b) * kCellPitch;
 				for (int i = lane; i < cells; i += 32)
 				{
-					const int8_t v = boards[static_cast<size_t>(b) * cells + i];
+					int8_t v = boards[static_cast<size_t>(b) * cells + i];
+					if (v < NONE or v > CIRCLE)
+					{ // not a Sign a board can hold: reported (kStatusBadInput), treated as empty so that nothing is indexed out of range
+						atomicOr(status, kStatusBadInput);
+						v = NONE;
+					}
 					ws.board[i] = v;
 					store.board[cell_base + i] = v;
 				}
+				if (lane == 0 and stm != CROSS and stm != CIRCLE)
+					atomicOr(status, kStatusBadInput);
 				if (lane < 2 * kHistTypes)
 					ws.hist_base[lane / kHistTypes][lane % kHistTypes] = 0;
 				if (lane == 0)
@@ -204,7 +211,7 @@ namespace agb
 		}
 
 		__global__ void __launch_bounds__(kWarpsPerBlock * 32) add_undo_kernel(BoardStore store, Tables tables, const uint16_t *__restrict__ moves, int n,
-				int S, int undo)
+				int S, int undo, uint32_t *status)
 		{
 			const int lane = threadIdx.x & 31;
 			const int warp = threadIdx.x >> 5;
@@ -217,6 +224,13 @@ namespace agb
 				const int r = (mv >> 2) & 127, c = (mv >> 9) & 127;
 				const size_t cell_base = static_cast<size_t>(b) * kCellPitch;
 				const int centre = r * S + c;
+				// the reference asserts on these (PatternCalculator.cpp:70, 89); here the slot is left untouched and the call fails
+				if (sign == ILLEGAL or r >= S or c >= S or store.board[cell_base + (r < S and c < S ? centre : 0)] != (undo ? sign : NONE))
+				{
+					if (lane == 0)
+						atomicOr(status, kStatusBadInput);
+					continue;
+				}
 
 				// the four lines through the move: lanes 0..3 own one each (RawPatternCalculator::addMove / undoMove)
 				uint64_t line = 0;
@@ -437,7 +451,7 @@ namespace agb
 	}
 	int launch_add_undo(AgbEngine *e, const uint16_t *moves_dev, int n, bool undo)
 	{
-		add_undo_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, moves_dev, n, e->cfg.rows, undo ? 1 : 0);
+		add_undo_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, e->stream>>>(e->store, e->tables, moves_dev, n, e->cfg.rows, undo ? 1 : 0, e->d_status);
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		return AGB_OK;

@@ -1018,6 +1018,9 @@ extern "C"
 			return e->fail(AGB_ESTATE, "no weights loaded");
 		const size_t cells = e->cells;
 		const bool want_q = (q_host != nullptr and e->cfg.q_head);
+		const int rc_valid = agb::validate_boards(e, boards_host, sign_to_move_host, static_cast<size_t>(n));
+		if (rc_valid != AGB_OK)
+			return rc_valid;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8, boards_host, n * cells, cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8b, sign_to_move_host, n, cudaMemcpyHostToDevice, e->stream));
 		int rc = agb::launch_set_boards(e, e->d_io8, e->d_io8b, n, e->d_features); // pack: K1 + K3

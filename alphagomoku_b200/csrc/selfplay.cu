@@ -1208,8 +1208,16 @@ namespace agb
 			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
 			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
 			const int root = p.s.root_node[g];
-			if (root < 0 or p.s.paused[g])
+			// paused 2: the game is over but its record did not fit the finished-game queue; it waits, with its record, until the host has
+			// popped (agb_pop_finished) and is published by the first make-move pass that finds room
+			const bool republish = p.s.paused[g] == 2;
+			if (not republish and (root < 0 or p.s.paused[g]))
 				return;
+			int8_t *board = p.s.root_board + static_cast<size_t>(g) * cells;
+			uint64_t *bits = p.s.root_bits + static_cast<size_t>(g) * kBitWords;
+			int outcome = republish ? p.s.outcome[g] : 0;
+			if (not republish)
+			{
 			const NodeD R = nodes[root];
 			// GameGenerator.cpp:95-101: fewer simulations when the root is drawish
 			const float reduction = fminf(1.0f, fmaxf(0.0f, (R.draw - 0.75f) / (1.0f - 0.75f)));
@@ -1302,8 +1310,6 @@ namespace agb
 			// game.makeMove
 			const int row = (chosen.move >> 2) & 127, col = (chosen.move >> 9) & 127, sign = chosen.move & 3;
 			const int cell = row * S + col;
-			int8_t *board = p.s.root_board + static_cast<size_t>(g) * cells;
-			uint64_t *bits = p.s.root_bits + static_cast<size_t>(g) * kBitWords;
 			__syncwarp();
 			if (lane == 0)
 			{
@@ -1318,7 +1324,6 @@ namespace agb
 			for (int i = lane; i < cells; i += 32)
 				sboards[warp][i] = board[i];
 			__syncwarp();
-			int outcome = 0;
 			if (lane == 0)
 			{
 				bool overflow = false;
@@ -1327,13 +1332,14 @@ namespace agb
 					atomicOr(p.status, 1u);
 			}
 			outcome = __shfl_sync(kFullMask, outcome, 0);
+			if (outcome != 0 and lane == 0)
+			{
+				p.s.outcome[g] = static_cast<int8_t>(outcome);
+				atomicAdd(p.s.stats + ST_GAMES, 1ull);
+			}
+			} // not republish
 			if (outcome != 0)
 			{ // game over: publish the outcome and start the next game from the openings pool (or an empty board)
-				if (lane == 0)
-				{
-					p.s.outcome[g] = static_cast<int8_t>(outcome);
-					atomicAdd(p.s.stats + ST_GAMES, 1ull);
-				}
 				// GameDataStorage::serialize (GameDataStorage.cpp:217-251): u32 samples, samples, u32 moves + u16[], outcome, rows = cols = 0
 				// (GameGenerator default-constructs its storage, GameGenerator.hpp:39); games without samples are not recorded
 				const int n_samples = p.s.rec_samples[g];
@@ -1342,14 +1348,30 @@ namespace agb
 					const int n_moves = p.s.n_moves[g];
 					const int body = p.s.rec_len[g];
 					const unsigned long long total = static_cast<unsigned long long>(body) + 4 + 2ull * n_moves + 12;
-					unsigned long long dst_off = 0;
+					unsigned long long dst_off = ~0ull;
 					if (lane == 0)
-						dst_off = atomicAdd(p.s.fin_used, total);
+					{ // reserve room, or none at all (the counter never runs past the capacity)
+						unsigned long long seen = *p.s.fin_used;
+						while (seen + total <= p.s.fin_cap)
+						{
+							const unsigned long long prev = atomicCAS(p.s.fin_used, seen, seen + total);
+							if (prev == seen)
+							{
+								dst_off = seen;
+								break;
+							}
+							seen = prev;
+						}
+					}
 					dst_off = __shfl_sync(kFullMask, dst_off, 0);
-					if (dst_off + total > p.s.fin_cap)
-					{
+					if (dst_off == ~0ull)
+					{ // queue full: keep the finished game and its record as they are and wait for the host to pop (reported once, nothing is lost)
 						if (lane == 0)
+						{
+							p.s.paused[g] = 2;
 							atomicOr(p.status, OVF_FINISHED);
+						}
+						return;
 					}
 					else
 					{
@@ -1416,6 +1438,7 @@ namespace agb
 					p.s.n_edges[g] = 0;
 					p.s.rec_len[g] = 4;
 					p.s.rec_samples[g] = 0;
+					p.s.paused[g] = 0;
 					if (p.s.noise_ready != nullptr)
 						p.s.noise_ready[g] = 0;
 					if (p.solver_mode != 0)
@@ -1677,6 +1700,8 @@ namespace agb
 		alloc(&s->rec_len, G);
 		alloc(&s->rec_samples, G);
 		s->fin_cap = static_cast<unsigned long long>(G) * 65536ull + (1ull << 22);
+		if (const char *cap = getenv("AGB_FINISHED_QUEUE_BYTES")) // tests of the queue-full path: a queue that a few games fill
+			s->fin_cap = std::max(1024ull, std::strtoull(cap, nullptr, 10));
 		alloc(&s->fin_buf, s->fin_cap);
 		alloc(&s->fin_used, 1);
 		alloc(&s->fin_games, 1);
@@ -1773,6 +1798,9 @@ extern "C"
 		{
 			if (sign_to_move_host == nullptr)
 				return e->fail(AGB_EINVAL, "sign_to_move is required with boards");
+			const int rc_valid = validate_boards(e, boards_host, sign_to_move_host, G);
+			if (rc_valid != AGB_OK)
+				return rc_valid;
 			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->root_board, boards_host, G * cells, cudaMemcpyHostToDevice, e->stream));
 			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->root_stm, sign_to_move_host, G, cudaMemcpyHostToDevice, e->stream));
 			// the starting positions double as the pool finished games restart from
@@ -1802,6 +1830,8 @@ extern "C"
 			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->task_sym, 0, G * s->batch, e->stream));
 		}
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(e->d_status, 0, 4, e->stream)); // a fresh start: earlier overflows were reported when they happened
+		e->overflow_seen = 0;
 		if (e->cfg.solver_max_positions > 0)
 		{
 			const int rc = solver_state_reset(e, &s->solver);
@@ -1915,6 +1945,9 @@ extern "C"
 		AGB_CUDA_CHECK(e, cudaMemcpy(s->rec_buf, rec.data(), rec.size(), cudaMemcpyHostToDevice));
 		// prepare_search for every game: empty trees, fresh hashes (the solver tables stay, like the reference's)
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(e->d_status, 0, 4, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->paused, 0, G, e->stream));
+		e->overflow_seen = 0;
 		const Params p = make_params(e);
 		reset_games_kernel<<<static_cast<unsigned>((G + 127) / 128), 128, 0, e->stream>>>(p, 1);
 		e->launches++;
@@ -2121,6 +2154,7 @@ extern "C"
 			}
 		uint32_t status = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(e->d_status, 0, 4, e->stream)); // reported once below; the engine stays usable (AgbStats keeps the flags)
 		unsigned long long evals_after = 0;
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(&evals_after, s->stats + ST_EVALS, 8, cudaMemcpyDeviceToHost, e->stream));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
@@ -2169,6 +2203,10 @@ extern "C"
 		}
 		e->nn_kernel_launches += static_cast<uint64_t>(n_steps) * groups;
 		e->nn_positions += evals_after - evals_before;
+		e->overflow_seen |= status;
+		if (status == OVF_FINISHED)
+			return e->fail(AGB_EOVERFLOW, "finished-game queue is full: call agb_pop_finished; the finished games wait with their records (nothing was lost) "
+					"and are published by the next agb_step");
 		if (status != 0)
 			return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status)
 					+ " (1 renju recursion, 2 nodes, 4 edges, 8 path, 16 table, 32 record, 64 finished queue, 256/512 solver forbidden-move recursion/cache, 1024 solver action stack, 2048 solver frames)");
@@ -2219,6 +2257,7 @@ extern "C"
 			uint32_t status = 0;
 			AGB_CUDA_CHECK(e, cudaMemcpyAsync(&status, e->d_status, 4, cudaMemcpyDeviceToHost, e->stream));
 			AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+			status |= e->overflow_seen; // flags already reported (and cleared on the device) stay visible here
 			stats->nb_network_evaluations = h[ST_EVALS];
 			stats->nb_node_count = h[ST_NODES];
 			stats->nb_duplicate_nodes = h[ST_DUP];

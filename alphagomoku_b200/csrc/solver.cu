@@ -345,6 +345,9 @@ extern "C" int agb_solve(AgbEngine *e, const int8_t *boards_host, const int8_t *
 	}
 	SolveScratch *sc = e->solve_scratch;
 	const size_t cells = e->cells;
+	const int rc_valid = validate_boards(e, boards_host, sign_to_move_host, static_cast<size_t>(n));
+	if (rc_valid != AGB_OK)
+		return rc_valid;
 	const int saved = e->cfg.solver_max_positions;
 	for (int begin = 0; begin < n; begin += sc->capacity)
 	{
@@ -383,7 +386,9 @@ extern "C" int agb_solve(AgbEngine *e, const int8_t *boards_host, const int8_t *
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 	}
 	uint32_t status = 0;
-	AGB_CUDA_CHECK(e, cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+	const int rc_status = take_status(e, &status);
+	if (rc_status != AGB_OK)
+		return rc_status;
 	if (status != 0)
 		return e->fail(AGB_EOVERFLOW, "device-side overflow, flags=" + std::to_string(status));
 	return AGB_OK;

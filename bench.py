@@ -37,7 +37,8 @@ FLOP_PER_POSITION = 2 * 1383.70e6  # BASELINE.md section 3 (algorithmic, ResNet 
 
 # --workload: the headline is configs[1]; configs[2] and configs[3] of BASELINE.json can be measured with the same harness (extra lines,
 # e.g. profiles/r01_bench_renju15.json), name -> (label, rules, size, simulations, algorithmic FLOP per position from BASELINE.md section 3)
-WORKLOADS = {"standard15": ("configs[1]: standard 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", 1, 15, 400, 2 * 1383.70e6),
+WORKLOADS = {"freestyle15": ("BASELINE.json metric config: freestyle 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", 0, 15, 400, 2 * 1383.70e6),
+             "standard15": ("configs[1]: standard 15x15 self-play, ResNet 20x128 bf16, 4096 concurrent games per GPU", 1, 15, 400, 2 * 1383.70e6),
              "renju15": ("configs[2]: renju 15x15 self-play with forbidden-move detection and the solver in the loop, ResNet 20x128 bf16", 2, 15, 400, 2 * 1383.70e6),
              "caro20": ("configs[3]: caro 20x20 self-play, ResNet 20x128 bf16, 800 playouts/move", 3, 20, 800, 2 * 2459.90e6)}
 WORKLOAD = WORKLOADS["standard15"][0]
