@@ -32,7 +32,7 @@ class AgbStats(ctypes.Structure):
         ("nb_information_leaks", ctypes.c_uint64), ("nb_proven_states", ctypes.c_uint64), ("nb_wasted_expansions", ctypes.c_uint64),
         ("nb_moves_played", ctypes.c_uint64), ("nb_games_finished", ctypes.c_uint64), ("nb_kernel_launches", ctypes.c_uint64),
         ("overflow_flags", ctypes.c_uint64), ("nn_kernel_ns", ctypes.c_uint64), ("nn_kernel_launches", ctypes.c_uint64),
-        ("nn_positions", ctypes.c_uint64), ("solver_kernel_ns", ctypes.c_uint64), ("solver_sms", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 1),
+        ("nn_positions", ctypes.c_uint64), ("solver_kernel_ns", ctypes.c_uint64), ("solver_sms", ctypes.c_uint64), ("pipeline_groups", ctypes.c_uint64),
     ]
 
 
@@ -45,6 +45,7 @@ SYMBOLS = {
     "agb_last_error": (ctypes.c_char_p, [_VP]),
     "agb_get_config": (_I, [_VP, ctypes.POINTER(AgbConfig)]),
     "agb_version": (ctypes.c_char_p, []),
+    "agb_config_from_json": (_I, [ctypes.c_char_p, ctypes.POINTER(AgbConfig), ctypes.c_char_p, ctypes.c_size_t]),
     "agb_get_tables": (_I, [_VP, _VP, _VP, _VP]),
     "agb_set_boards": (_I, [_VP, _VP, _VP, _I, _VP]),
     "agb_set_boards_dev": (_I, [_VP, _VP, _VP, _I, _VP]),
@@ -67,6 +68,8 @@ SYMBOLS = {
     "agb_save_games": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "agb_load_games": (_I, [_VP, _VP, ctypes.c_size_t]),
     "agb_set_solver_keys": (_I, [_VP, _VP, ctypes.c_size_t]),
+    "agb_set_symmetry_table": (_I, [_VP, _VP, _I]),
+    "agb_get_root_scores": (_I, [_VP, _I, _VP, _VP]),
     "agb_solve": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "agb_step": (_I, [_VP, _I]),
     "agb_pop_finished": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I)]),

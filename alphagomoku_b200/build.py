@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
-SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu"]
+SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu", "partition.cu"]
 # host-only sources, compiled by g++ with the reference's floating-point flags (no FMA contraction, libm overloads as in the reference)
-HOST_SOURCES = ["openings.cpp"]
+HOST_SOURCES = ["openings.cpp", "config_json.cpp"]
 HOST_FLAGS = ["-O2", "-std=c++17", "-msse2", "-fPIC", "-I/usr/local/cuda/include"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -59,6 +59,30 @@ struct AgbEngine
 
 namespace agb
 {
+	// The evaluator's randInt(8) per scheduled task as a counter-based stream keyed by (seed, global game id, evaluations drawn so far), so that
+	// results do not depend on how games are sharded; or, for replaying a reference run, a caller-supplied table indexed by that counter.
+	struct SymmetryStream
+	{
+			int8_t *task_sym = nullptr; // [slots]
+			uint32_t *counter = nullptr; // [games]
+			unsigned long long seed = 0;
+			int first_game_id = 0;
+			const int8_t *table = nullptr; // agb_set_symmetry_table
+			int table_size = 0;
+#ifdef __CUDACC__
+			__device__ int draw(int game) const
+			{
+				const uint32_t i = counter[game]++;
+				if (table != nullptr)
+					return table[i % static_cast<uint32_t>(table_size)];
+				unsigned long long z = seed ^ (static_cast<unsigned long long>(first_game_id + game) << 32) ^ i;
+				z += 0x9E3779B97F4A7C15ull;
+				z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+				z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+				return static_cast<int>((z ^ (z >> 31)) & 7ull);
+			}
+#endif
+	};
 	// Reads the device status word on the engine's stream and clears it, so that one overflow is reported once and the engine stays
 	// usable afterwards (the flags stay visible in AgbStats::overflow_flags). Synchronises the stream.
 	inline int take_status(AgbEngine *e, uint32_t *status)
@@ -106,6 +130,10 @@ namespace agb
 			int32_t *order = nullptr; // [games] games of a launch, most expensive (by the previous launch's clocks) first
 			int32_t *next = nullptr; // [games] work-queue heads, one per launch range (indexed by its first game)
 			const uint16_t *def_table = nullptr;
+			// SelfplayConfig::use_symmetries with the solver on: the evaluator draws a symmetry for the tasks that are actually scheduled to the
+			// network, in task order (Search::scheduleToNN -> NNEvaluator::addToQueue, Search.cpp:184-198, NNEvaluator.cpp:134-139) -- which
+			// only the solver kernel knows. Unset (task_sym == nullptr): no symmetries.
+			SymmetryStream sym { };
 	};
 	// capi.cu: caller-supplied boards hold only Sign values 0..2 and sign_to_move (may be NULL) only 1..2, else AGB_EINVAL
 	int validate_boards(AgbEngine *e, const int8_t *boards, const int8_t *sign_to_move, size_t n);
@@ -116,9 +144,10 @@ namespace agb
 	void solver_state_destroy(SolverState *st);
 	void solve_scratch_destroy(AgbEngine *e);
 	void openings_destroy(AgbEngine *e);
-	// solver_sms > 0: run on that many SMs only, in blocks that take whole SMs (side by side with the network kernel, see AgbConfig::solver_sms)
+	// solver_sms > 0: run on that many SMs only (side by side with the network kernel, see AgbConfig::solver_sms). green: the stream belongs to a
+	// green context of that many SMs, any block shape stays inside it; otherwise the launch uses blocks that take whole SMs
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,
-			int *nn_count, cudaStream_t stream, int solver_sms = 0);
+			int *nn_count, cudaStream_t stream, int solver_sms = 0, bool green = false);
 	// tables.cu
 	int build_tables(AgbEngine *e);
 	// patterns.cu

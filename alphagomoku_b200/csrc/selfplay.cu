@@ -13,9 +13,8 @@
 // built without FMA contraction, CMakeLists.txt:52-54), so visit counts, values and move choices are bit-identical when
 // the evaluator outputs are.
 //
-// Scope of this round: the per-leaf alpha-beta solver is not on the device yet, so tasks take the
-// reference's "not processed by solver" path: edges for all empty cells + check_terminal_conditions.
 #include "engine.hpp"
+#include "partition.hpp"
 #include "patterns_logic.cuh"
 #include "records.cuh"
 
@@ -123,7 +122,7 @@ namespace agb
 			int32_t path_edge[kMaxPath];
 	};
 
-	constexpr int kMaxGroups = 4;
+	constexpr int kMaxGroups = 8;
 	struct SelfplayState
 	{
 			int games = 0, batch = 0, cells = 0, S = 0;
@@ -157,8 +156,15 @@ namespace agb
 			// solver / tree kernels of one half overlap the network kernel of the other (the network launches share one stream)
 			int groups = 1;
 			int solver_sms = 0, net_sms = 0; // SM partition between K5 and K4 (AgbConfig::solver_sms; 0 = none)
+			// the partition as two green contexts (partition.hpp): the group streams live in the solver's, the network stream in the other. When
+			// the driver cannot provide them the partition falls back to SM-filling solver blocks (solver.cu) and at most 2 groups pay
+			SmPartition partition { };
+			bool green = false;
 			cudaStream_t group_stream[kMaxGroups] = { };
+			cudaStream_t solver_stream[kMaxGroups] = { }; // green partition: K5 of each group on the solver's SMs, everything else of the group on the tree SMs
+			cudaEvent_t solver_go[kMaxGroups] = { }, solver_done[kMaxGroups] = { };
 			cudaStream_t nn_stream = nullptr;
+			cudaStream_t nn_group_stream[kMaxGroups] = { }; // green partition: one network stream per group, so that K4 launches run in the order their inputs become ready
 			cudaEvent_t ready[kMaxGroups] = { }, evaluated[kMaxGroups] = { }, joined = nullptr;
 			uint32_t *features = nullptr;
 			float *policy = nullptr, *value = nullptr, *q = nullptr;
@@ -172,6 +178,8 @@ namespace agb
 			uint32_t *noise_counter = nullptr; // [games] searches drawn so far
 			int8_t *task_sym = nullptr; // [games*batch] symmetry of the slot's evaluation
 			uint32_t *sym_counter = nullptr; // [games] evaluations drawn so far (the random stream is keyed by the global game id)
+			int8_t *sym_table = nullptr; // agb_set_symmetry_table: replayed symmetries instead of the random stream
+			int sym_table_size = 0;
 			uint32_t *features_aug = nullptr; // [games*batch][cells] augmented feature words
 			float *policy_raw = nullptr, *q_raw = nullptr; // network outputs before the inverse symmetry
 			uint64_t *zobrist = nullptr; // [cells][2] + [2]
@@ -223,6 +231,7 @@ namespace agb
 				float final_exploration; // its exploration_constant (lcb)
 				float expansion_threshold; // MCTSConfig::policy_expansion_threshold
 				unsigned long long sym_seed;
+				SymmetryStream sym;
 				Tables tables;
 				BoardStore store;
 				uint32_t *status;
@@ -653,14 +662,8 @@ namespace agb
 					task.nn_slot = slot;
 					p.s.task_stm[slot] = task.stm;
 					p.s.slot_is_root[slot] = (task.path_len == 0) ? 1 : 0;
-					if (p.use_symmetries)
-					{ // randInt(8) of the reference's evaluator, as a counter-based stream per (seed, global game id)
-						unsigned long long z = p.sym_seed ^ (static_cast<unsigned long long>(p.first_game_id + g) << 32) ^ p.s.sym_counter[g]++;
-						z += 0x9E3779B97F4A7C15ull;
-						z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-						z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-						p.s.task_sym[slot] = static_cast<int8_t>((z ^ (z >> 31)) & 7ull);
-					}
+					if (p.use_symmetries and p.solver_mode == 0) // with the solver on, K5 draws for the tasks it schedules (SolverState::sym)
+						p.s.task_sym[slot] = static_cast<int8_t>(p.sym.draw(g));
 					if (p.solver_mode != 0)
 						p.s.solver.game_slots[static_cast<size_t>(g) * p.s.batch + n_slots] = slot; // the solver walks them in task order
 				}
@@ -1601,6 +1604,7 @@ namespace agb
 			p.expansion_threshold = e->cfg.policy_expansion_threshold;
 			p.first_game_id = e->cfg.first_game_id;
 			p.sym_seed = e->cfg.seed * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull;
+			p.sym = SymmetryStream { p.s.task_sym, p.s.sym_counter, p.sym_seed, e->cfg.first_game_id, p.s.sym_table, p.s.sym_table_size };
 			p.tables = e->tables;
 			p.store = e->store;
 			p.status = e->d_status;
@@ -1710,26 +1714,69 @@ namespace agb
 			ok = cudaMemset(s->tasks, 0, T * sizeof(TaskD)) == cudaSuccess; // sticky per-slot flags start cleared
 		if (not ok)
 			return e->fail(AGB_ENOMEM, std::string("self-play arenas: ") + cudaGetErrorString(cudaGetLastError()));
-		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : ((c.solver_max_positions > 1 and c.games >= 1024) ? 2 : 1);
+		const bool pipelined = (c.pipeline_groups > 1) or (c.pipeline_groups == 0 and c.solver_max_positions > 1 and c.games >= 1024);
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+		// Opt-in (AGB_GREEN_CONTEXTS=1): measured at steady state the three-way split loses to the SM-filling solver blocks (178 k against 188 k
+		// evaluations per second): the tree kernels' 8 SMs are mostly idle and K4 does not speed up in proportion to its SMs
+		if (pipelined and c.solver_max_positions > 1 and c.solver_sms >= 0 and getenv("AGB_GREEN_CONTEXTS") != nullptr)
+		{ // real SM partitions (green contexts); the provisioned sizes are multiples of 8 SMs. Automatic: 64 of 148 for the solver, 8 for the tree kernels
+			std::string why;
+			const int want = c.solver_sms > 0 ? std::min(c.solver_sms, sms - 24) : sms * 64 / 148;
+			s->green = partition_create(c.device, std::max(8, (want + 4) / 8 * 8), 8, &s->partition, &why);
+			if (getenv("AGB_VERBOSE") != nullptr)
+			{
+				if (s->green)
+					fprintf(stderr, "agb200: green-context SM partition: solver %d, network %d, tree kernels %d SMs %s\n", s->partition.solver_sms, s->partition.net_sms,
+							s->partition.tree_sms, why.c_str());
+				else
+					fprintf(stderr, "agb200: no green-context SM partition (%s); using SM-filling solver blocks\n", why.c_str());
+			}
+		}
+		// groups: with green contexts the launches of several groups share the solver's SMs, so more groups hide each launch's tail (6: measured
+		// best of 2..8 at steady state); without them the solver runs in SM-filling blocks and more than 2 groups only get in each other's way
+		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : (pipelined ? (s->green ? 6 : 2) : 1);
+		s->solver_sms = 0;
+		if (s->green)
+		{
+			s->solver_sms = s->partition.solver_sms;
+			s->net_sms = s->partition.net_sms;
+		}
+		else
 		{ // AgbConfig::solver_sms
-			int sms = 148;
-			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
-			s->solver_sms = 0;
 			if (s->groups > 1 and c.solver_max_positions > 1 and c.solver_sms >= 0)
 				s->solver_sms = (c.solver_sms > 0 ? std::min(c.solver_sms, sms - 2) : sms * 28 / 148) & ~1;
 			s->net_sms = s->solver_sms > 0 ? sms - s->solver_sms : 0;
 		}
 		if (s->groups > kMaxGroups or s->groups > c.games)
-			return e->fail(AGB_EINVAL, "pipeline_groups must be 1..4 and not exceed the number of games");
+			return e->fail(AGB_EINVAL, "pipeline_groups must be 1..8 and not exceed the number of games");
 		if (s->groups > 1)
 		{
 			for (int k = 0; k < s->groups; k++)
 			{
-				AGB_CUDA_CHECK(e, cudaStreamCreateWithFlags(&s->group_stream[k], cudaStreamNonBlocking));
+				if (s->green)
+				{
+					if (not partition_stream(s->partition.tree_ctx, &s->group_stream[k]) or not partition_stream(s->partition.solver_ctx, &s->solver_stream[k]))
+						return e->fail(AGB_ECUDA, "cuGreenCtxStreamCreate failed");
+					AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->solver_go[k], cudaEventDisableTiming));
+					AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->solver_done[k], cudaEventDisableTiming));
+				}
+				else
+					AGB_CUDA_CHECK(e, cudaStreamCreateWithFlags(&s->group_stream[k], cudaStreamNonBlocking));
 				AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->ready[k], cudaEventDisableTiming));
 				AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->evaluated[k], cudaEventDisableTiming));
 			}
-			AGB_CUDA_CHECK(e, cudaStreamCreateWithFlags(&s->nn_stream, cudaStreamNonBlocking));
+			if (s->green)
+			{
+				if (not partition_stream(s->partition.net_ctx, &s->nn_stream))
+					return e->fail(AGB_ECUDA, "cuGreenCtxStreamCreate failed");
+				if (getenv("AGB_NET_PER_GROUP") != nullptr) // experiment: K4 launches in the order their inputs become ready instead of round-robin
+					for (int k = 0; k < s->groups; k++)
+						if (not partition_stream(s->partition.net_ctx, &s->nn_group_stream[k]))
+							return e->fail(AGB_ECUDA, "cuGreenCtxStreamCreate failed");
+			}
+			else
+				AGB_CUDA_CHECK(e, cudaStreamCreateWithFlags(&s->nn_stream, cudaStreamNonBlocking));
 			AGB_CUDA_CHECK(e, cudaEventCreateWithFlags(&s->joined, cudaEventDisableTiming));
 		}
 		if (c.solver_max_positions > 0)
@@ -1759,7 +1806,7 @@ namespace agb
 			return;
 		void *ptrs[] = { s->root_board, s->root_bits, s->root_hash, s->root_stm, s->root_node, s->n_nodes, s->n_edges, s->n_stored, s->n_moves, s->moves,
 				s->outcome, s->nodes, s->node_bits, s->edges, s->table, s->remap, s->tasks, s->task_boards, s->task_stm, s->eval_count, s->features, s->policy,
-				s->value, s->q, s->paused, s->decision, s->root_noise, s->noise_ready, s->noise_counter, s->task_sym, s->sym_counter, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
+				s->value, s->q, s->paused, s->decision, s->root_noise, s->noise_ready, s->noise_counter, s->task_sym, s->sym_counter, s->sym_table, s->features_aug, s->policy_raw, s->q_raw, s->zobrist, s->stats, s->openings, s->opening_stm, s->opening_cursor, s->sample_visits, s->sample_prior, s->sample_win,
 				s->sample_root, s->sample_draw, s->sample_score, s->slot_is_root, s->nn_list, s->nn_count, s->solver_out.moves, s->solver_out.scores,
 				s->solver_out.n_actions, s->solver_out.score, s->solver_out.must_defend, s->solver_out.nodes, s->rec_buf, s->rec_len, s->rec_samples, s->fin_buf, s->fin_used, s->fin_games };
 		for (void *ptr : ptrs)
@@ -1777,6 +1824,18 @@ namespace agb
 		}
 		if (s->nn_stream)
 			cudaStreamDestroy(s->nn_stream);
+		for (int k = 0; k < kMaxGroups; k++)
+		{
+			if (s->nn_group_stream[k])
+				cudaStreamDestroy(s->nn_group_stream[k]);
+			if (s->solver_stream[k])
+				cudaStreamDestroy(s->solver_stream[k]);
+			if (s->solver_go[k])
+				cudaEventDestroy(s->solver_go[k]);
+			if (s->solver_done[k])
+				cudaEventDestroy(s->solver_done[k]);
+		}
+		partition_destroy(&s->partition);
 		if (s->joined)
 			cudaEventDestroy(s->joined);
 		delete s;
@@ -2015,6 +2074,30 @@ extern "C"
 		return AGB_OK;
 	}
 
+	int agb_set_symmetry_table(AgbEngine *e, const int8_t *table_host, int n)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or s->sym_counter == nullptr)
+			return e->fail(AGB_ESTATE, "engine was created without games or without use_symmetries");
+		if (n < 0 or (n > 0 and table_host == nullptr))
+			return e->fail(AGB_EINVAL, "bad symmetry table");
+		for (int i = 0; i < n; i++)
+			if (table_host[i] < 0 or table_host[i] > 7)
+				return e->fail(AGB_EINVAL, "symmetry must be in 0..7");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		if (s->sym_table != nullptr)
+			cudaFree(s->sym_table);
+		s->sym_table = nullptr;
+		s->sym_table_size = 0;
+		if (n > 0)
+		{
+			AGB_CUDA_CHECK(e, cudaMalloc(&s->sym_table, n));
+			AGB_CUDA_CHECK(e, cudaMemcpy(s->sym_table, table_host, n, cudaMemcpyHostToDevice));
+			s->sym_table_size = n;
+		}
+		return AGB_OK;
+	}
+
 	int agb_set_solver_keys(AgbEngine *e, const uint64_t *keys_host, size_t n_words)
 	{
 		SelfplayState *s = e->selfplay;
@@ -2078,6 +2161,9 @@ extern "C"
 			for (int k = 0; k < groups; k++)
 				AGB_CUDA_CHECK(e, cudaStreamWaitEvent(s->group_stream[k], s->joined, 0));
 			AGB_CUDA_CHECK(e, cudaStreamWaitEvent(s->nn_stream, s->joined, 0));
+			for (int k = 0; k < groups; k++)
+				if (s->nn_group_stream[k] != nullptr)
+					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(s->nn_group_stream[k], s->joined, 0));
 		}
 		for (int step = 0; step < n_steps; step++)
 			for (int k = 0; k < groups; k++)
@@ -2091,7 +2177,7 @@ extern "C"
 				const int max_tasks = p.game_count * s->batch;
 				const unsigned grid = static_cast<unsigned>((p.game_count + 3) / 4);
 				cudaStream_t gs = (groups > 1) ? s->group_stream[k] : e->stream;
-				cudaStream_t ns = (groups > 1) ? s->nn_stream : e->stream;
+				cudaStream_t ns = (groups > 1) ? (s->nn_group_stream[k] != nullptr ? s->nn_group_stream[k] : s->nn_stream) : e->stream;
 				cudaEvent_t *ev = e->events.data() + 4 * (step * groups + k); // before / after K5 (group stream), before / after K4 (network stream)
 
 				AGB_CUDA_CHECK(e, cudaMemsetAsync(p.eval_count, 0, sizeof(int32_t), gs));
@@ -2101,15 +2187,32 @@ extern "C"
 				int rc = launch_set_boards_counted(e, s->task_boards, s->task_stm, p.eval_count, max_tasks, s->features, p.slot_base, gs);
 				if (rc != AGB_OK)
 					return rc;
-				AGB_CUDA_CHECK(e, cudaEventRecord(ev[0], gs));
+				// K5 runs on the solver's SMs: with green contexts that is another stream than the group's (whose kernels run on the tree SMs)
+				cudaStream_t ks = (s->green and p.solver_mode != 0) ? s->solver_stream[k] : gs;
+				if (ks != gs)
+				{
+					AGB_CUDA_CHECK(e, cudaMemsetAsync(nn_count, 0, sizeof(int32_t), gs));
+					AGB_CUDA_CHECK(e, cudaEventRecord(s->solver_go[k], gs));
+					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(ks, s->solver_go[k], 0));
+				}
+				AGB_CUDA_CHECK(e, cudaEventRecord(ev[0], ks));
 				if (p.solver_mode != 0)
 				{ // K5 on every leaf; only unproven positions (and roots) go on to the network
-					AGB_CUDA_CHECK(e, cudaMemsetAsync(nn_count, 0, sizeof(int32_t), gs));
-					rc = launch_solve_games(e, s->solver, p.game_begin, p.game_count, s->solver_out, s->slot_is_root, s->nn_list + p.slot_base, nn_count, gs, s->solver_sms);
+					if (ks == gs)
+						AGB_CUDA_CHECK(e, cudaMemsetAsync(nn_count, 0, sizeof(int32_t), gs));
+					SolverState solver = s->solver;
+					if (p.use_symmetries)
+						solver.sym = p.sym; // the evaluator's symmetry draw happens where tasks are scheduled to the network, i.e. in K5
+					rc = launch_solve_games(e, solver, p.game_begin, p.game_count, s->solver_out, s->slot_is_root, s->nn_list + p.slot_base, nn_count, ks, s->solver_sms, s->green);
 					if (rc != AGB_OK)
 						return rc;
 				}
-				AGB_CUDA_CHECK(e, cudaEventRecord(ev[1], gs));
+				AGB_CUDA_CHECK(e, cudaEventRecord(ev[1], ks));
+				if (ks != gs)
+				{
+					AGB_CUDA_CHECK(e, cudaEventRecord(s->solver_done[k], ks));
+					AGB_CUDA_CHECK(e, cudaStreamWaitEvent(gs, s->solver_done[k], 0));
+				}
 				const bool sym = p.use_symmetries != 0;
 				const size_t off = static_cast<size_t>(p.slot_base);
 				// Only K4 itself goes on the network stream; what surrounds it (augment before, dense value layers and inverse symmetries after)
@@ -2173,7 +2276,7 @@ extern "C"
 				call_solver_ms += ms;
 			}
 		}
-		if (s->solver_sms > 0 and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0)
+		if (s->solver_sms > 0 and not s->green and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0)
 		{ // automatic partition: both kernels scale with their SMs, so split the SMs in proportion to the SM-time each needed in this
 		  // call (K5 and K4 launches then take equally long); move three quarters of the way, in whole TPCs. Results do not depend on it.
 			const int sms = s->solver_sms + s->net_sms;
@@ -2250,6 +2353,7 @@ extern "C"
 		stats->nn_positions = e->nn_positions;
 		stats->solver_kernel_ns = e->solver_kernel_ns;
 		stats->solver_sms = (e->selfplay != nullptr) ? static_cast<uint64_t>(e->selfplay->solver_sms) : 0;
+		stats->pipeline_groups = (e->selfplay != nullptr) ? static_cast<uint64_t>(e->selfplay->groups) : 0;
 		if (e->selfplay != nullptr)
 		{
 			unsigned long long h[16];
@@ -2319,6 +2423,28 @@ extern "C"
 		}
 		if (root_visits)
 			*root_visits = node.visits;
+		return AGB_OK;
+	}
+	int agb_get_root_scores(AgbEngine *e, int game, uint16_t *edge_scores_host, uint16_t *root_score)
+	{
+		SelfplayState *s = e->selfplay;
+		if (s == nullptr or game < 0 or game >= s->games or edge_scores_host == nullptr or root_score == nullptr)
+			return e->fail(AGB_EINVAL, "bad game index or null pointer");
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		for (int i = 0; i < s->cells; i++)
+			edge_scores_host[i] = score::kDefault;
+		*root_score = score::kDefault;
+		int32_t root = -1;
+		AGB_CUDA_CHECK(e, cudaMemcpy(&root, s->root_node + game, 4, cudaMemcpyDeviceToHost));
+		if (root < 0)
+			return AGB_OK;
+		NodeD node;
+		AGB_CUDA_CHECK(e, cudaMemcpy(&node, s->nodes + static_cast<size_t>(game) * s->max_nodes + root, sizeof(NodeD), cudaMemcpyDeviceToHost));
+		std::vector<EdgeD> edges(node.n_edges);
+		AGB_CUDA_CHECK(e, cudaMemcpy(edges.data(), s->edges + static_cast<size_t>(game) * s->max_edges + node.edge_begin, sizeof(EdgeD) * node.n_edges, cudaMemcpyDeviceToHost));
+		for (const EdgeD &ed : edges)
+			edge_scores_host[((ed.move >> 2) & 127) * s->S + ((ed.move >> 9) & 127)] = ed.score;
+		*root_score = node.score;
 		return AGB_OK;
 	}
 	int agb_get_root_noise(AgbEngine *e, int game, float *noisy_policy_host)

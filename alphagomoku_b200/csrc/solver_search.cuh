@@ -38,9 +38,13 @@ namespace agb
 				uint32_t n_adds = 0, n_quiet = 0, n_gen = 0, n_gen_actions = 0; // work counters (scheduling weights, solver.cu)
 		};
 
+		// The solver never walks the HALF_OPEN_3 lists and never asks for their length (MoveGenerator.cpp reads a cell's HALF_OPEN_3 threat
+		// only through threat_at / the pattern table; AlphaBetaSearch::evaluate gives the type weight 0), and the slot's lists die with the
+		// launch, so the search keeps only the lists of OPEN_3 and stronger in step: the longest list of a mid-game position costs nothing.
+		AGB_HD inline bool list_is_kept(int type) { return type > TT_HALF_OPEN_3; }
 		AGB_HD_NOINLINE inline void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
 		{ // ThreatHistogram::remove (ThreatHistogram.hpp:74-91)
-			if (type == TT_NONE)
+			if (not list_is_kept(type))
 				return;
 			int32_t &count = d.hist_count[colour * kHistTypes + type];
 			uint16_t *list = d.hist_cells + (colour * kHistTypes + type) * d.v.pitch;
@@ -76,41 +80,47 @@ namespace agb
 		}
 		AGB_HD inline void dyn_hist_add(DynState &d, int colour, int type, uint16_t loc)
 		{
-			if (type == TT_NONE)
+			if (not list_is_kept(type))
 				return;
 			int32_t &count = d.hist_count[colour * kHistTypes + type];
 			d.hist_cells[(colour * kHistTypes + type) * d.v.pitch + count] = loc;
 			count++;
 		}
-		AGB_HD_NOINLINE inline void dyn_update_neighbours(DynState &d, int r, int c, const uint64_t *line4, const int *pos4)
-		{ // the 40 cells at distance 1..5 in the visiting order of update_around (PatternCalculator.cpp:320-330)
-			const int S = d.v.S;
 #ifdef __CUDA_ARCH__
-			// On the device all 32 lanes of the game's warp run the solver in lockstep on identical data; here they split the 40 cells
-			// (entry q = 4 * k + dir, k-th offset of -5..-1,1..5, like K2) and then replay the list changes together, in visiting order.
+		// Device form of addMove / undoMove. All 32 lanes of the game's warp run the solver in lockstep on identical data; here they split the
+		// work: lane q (and q + 32) owns entry q = 4 * k + dir of the 40 neighbour cells (k-th offset of -5..-1, 1..5, like K2), so a lane only
+		// ever needs the line word of ITS direction (dir = lane & 3). The list changes are then replayed by the whole warp in the visiting
+		// order of update_around (PatternCalculator.cpp:320-330), which is the order of q.
+		__device__ __forceinline__ void dyn_update_neighbours_warp(DynState &d, int S, int r, int c, int dir, uint64_t my_line, int my_pos)
+		{
 			const int lane = threadIdx.x & 31;
+			// the state's pointers in registers: the byte stores below could alias the fields of `d` and would force a reload after each
+			const int8_t *const board = d.board;
+			uint32_t *const ptypes = d.ptypes;
+			uint8_t *const threats = d.threats;
+			const uint8_t *const pattern_table = d.v.pattern_table, *const threat_table = d.threat_table;
+			const int row_step = dir_row_step(dir), col_step = dir_col_step(dir);
 			uint32_t old_t[2] = { 0, 0 }, new_t[2] = { 0, 0 }, loc[2] = { 0, 0 };
 #pragma unroll
 			for (int half = 0; half < 2; half++)
 			{
-				const int q = lane + 32 * half;
+				const int q = lane + 32 * half; // q & 3 == dir in both halves
 				if (q < 40)
 				{
-					const int dir = q & 3;
 					const int k = q >> 2;
 					const int off = (k < 5) ? (k - 5) : (k - 4);
-					const int nr = r + off * dir_row_step(dir), nc = c + off * dir_col_step(dir);
-					if (nr >= 0 and nr < S and nc >= 0 and nc < S and d.board[nr * S + nc] == NONE)
+					const int nr = r + off * row_step, nc = c + off * col_step;
+					const int ncell = nr * S + nc;
+					if (nr >= 0 and nr < S and nc >= 0 and nc < S and board[ncell] == NONE)
 					{
-						const int ncell = nr * S + nc;
-						const uint32_t window = static_cast<uint32_t>(line4[dir] >> (2 * (pos4[dir] + off) + 2)) & 0x3FFFFFu;
-						const uint32_t byte = d.v.pattern_table[narrow_window(window)];
-						const uint32_t p = (d.ptypes[ncell] & ~(0xFFu << (8 * dir))) | (byte << (8 * dir));
-						old_t[half] = d.threats[ncell];
-						new_t[half] = threat_of_cell(p, d.threat_table);
+						const uint32_t window = static_cast<uint32_t>(my_line >> (2 * (my_pos + off) + 2)) & 0x3FFFFFu;
+						const uint32_t byte = pattern_table[narrow_window(window)];
+						const uint32_t p = (ptypes[ncell] & ~(0xFFu << (8 * dir))) | (byte << (8 * dir));
+						old_t[half] = threats[ncell];
+						new_t[half] = threat_of_cell(p, threat_table);
 						loc[half] = mk_loc(nr, nc);
-						d.ptypes[ncell] = p;
-						d.threats[ncell] = static_cast<uint8_t>(new_t[half]);
+						ptypes[ncell] = p;
+						threats[ncell] = static_cast<uint8_t>(new_t[half]);
 					}
 				}
 			}
@@ -118,28 +128,90 @@ namespace agb
 #pragma unroll
 			for (int half = 0; half < 2; half++)
 			{
-				unsigned changed = __ballot_sync(0xFFFFFFFFu, old_t[half] != new_t[half]);
+				// only changes that touch a kept list (OPEN_3 or stronger, either colour) are replayed
+				const uint32_t ot = old_t[half], nt = new_t[half];
+				const bool touches = ((ot & 15u) != (nt & 15u) and (list_is_kept(ot & 15u) or list_is_kept(nt & 15u)))
+						or ((ot >> 4) != (nt >> 4) and (list_is_kept(ot >> 4) or list_is_kept(nt >> 4)));
+				unsigned changed = __ballot_sync(0xFFFFFFFFu, touches);
 				while (changed)
 				{
 					const int src = __ffs(changed) - 1;
 					changed &= changed - 1;
-					const int o = __shfl_sync(0xFFFFFFFFu, static_cast<int>(old_t[half]), src);
-					const int nw = __shfl_sync(0xFFFFFFFFu, static_cast<int>(new_t[half]), src);
-					const uint16_t l = static_cast<uint16_t>(__shfl_sync(0xFFFFFFFFu, static_cast<int>(loc[half]), src));
+					// one shuffle: old threats | new threats << 8 | location << 16
+					const uint32_t packed = __shfl_sync(0xFFFFFFFFu, ot | (nt << 8) | (loc[half] << 16), src);
+					const int o = packed & 255u, nw = (packed >> 8) & 255u;
+					const uint16_t l = static_cast<uint16_t>(packed >> 16);
 					if ((o & 15) != (nw & 15))
 					{
-						dyn_hist_remove(d, 0, o & 15, l);
+						if (list_is_kept(o & 15))
+							dyn_hist_remove(d, 0, o & 15, l);
 						dyn_hist_add(d, 0, nw & 15, l);
 					}
 					if ((o >> 4) != (nw >> 4))
 					{
-						dyn_hist_remove(d, 1, o >> 4, l);
+						if (list_is_kept(o >> 4))
+							dyn_hist_remove(d, 1, o >> 4, l);
 						dyn_hist_add(d, 1, nw >> 4, l);
 					}
 				}
 			}
 			__syncwarp();
+		}
+		__device__ __noinline__ void dyn_add_move(DynState &d, int r, int c, int sign)
+		{ // PatternCalculator::addMove (PatternCalculator.cpp:68-86)
+			d.n_adds++;
+			const int S = d.v.S;
+			const int dir = threadIdx.x & 3;
+			const int li = line_index(dir, r, c, S), pos = pos_in_line(dir, r, c, S);
+			uint64_t *const lines = d.lines;
+			const uint64_t line = lines[li] | (static_cast<uint64_t>(sign) << (12 + 2 * pos));
+			__syncwarp();
+			if ((threadIdx.x & 31) < 4)
+				lines[li] = line;
+			const int centre = r * S + c;
+			const uint8_t old_t = d.threats[centre];
+			__syncwarp();
+			d.board[centre] = static_cast<int8_t>(sign);
+			d.ptypes[centre] = 0;
+			d.threats[centre] = 0;
+			if (list_is_kept(old_t & 15))
+				dyn_hist_remove(d, 0, old_t & 15, mk_loc(r, c));
+			if (list_is_kept(old_t >> 4))
+				dyn_hist_remove(d, 1, old_t >> 4, mk_loc(r, c));
+			dyn_update_neighbours_warp(d, S, r, c, dir, line, pos);
+			d.v.stm = 3 - d.v.stm;
+			d.v.stones++;
+		}
+		__device__ __noinline__ void dyn_undo_move(DynState &d, int r, int c, int sign)
+		{ // PatternCalculator::undoMove (PatternCalculator.cpp:87-106)
+			(void) sign;
+			const int S = d.v.S;
+			const int dir = threadIdx.x & 3;
+			const int li = line_index(dir, r, c, S), pos = pos_in_line(dir, r, c, S);
+			uint64_t *const lines = d.lines;
+			const uint64_t line = lines[li] & ~(3ull << (12 + 2 * pos));
+			__syncwarp();
+			if ((threadIdx.x & 31) < 4)
+				lines[li] = line;
+			const int centre = r * S + c;
+			// the centre's four direction bytes: lanes 0..3 look one up each
+			const uint32_t mine = ((threadIdx.x & 31) < 4)
+					? static_cast<uint32_t>(d.v.pattern_table[narrow_window(static_cast<uint32_t>(line >> (2 * pos + 2)) & 0x3FFFFFu)]) << (8 * dir) : 0u;
+			const uint32_t p = __reduce_or_sync(0xFFFFFFFFu, mine);
+			const uint8_t new_t = threat_of_cell(p, d.threat_table);
+			d.board[centre] = NONE;
+			d.ptypes[centre] = p;
+			d.threats[centre] = new_t;
+			dyn_hist_add(d, 0, new_t & 15, mk_loc(r, c));
+			dyn_hist_add(d, 1, new_t >> 4, mk_loc(r, c));
+			dyn_update_neighbours_warp(d, S, r, c, dir, line, pos);
+			d.v.stm = 3 - d.v.stm;
+			d.v.stones--;
+		}
 #else
+		inline void dyn_update_neighbours(DynState &d, int r, int c, const uint64_t *line4, const int *pos4)
+		{ // the 40 cells at distance 1..5 in the visiting order of update_around (PatternCalculator.cpp:320-330)
+			const int S = d.v.S;
 			for (int off = -5; off <= 5; off++)
 				if (off != 0)
 					for (int dir = 0; dir < 4; dir++)
@@ -172,9 +244,8 @@ namespace agb
 							}
 						}
 					}
-#endif
 		}
-		AGB_HD_NOINLINE inline void dyn_add_move(DynState &d, int r, int c, int sign)
+		inline void dyn_add_move(DynState &d, int r, int c, int sign)
 		{ // PatternCalculator::addMove (PatternCalculator.cpp:68-86)
 			d.n_adds++;
 			const int S = d.v.S;
@@ -198,7 +269,7 @@ namespace agb
 			d.v.stm = 3 - d.v.stm;
 			d.v.stones++;
 		}
-		AGB_HD_NOINLINE inline void dyn_undo_move(DynState &d, int r, int c, int sign)
+		inline void dyn_undo_move(DynState &d, int r, int c, int sign)
 		{ // PatternCalculator::undoMove (PatternCalculator.cpp:87-106)
 			(void) sign;
 			const int S = d.v.S;
@@ -225,6 +296,7 @@ namespace agb
 			d.v.stm = 3 - d.v.stm;
 			d.v.stones--;
 		}
+#endif
 
 		// ---- renju forbidden moves on the live state (with the reference's side effect on the list order) ---------------------------
 		constexpr int kMaxForbiddenDepth = 8;

@@ -54,6 +54,16 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def config_from_json(text):
+    """The reference's config.json text -> AgbConfig (agb_config_from_json; src/utils/configs.cpp:33-306)."""
+    cfg = _lib.AgbConfig()
+    err = ctypes.create_string_buffer(512)
+    rc = _lib.load().agb_config_from_json(text.encode(), ctypes.byref(cfg), err, len(err))
+    if rc != 0:
+        raise AgbError(rc, err.value.decode())
+    return cfg
+
+
 class Engine:
     """One engine per GPU (one GeneratorThread per DeviceConfig in the reference)."""
 
@@ -255,13 +265,18 @@ class Engine:
         k = np.ascontiguousarray(keys, np.uint64).reshape(-1)
         self._check(self._lib.agb_set_solver_keys(self._h, _ptr(k), k.size))
 
+    def set_symmetry_table(self, table):
+        """Replay hook: the i-th network evaluation of every game uses symmetry table[i % len(table)] (empty: back to the random stream)."""
+        t = np.ascontiguousarray(table, np.int8).reshape(-1)
+        self._check(self._lib.agb_set_symmetry_table(self._h, _ptr(t) if t.size else None, int(t.size)))
+
     def step(self, n_steps=1):
         self._check(self._lib.agb_step(self._h, n_steps))
 
     def stats(self):
         st = _lib.AgbStats()
         self._check(self._lib.agb_get_stats(self._h, ctypes.byref(st)))
-        return {name: getattr(st, name) for name, _ in st._fields_ if name != "reserved"}
+        return {name: getattr(st, name) for name, _ in st._fields_}
 
     def get_root(self, game):
         visits = np.zeros(self.cells, np.int32)
@@ -271,6 +286,13 @@ class Engine:
         rv = ctypes.c_int32(0)
         self._check(self._lib.agb_get_root(self._h, game, _ptr(visits), _ptr(priors), _ptr(q), _ptr(value), ctypes.byref(rv)))
         return visits, priors, q, value, rv.value
+
+    def get_root_scores(self, game):
+        """Score::to_short of every root edge (per cell) and of the root node."""
+        scores = np.zeros(self.cells, np.uint16)
+        root = ctypes.c_uint16(0)
+        self._check(self._lib.agb_get_root_scores(self._h, game, _ptr(scores), ctypes.byref(root)))
+        return scores, root.value
 
     def get_root_noise(self, game):
         """PUCTSelector::noisy_policy of game's current search, per cell (zeros before it is drawn)."""

@@ -95,19 +95,20 @@ typedef struct AgbConfig
 	int32_t first_game_id; /* global id of this engine's game 0 (rank * games when sharded) */
 	int32_t solver_table_entries; /* entries of each game's solver transposition table (power of two; 0 = 65536; the reference uses 4 Mi,
 	                                 AlphaBetaSearch.cpp:55) */
-	int32_t pipeline_groups; /* 1: all games advance together; 2..4: that many groups of games on their own streams, so that one group's solver and tree
-	                            kernels overlap another group's network kernel; 0 = automatic (2 when the alpha-beta solver is on and there are at
-	                            least 1024 games, else 1). Per-game results do not depend on it */
+	int32_t pipeline_groups; /* 1: all games advance together; 2..8: that many groups of games on their own streams, so that the solver and tree
+	                            kernels of some groups overlap another group's network kernel; 0 = automatic (with the alpha-beta solver on and at
+	                            least 1024 games: 6 when the SM partition is made of green contexts, else 2; otherwise 1). Per-game results do not
+	                            depend on it */
 	int32_t final_selector; /* SelfplayConfig::final_selector.policy: AGB_FINAL_* (EdgeSelector::create, EdgeSelector.cpp:680-711) */
 	float final_exploration_constant; /* its exploration_constant (used by AGB_FINAL_LCB) */
 	int32_t noise_type; /* EdgeSelectorConfig::noise_type of the tree selector: AGB_NOISE_* (applied at the root, EdgeSelector.cpp:1127-1137) */
 	float noise_weight; /* EdgeSelectorConfig::noise_weight; 0 = no noise */
 	float policy_temperature; /* MCTSConfig::policy_temperature: 0 or 1 = priors as the network gives them (the default), t > 0 = prior^(1/t),
 	                             negative = the reference's temperature 0 (one-hot on the best move) */
-	int32_t solver_sms; /* with 2..4 pipeline groups and the alpha-beta solver: SMs the solver kernel runs on while the network kernel takes the
-	                       others (side by side, not sharing SMs: the solver is bound by instruction supply, the network by the tensor pipe, and
-	                       on a shared SM both lose). 0 = automatic (starts at 28 of 148 and follows the measured launch times of the two kernels),
-	                       -1 = no partition. Even; ignored with one group */
+	int32_t solver_sms; /* with 2..8 pipeline groups and the alpha-beta solver: SMs the solver side (K5 and the small tree kernels) runs on while the
+	                       network kernel takes the others (side by side, not sharing SMs: the solver is bound by instruction supply, the network by
+	                       the tensor pipe, and on a shared SM both lose). The partition is a pair of CUDA green contexts (sizes in multiples of 8
+	                       SMs); where the driver has none, SM-filling solver blocks. 0 = automatic, -1 = no partition. Ignored with one group */
 } AgbConfig;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -115,6 +116,14 @@ int agb_create(const AgbConfig *config, AgbEngine **engine);
 void agb_destroy(AgbEngine *engine);
 const char* agb_last_error(const AgbEngine *engine); /* engine may be NULL: error of the last failed agb_create */
 int agb_get_config(const AgbEngine *engine, AgbConfig *config);
+/* The reference's config.json (MasterLearningConfig, src/utils/configs.cpp:33-306) -> AgbConfig: "game_config" (GameConfig), "generation_config"
+ * (SelfplayConfig with its search_config: tree / mcts / tss, edge selector, constraints or "simulations", final_selector) and, when present,
+ * "training_config" (network_arch ResnetPV / ResnetPVQ, blocks, filters). Same key names, required keys and defaults as the reference's
+ * (const Json&) constructors, incl. init_to = "parent" when absent (configs.cpp:71). games = games_per_thread x device_config entries,
+ * max_boards = games x max_batch_size; device, seed, first_game_id, the table size, groups and SM split stay 0 (= engine defaults) for the
+ * caller to set. What the engine cannot do (selectors other than puct, time constraints, other architectures) is an error, not ignored.
+ * Returns AGB_OK or AGB_EINVAL with a message in `error` (may be NULL). */
+int agb_config_from_json(const char *json_text, AgbConfig *config, char *error, size_t error_size);
 const char* agb_version(void);
 
 /* ---- static tables (replaces PatternTable::get / ThreatTable::get, src/patterns/PatternTable.cpp:110-142,
@@ -209,6 +218,11 @@ int agb_load_games(AgbEngine *engine, const void *blob_host, size_t bytes);
  * games, or games times that for one set per game (the reference has one per GameGenerator); agb_solve uses the first set. Call before
  * agb_selfplay_reset. */
 int agb_set_solver_keys(AgbEngine *engine, const uint64_t *keys_host, size_t n_words);
+/* replay hook for SelfplayConfig::use_symmetries: the i-th position a game sends to the network uses symmetry table[i mod n] instead of the
+ * engine's random stream (n = 0 restores the stream). With table[i] = the i-th randInt(8) of a fresh reference thread this is exactly what
+ * NNEvaluator::addToQueue draws (src/search/monte_carlo/NNEvaluator.cpp:134-139, src/utils/random.cpp:17-23) when each game has its own
+ * evaluator thread, so a lockstep run can be compared with the reference move for move with symmetries on. Call before agb_selfplay_reset. */
+int agb_set_symmetry_table(AgbEngine *engine, const int8_t *table_host, int n);
 /* advance every game by n_steps lockstep iterations of select -> solve/encode -> evaluate -> expand -> backup (-> move) */
 int agb_step(AgbEngine *engine, int n_steps);
 /* pop finished-game records (GameDataStorage::serialize, src/dataset/GameDataStorage.cpp:217-251, format 201) */
@@ -234,7 +248,7 @@ typedef struct AgbStats
 	uint64_t solver_kernel_ns; /* total CUDA-event time of the solver kernel (K5) launches issued by agb_step */
 	uint64_t solver_sms; /* SMs the solver kernel currently runs on (AgbConfig::solver_sms; 0 = no partition). In automatic mode the engine
 	                        re-balances it after every agb_step call from the measured K5 and K4 launch times */
-	uint64_t reserved[1];
+	uint64_t pipeline_groups; /* groups of games the engine advances on their own streams (AgbConfig::pipeline_groups after defaults) */
 } AgbStats;
 int agb_get_stats(AgbEngine *engine, AgbStats *stats);
 
@@ -242,6 +256,9 @@ int agb_get_stats(AgbEngine *engine, AgbStats *stats);
  * against Tree::getInfo({}) (src/search/monte_carlo/Tree.cpp:394-416) */
 int agb_get_root(AgbEngine *engine, int game, int32_t *visits_host, float *priors_host, float *q_host, float *root_value3_host,
 		int32_t *root_visits);
+/* proven scores of game g's root: edge_scores[cells] = Score::to_short of every root edge (Edge::getScore; the default Score for cells without an
+ * edge), *root_score = the root node's (Node::getScore, include/alphagomoku/search/monte_carlo/Node.hpp). For checks of what the solver proved. */
+int agb_get_root_scores(AgbEngine *engine, int game, uint16_t *edge_scores_host, uint16_t *root_score);
 int agb_get_board(AgbEngine *engine, int game, int8_t *board_host, int8_t *sign_to_move, int32_t *move_number);
 /* the root priors as the tree selector currently sees them (PUCTSelector::noisy_policy), noisy_policy[cells]; zeros until the search
  * of the current move has drawn its noise */

@@ -4,6 +4,8 @@
 #pragma once
 #include <agb200.h>
 
+#include <alphagomoku/dataset/GameDataBuffer.hpp>
+#include <alphagomoku/dataset/GameDataStorage.hpp>
 #include <alphagomoku/game/Move.hpp>
 #include <alphagomoku/search/Score.hpp>
 #include <alphagomoku/search/Value.hpp>
@@ -11,8 +13,12 @@
 #include <alphagomoku/utils/configs.hpp>
 #include <alphagomoku/utils/matrix.hpp>
 
+#include <minml/utils/serialization.hpp>
+
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -164,4 +170,134 @@ namespace ag
 			t.markAsProcessedBySolver();
 		}
 	}
+
+	// GeneratorManager's surface (include/alphagomoku/selfplay/GeneratorManager.hpp:87-102) over the device engine: the whole self-play loop of
+	// every GeneratorThread -- select, solve, evaluate, expand, backup, make move, record -- is agb_step; finished games arrive through
+	// agb_pop_finished as GameDataStorage::serialize blobs (format 201) and are added to a real GameDataBuffer, so getGameBuffer() gives the
+	// trainer exactly what the reference's manager gives it. saveState / loadState keep the reference's directory layout
+	// (<working directory>/saved_state/buffer.bin written by GameDataBuffer::save; the games in flight in engine.bin, the engine's own blob).
+	class GeneratorManagerB200
+	{
+			AgbEngine *engine = nullptr;
+			GameDataBuffer game_buffer;
+			std::string working_directory;
+			std::vector<uint8_t> records;
+			int steps_per_poll;
+		public:
+			// `config` carries GameConfig and the SelfplayConfig / SearchConfig fields the engine honours (agb_config_from_json fills it from the
+			// reference's config.json); weights: fp32 blob (NetworkLoader's role, see NNEvaluator_b200.cpp)
+			GeneratorManagerB200(const GameConfig &gameOptions, const AgbConfig &config, const void *weights, size_t weightBytes, int stepsPerPoll = 10) :
+					game_buffer(gameOptions),
+					records(64u << 20),
+					steps_per_poll(stepsPerPoll)
+			{
+				if (agb_create(&config, &engine) != AGB_OK)
+					throw std::runtime_error(std::string("GeneratorManagerB200 : ") + agb_last_error(nullptr));
+				if (agb_load_weights(engine, weights, weightBytes) != AGB_OK)
+					fail("agb_load_weights");
+			}
+			GeneratorManagerB200(const GeneratorManagerB200&) = delete;
+			GeneratorManagerB200& operator=(const GeneratorManagerB200&) = delete;
+			~GeneratorManagerB200()
+			{
+				agb_destroy(engine);
+			}
+			void setWorkingDirectory(const std::string &path)
+			{
+				working_directory = path;
+			}
+			const GameDataBuffer& getGameBuffer() const noexcept
+			{
+				return game_buffer;
+			}
+			GameDataBuffer& getGameBuffer() noexcept
+			{
+				return game_buffer;
+			}
+			bool hasEnoughGames(int numberOfGames) const noexcept
+			{
+				return game_buffer.numberOfGames() >= numberOfGames;
+			}
+			AgbEngine* getEngine() noexcept
+			{
+				return engine;
+			}
+			// start every game from a given position (or empty boards): the opening generator's output goes here (agb_generate_openings)
+			void resetGames(const int8_t *boards = nullptr, const int8_t *signToMove = nullptr)
+			{
+				if (agb_selfplay_reset(engine, boards, signToMove) != AGB_OK)
+					fail("agb_selfplay_reset");
+			}
+			// GeneratorManager::generate (GeneratorManager.cpp:177-218): play until the buffer holds numberOfGames games
+			void generate(int numberOfGames)
+			{
+				while (not hasEnoughGames(numberOfGames))
+				{
+					if (agb_step(engine, steps_per_poll) != AGB_OK)
+						fail("agb_step");
+					collectFinishedGames();
+				}
+			}
+			// GameGenerator.cpp:104-111 (manager.addToBuffer) for every game the device finished since the last call
+			int collectFinishedGames()
+			{
+				size_t used = 0;
+				int n_games = 0;
+				if (agb_pop_finished(engine, records.data(), records.size(), &used, &n_games) != AGB_OK)
+					fail("agb_pop_finished");
+				SerializedObject so;
+				so.save(records.data(), used);
+				size_t offset = 0;
+				for (int i = 0; i < n_games; i++)
+					game_buffer.addGameData(GameDataStorage(so, offset, 201));
+				if (offset != used)
+					throw std::runtime_error("GeneratorManagerB200 : finished-game records do not parse");
+				return n_games;
+			}
+			void saveState(bool saveBuffer)
+			{ // GeneratorManager.cpp:240-263
+				if (working_directory.empty())
+					return;
+				const std::string path = working_directory + "/saved_state/";
+				if (saveBuffer)
+					game_buffer.save(path + "buffer.bin");
+				collectFinishedGames(); // nothing finished may stay on the device: the saved games are the ones in flight
+				size_t used = 0;
+				agb_save_games(engine, nullptr, 0, &used);
+				std::vector<uint8_t> blob(used);
+				if (agb_save_games(engine, blob.data(), blob.size(), &used) != AGB_OK)
+					fail("agb_save_games");
+				FILE *f = std::fopen((path + "engine.bin").c_str(), "wb");
+				if (f == nullptr or std::fwrite(blob.data(), 1, used, f) != used)
+					throw std::runtime_error("GeneratorManagerB200::saveState() : cannot write " + path + "engine.bin");
+				std::fclose(f);
+			}
+			void loadState()
+			{ // GeneratorManager.cpp:264-290
+				if (working_directory.empty())
+					return;
+				const std::string path = working_directory + "/saved_state/";
+				if (FILE *f = std::fopen((path + "buffer.bin").c_str(), "rb"))
+				{
+					std::fclose(f);
+					game_buffer.load(path + "buffer.bin");
+				}
+				if (FILE *f = std::fopen((path + "engine.bin").c_str(), "rb"))
+				{
+					std::vector<uint8_t> blob;
+					uint8_t chunk[65536];
+					size_t n;
+					while ((n = std::fread(chunk, 1, sizeof(chunk), f)) > 0)
+						blob.insert(blob.end(), chunk, chunk + n);
+					std::fclose(f);
+					if (agb_load_games(engine, blob.data(), blob.size()) != AGB_OK)
+						fail("agb_load_games");
+				}
+			}
+		private:
+			[[noreturn]] void fail(const char *what) const
+			{
+				throw std::runtime_error(std::string("GeneratorManagerB200 : ") + what + " : " + agb_last_error(engine));
+			}
+	};
 } /* namespace ag */

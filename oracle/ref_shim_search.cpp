@@ -10,6 +10,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 // the solver's hash keys are private to AlphaBetaSearch; tests need them to give the device table the same bucket mapping
 #define private public
@@ -30,6 +31,7 @@
 #include <alphagomoku/selfplay/NetworkLoader.hpp>
 #include <alphagomoku/utils/configs.hpp>
 #include <alphagomoku/utils/misc.hpp>
+#include <alphagomoku/utils/random.hpp>
 
 #include <minml/utils/serialization.hpp>
 
@@ -124,6 +126,22 @@ extern "C"
 		agref::g_eval_fn = eval_fn;
 		agref::g_eval_ctx = ctx;
 		return new RefSelfplay(gc, sc, use_solver != 0);
+	}
+	// SelfplayConfig::use_symmetries for this instance's evaluator (GeneratorThread's constructor does the same, GeneratorManager.cpp:35)
+	void agref_sp_use_symmetries(void *h, int on)
+	{
+		static_cast<RefSelfplay*>(h)->evaluator.useSymmetries(on != 0);
+	}
+	// the first n values of ag::randInt(r) on a fresh thread, i.e. from a newly constructed thread_local generator (src/utils/random.cpp:17-23):
+	// what an NNEvaluator draws for its first n tasks when it is the only consumer on its thread (NNEvaluator.cpp:134-139)
+	void agref_rand_ints(int r, int n, int32_t *out)
+	{
+		std::thread worker([=]()
+		{
+			for (int i = 0; i < n; i++)
+				out[i] = ag::randInt(r);
+		});
+		worker.join();
 	}
 	void agref_sp_destroy(void *h)
 	{

@@ -170,3 +170,33 @@ class RefSelfplay:
         if self.h:
             self.lib.agref_sp_destroy(self.h)
             self.h = None
+
+
+def run_generator_threads(rules, size, evaluate, seconds, threads=1, games_per_thread=8, max_batch_size=8, evaluator_batch=64, max_simulations=400,
+                          solver_max_positions=100, use_opening=True, use_symmetries=True, init_to="parent", exploration_constant=1.25,
+                          start_boards=None, fast=True):
+    """The reference's own GeneratorManager / GeneratorThread::run loop (oracle/ref_shim_manager.cpp) for `seconds`; `evaluate` as in
+    RefSelfplay. Returns a dict: network evaluations (SearchStats), evaluator batches, finished games, seconds run, evaluator positions."""
+    lib = ctypes.CDLL(REF_LIB_FAST if fast and os.path.exists(REF_LIB_FAST) else REF_LIB)
+
+    def callback(ctx, features, batch, rows, cols, policy, value, action_values, moves_left):
+        f = np.ctypeslib.as_array(features, shape=(batch, rows * cols)).copy()
+        p, v, q = evaluate(f)
+        np.ctypeslib.as_array(policy, shape=(batch, rows * cols))[:] = p
+        np.ctypeslib.as_array(value, shape=(batch, 3))[:] = v
+        av = np.ctypeslib.as_array(action_values, shape=(batch, rows * cols, 3))
+        av[:] = 0.0 if q is None else q
+        np.ctypeslib.as_array(moves_left, shape=(batch,))[:] = 0.0
+
+    cb = EVAL_FN(callback)
+    lib.agref_manager_run.argtypes = [ctypes.c_int] * 11 + [ctypes.c_char_p, ctypes.c_float, ctypes.c_double, EVAL_FN, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p]
+    out = np.zeros(8, np.float64)
+    sb = None
+    if start_boards is not None:
+        sb = np.ascontiguousarray(start_boards, np.int8).reshape(threads * games_per_thread, size * size)
+    rc = lib.agref_manager_run(rules, size, size, threads, games_per_thread, max_batch_size, evaluator_batch, max_simulations, solver_max_positions,
+                               int(use_opening), int(use_symmetries), init_to.encode(), exploration_constant, float(seconds), cb, None, _p(sb), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"agref_manager_run failed ({rc})")
+    return {"nb_network_evaluations": out[0], "evaluator_batches": out[1], "games_finished": out[2], "seconds": out[3], "evaluator_positions": out[4]}

@@ -28,7 +28,7 @@ def test_misuse_is_reported():
     policy, value, _ = eng.evaluate(boards[:2], stm[:2])
     assert np.isfinite(policy).all() and abs(float(value[0].sum()) - 1.0) < 1e-5
     eng.close()
-    for bad in (dict(filters=48, blocks=1), dict(games=4, max_batch_size=4, blocks=1, filters=64, max_boards=8), dict(pipeline_groups=5, games=8, blocks=1, filters=64, max_boards=64),
+    for bad in (dict(filters=48, blocks=1), dict(games=4, max_batch_size=4, blocks=1, filters=64, max_boards=8), dict(pipeline_groups=9, games=16, blocks=1, filters=64, max_boards=128),
                 dict(solver_table_entries=1000, solver_max_positions=10, games=2, blocks=1, filters=64, max_boards=64)):
         kwargs = dict(max_boards=8)
         kwargs.update(bad)

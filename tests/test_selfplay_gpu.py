@@ -314,3 +314,164 @@ def test_root_noise(noise_type):
         assert (eng.get_root_noise(16 + g) == shard.get_root_noise(g)).all()
     eng.close()
     shard.close()
+
+
+# ---- the configuration bench.py times: 20 x 128 network, batch 8, 400 simulations, solver 100, evaluation symmetries on ------------------
+class _OwnThread:
+    """Runs every call of one reference game on its own OS thread: the reference's random generators are thread_local (utils/random.cpp:17-23),
+    so each game's evaluator then draws its symmetries from a fresh mt19937(0) of its own, independent of how the games are interleaved."""
+
+    def __init__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool = ThreadPoolExecutor(max_workers=1)
+
+    def __call__(self, fn, *args):
+        return self.pool.submit(fn, *args).result()
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def _reference_symmetry_stream(n):
+    """The first n symmetries a reference NNEvaluator draws on a fresh thread: randInt(8) of mt19937(0) (NNEvaluator.cpp:134-139)."""
+    import ctypes
+    import refapi
+    lib = ctypes.CDLL(refapi.REF_LIB)
+    out = np.zeros(n, np.int32)
+    lib.agref_rand_ints(8, n, refapi._p(out))
+    assert ((np.random.RandomState(0).randint(0, 2 ** 32, n, dtype=np.uint64) >> 29) == out).all()  # it IS std::mt19937(0) >> 29
+    return out.astype(np.int8)
+
+
+def _benched_engine(games, table_entries, sym_table, **kw):
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob
+    size, blocks, filters = 15, 20, 128
+    eng = agb.Engine(agb.GameConfig(agb.GameRules.FREESTYLE, size, size), max_boards=games * 8, blocks=blocks, filters=filters, games=games, max_batch_size=8,
+                     max_simulations=400, init_to="parent", max_nodes_per_game=1536, max_edges_per_game=1536 * 200, solver_max_positions=100,
+                     solver_table_entries=table_entries, use_symmetries=True, seed=1234, **kw)
+    eng.load_weights(netblob.pack(netblob.random_tensors(size, size, blocks, filters, False), size, size, blocks, filters, False))
+    eng.set_symmetry_table(sym_table)
+    return eng
+
+
+def test_benched_configuration_matches_reference(ref):
+    """Eight full-length freestyle games at the bench's settings (ResNet 20 x 128, 8 leaves per step, 400 simulations, solver at 100 positions
+    with the reference's 4 Mi-entry table, evaluation symmetries ON and replayed from the reference's own generator) against the reference's
+    Tree / Search / AlphaBetaSearch / NNEvaluator, step by step: boards, visit counts, priors, edge and root values to the bit, and the records."""
+    import refapi
+    from alphagomoku_b200 import dataset
+    import bench
+    games, size = 8, 15
+    sym = _reference_symmetry_stream(1 << 17)
+    eng = _benched_engine(games, 4 * 1024 * 1024, sym)
+
+    def evaluate(features):
+        return eng.forward(features)
+
+    bench.select_workload("freestyle15")
+    boards, stm = bench.random_openings(np.random.default_rng(5), games)
+    threads = [_OwnThread() for _ in range(games)]
+    refs = []
+    for g in range(games):
+        r = threads[g](lambda: refapi.RefSelfplay(0, size, evaluate, max_batch_size=8, max_simulations=400, init_to="parent", use_solver=True, solver_max_positions=100))
+        threads[g](r.lib.agref_sp_use_symmetries, r.h, 1)
+        refs.append(r)
+    eng.set_solver_keys(np.stack([r.solver_keys() for r in refs]))
+    eng.selfplay_reset(boards, stm)
+    for g in range(games):
+        threads[g](refs[g].set_position, boards[g], stm[g])
+    active, plies, ref_records = [True] * games, 0, []
+    for step in range(4000):
+        eng.step(1)
+        for g in range(games):
+            if not active[g]:
+                continue
+            status = threads[g](refs[g].step)
+            if status == 2:
+                active[g] = False
+                ref_records.append(refs[g].record())
+                plies += 1
+                continue
+            rb, rstm, _, _ = refs[g].board()
+            db, dstm, _ = eng.get_board(g)
+            assert (db == rb).all() and dstm == rstm, (step, g)
+            rv, rp, rq, rval, rn = refs[g].root()
+            dv, dp, dq, dval, dn = eng.get_root(g)
+            assert dn == rn and (dv == rv).all(), (step, g, dn, rn)
+            assert (dp.view(np.uint32) == rp.view(np.uint32)).all(), (step, g)
+            assert (dq.view(np.uint32) == rq.view(np.uint32)).all(), (step, g)
+            assert (dval.view(np.uint32) == rval.view(np.uint32)).all(), (step, g)
+            plies += status
+        if not any(active):
+            break
+    assert not any(active), "a game did not finish"
+    assert eng.stats()["overflow_flags"] == 0
+    blob, n = eng.pop_finished()
+    device_records = dataset.split_records(blob, n)
+    for rec in ref_records:
+        assert rec in device_records
+    print(f"benched configuration: {games} games, {plies} plies, {step + 1} lockstep steps identical to the reference")
+    for r, t in zip(refs, threads):
+        r.close()
+        t.close()
+    eng.close()
+
+
+def test_small_solver_table_is_sound_and_rarely_changes_moves():
+    """The bench runs 65 536-entry solver tables per game (the reference: 4 Mi). Same games, same seeds, both sizes side by side: as long as two
+    copies of a game are in the same position, nothing one table proves may contradict the other (a win is never a loss or a draw elsewhere),
+    and the share of plies where the played move differs is reported."""
+    games = 8
+    import bench
+    bench.select_workload("freestyle15")
+    sym = _reference_symmetry_stream(1 << 17)
+    big, small = _benched_engine(games, 4 * 1024 * 1024, sym), _benched_engine(games, 65536, sym)
+    boards, stm = bench.random_openings(np.random.default_rng(5), games)
+    keys = np.random.default_rng(7).integers(0, 2 ** 63, (games, 2 * 225, 2), dtype=np.int64).astype(np.uint64)
+    for eng in (big, small):
+        eng.set_solver_keys(keys)
+        eng.selfplay_reset(boards, stm)
+    same = [True] * games
+    plies, differing, proven_compared, contradictions = 0, 0, 0, []
+    stones = [int((boards[g] != 0).sum()) for g in range(games)]
+    for step in range(3000):
+        big.step(1)
+        small.step(1)
+        for g in range(games):
+            if not same[g]:
+                continue
+            b1, s1, n1 = big.get_board(g)
+            b2, s2, n2 = small.get_board(g)
+            if n1 != stones[g] or n2 != stones[g]:  # a move was played (or the game ended and restarted) in at least one copy
+                if n1 == stones[g] or n2 == stones[g]:
+                    continue  # only one copy has moved so far (its root was proven a step earlier): wait for the other
+                if n1 < stones[g] or n2 < stones[g]:
+                    same[g] = False  # the game is over in at least one copy: stop following it
+                    differing += int(n1 >= stones[g] or n2 >= stones[g])
+                    plies += 1
+                elif (b1 == b2).all():
+                    plies += 1
+                    stones[g] = n1
+                else:
+                    differing += 1
+                    plies += 1
+                    same[g] = False
+                continue
+            e1, r1 = big.get_root_scores(g)
+            e2, r2 = small.get_root_scores(g)
+            for a, b in list(zip(e1.tolist(), e2.tolist())) + [(r1, r2)]:
+                pa, pb = (a >> 13) & 3, (b >> 13) & 3  # ProvenValue: 0 loss, 1 draw, 2 unknown, 3 win (Score.hpp)
+                if pa != 2 and pb != 2 and a not in (0, 0xFFFF) and b not in (0, 0xFFFF):
+                    proven_compared += 1
+                    if pa != pb:
+                        contradictions.append((step, g, a, b))
+        if not any(same):
+            break
+    print(f"small solver table: {plies} plies followed, {differing} played differently ({100.0 * differing / max(plies, 1):.1f} %), "
+          f"{proven_compared} proven scores compared, {len(contradictions)} contradictions")
+    assert not contradictions, contradictions[:5]
+    assert plies >= 40 and proven_compared > 0
+    assert big.stats()["overflow_flags"] == 0 and small.stats()["overflow_flags"] == 0
+    big.close()
+    small.close()
