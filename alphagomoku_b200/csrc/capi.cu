@@ -165,6 +165,7 @@ extern "C"
 	{
 		if (e == nullptr)
 			return;
+		const agb::DeviceGuard on_device(e);
 		if (e->stream)
 			cudaStreamSynchronize(e->stream);
 		agb::selfplay_destroy(e);
@@ -192,6 +193,7 @@ extern "C"
 	}
 	int agb_synchronize(AgbEngine *e)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		return AGB_OK;
 	}
@@ -202,6 +204,7 @@ extern "C"
 
 	int agb_get_tables(AgbEngine *e, uint8_t *pattern_types_host, uint8_t *half_open_3_host, uint8_t *threats_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		if (pattern_types_host != nullptr or half_open_3_host != nullptr)
 		{
 			std::string raw(1u << 20, '\0');
@@ -232,6 +235,7 @@ extern "C"
 
 	int agb_set_boards_dev(AgbEngine *e, const int8_t *boards_dev, const int8_t *sign_to_move_dev, int n, uint32_t *features_dev)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_REQUIRE(e, n >= 0 and n <= e->store.capacity, "n exceeds max_boards");
 		AGB_REQUIRE(e, boards_dev and sign_to_move_dev and features_dev, "null pointer");
 		if (n == 0)
@@ -240,6 +244,7 @@ extern "C"
 	}
 	int agb_set_boards(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, uint32_t *features_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_REQUIRE(e, n >= 0 and n <= e->store.capacity, "n exceeds max_boards");
 		AGB_REQUIRE(e, boards_host and sign_to_move_host and features_host, "null pointer");
 		if (n == 0)
@@ -271,14 +276,17 @@ extern "C"
 	}
 	int agb_add_moves(AgbEngine *e, const uint16_t *moves_host, int n)
 	{
+		const agb::DeviceGuard on_device(e);
 		return add_undo(e, moves_host, n, false);
 	}
 	int agb_undo_moves(AgbEngine *e, const uint16_t *moves_host, int n)
 	{
+		const agb::DeviceGuard on_device(e);
 		return add_undo(e, moves_host, n, true);
 	}
 	int agb_encode(AgbEngine *e, int n, uint32_t *features_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_REQUIRE(e, n >= 0 and n <= e->store.capacity, "n exceeds max_boards");
 		AGB_REQUIRE(e, features_host, "null pointer");
 		if (n == 0)
@@ -290,6 +298,7 @@ extern "C"
 	int agb_get_state(AgbEngine *e, int n, uint8_t *pattern_types_host, uint8_t *threats_host, uint8_t *legal_host, uint8_t *forbidden_host,
 			int32_t *hist_counts_host, uint16_t *hist_cells_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_REQUIRE(e, n >= 0 and n <= e->store.capacity, "n exceeds max_boards");
 		if (n == 0)
 			return AGB_OK;
@@ -344,6 +353,7 @@ extern "C"
 	}
 	int agb_augment(AgbEngine *e, uint32_t *features_host, const int8_t *symmetry_host, int n)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_REQUIRE(e, n >= 0 and n <= e->store.capacity, "n exceeds max_boards");
 		AGB_REQUIRE(e, features_host and symmetry_host, "null pointer");
 		if (n == 0)
@@ -360,6 +370,7 @@ extern "C"
 	}
 	int agb_get_outcomes(AgbEngine *e, const int8_t *boards_host, const uint16_t *last_moves_host, int n, int8_t *outcomes_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		AGB_REQUIRE(e, n >= 0 and n <= e->store.capacity, "n exceeds max_boards");
 		AGB_REQUIRE(e, boards_host and last_moves_host and outcomes_host, "null pointer");
 		if (n == 0)

@@ -59,6 +59,26 @@ struct AgbEngine
 
 namespace agb
 {
+	// Every entry point that takes an engine runs with the engine's device current and restores the caller's afterwards: one process may hold
+	// engines on several GPUs (one GeneratorThread per DeviceConfig in the reference; two engines of an arena on different devices).
+	struct DeviceGuard
+	{
+			int previous = -1;
+			explicit DeviceGuard(const AgbEngine *e)
+			{
+				if (e != nullptr and cudaGetDevice(&previous) == cudaSuccess and previous != e->cfg.device)
+					cudaSetDevice(e->cfg.device);
+				else
+					previous = -1;
+			}
+			~DeviceGuard()
+			{
+				if (previous >= 0)
+					cudaSetDevice(previous);
+			}
+			DeviceGuard(const DeviceGuard&) = delete;
+			DeviceGuard& operator=(const DeviceGuard&) = delete;
+	};
 	// The evaluator's randInt(8) per scheduled task as a counter-based stream keyed by (seed, global game id, evaluations drawn so far), so that
 	// results do not depend on how games are sharded; or, for replaying a reference run, a caller-supplied table indexed by that counter.
 	struct SymmetryStream

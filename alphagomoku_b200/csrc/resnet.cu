@@ -990,12 +990,14 @@ extern "C"
 	}
 	int agb_load_weights(AgbEngine *e, const void *blob_host, size_t bytes)
 	{
+		const agb::DeviceGuard on_device(e);
 		if (blob_host == nullptr)
 			return e->fail(AGB_EINVAL, "null pointer");
 		return agb::net_load(e, static_cast<const float*>(blob_host), bytes);
 	}
 	int agb_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n, float *policy_dev, float *value_dev, float *q_dev)
 	{
+		const agb::DeviceGuard on_device(e);
 		if (n < 0 or n > e->store.capacity)
 			return e->fail(AGB_EINVAL, "n exceeds max_boards");
 		if (features_dev == nullptr or policy_dev == nullptr or value_dev == nullptr)
@@ -1007,6 +1009,7 @@ extern "C"
 	int agb_evaluate(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *symmetry_host, int n, float *policy_host,
 			float *value_host, float *q_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		if (n < 0 or n > e->store.capacity)
 			return e->fail(AGB_EINVAL, "n exceeds max_boards");
 		if (boards_host == nullptr or sign_to_move_host == nullptr or policy_host == nullptr or value_host == nullptr)
@@ -1066,6 +1069,7 @@ extern "C"
 	}
 	int agb_forward(AgbEngine *e, const uint32_t *features_host, int n, float *policy_host, float *value_host, float *q_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		if (n < 0 or n > e->store.capacity)
 			return e->fail(AGB_EINVAL, "n exceeds max_boards");
 		if (features_host == nullptr or policy_host == nullptr or value_host == nullptr)

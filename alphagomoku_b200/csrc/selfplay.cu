@@ -188,7 +188,7 @@ namespace agb
 			int8_t *openings = nullptr; // [n_openings][cells]
 			int8_t *opening_stm = nullptr;
 			int n_openings = 0;
-			int32_t *opening_cursor = nullptr;
+			uint32_t *opening_cursor = nullptr; // [games] restarts of each game so far (selects its next opening)
 			// last sample per game (dense), for parity checks and K8
 			int32_t *sample_visits = nullptr; // [games][cells]
 			float *sample_prior = nullptr, *sample_win = nullptr, *sample_draw = nullptr; // [games][cells]
@@ -1405,9 +1405,17 @@ namespace agb
 				const int8_t *src = nullptr;
 				if (p.s.n_openings > 0)
 				{
-					int k = 0;
+					// which opening comes next depends only on the game's global id and on how often it has restarted: reproducible whatever the
+					// scheduling, the stream layout or the sharding
+					unsigned k = 0;
 					if (lane == 0)
-						k = atomicAdd(p.s.opening_cursor, 1) % p.s.n_openings;
+					{
+						unsigned long long z = p.sym_seed ^ 0x6F70656E696E67ull ^ (static_cast<unsigned long long>(p.first_game_id + g) << 32) ^ p.s.opening_cursor[g]++;
+						z += 0x9E3779B97F4A7C15ull;
+						z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+						z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+						k = static_cast<unsigned>((z ^ (z >> 31)) % static_cast<unsigned long long>(p.s.n_openings));
+					}
 					k = __shfl_sync(kFullMask, k, 0);
 					src = p.s.openings + static_cast<size_t>(k) * cells;
 					next_stm = p.s.opening_stm[k];
@@ -1693,7 +1701,7 @@ namespace agb
 		}
 		alloc(&s->zobrist, cells * 2 + 2);
 		alloc(&s->stats, 16);
-		alloc(&s->opening_cursor, 1);
+		alloc(&s->opening_cursor, G);
 		alloc(&s->sample_visits, G * cells);
 		alloc(&s->sample_prior, G * cells);
 		alloc(&s->sample_win, G * cells);
@@ -1791,7 +1799,7 @@ namespace agb
 			k = splitmix64(seed);
 		AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->zobrist, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->stats, 0, 16 * 8, e->stream));
-		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->opening_cursor, 0, 4, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->opening_cursor, 0, G * sizeof(uint32_t), e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->paused, 0, G, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->decision, 0, G * sizeof(uint16_t), e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->fin_used, 0, 8, e->stream));
@@ -1849,6 +1857,7 @@ extern "C"
 
 	int agb_selfplay_reset(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games");
@@ -1881,6 +1890,7 @@ extern "C"
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->table, 0xFF, G * s->table_size * sizeof(int32_t), e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->paused, 0, G, e->stream));
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->decision, 0, G * sizeof(uint16_t), e->stream));
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(s->opening_cursor, 0, G * sizeof(uint32_t), e->stream));
 		if (s->noise_counter != nullptr)
 			AGB_CUDA_CHECK(e, cudaMemsetAsync(s->noise_counter, 0, G * sizeof(uint32_t), e->stream));
 		if (s->sym_counter != nullptr)
@@ -1916,6 +1926,7 @@ extern "C"
 	};
 	int agb_save_games(AgbEngine *e, void *blob_host, size_t capacity, size_t *used)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games");
@@ -1960,6 +1971,7 @@ extern "C"
 	}
 	int agb_load_games(AgbEngine *e, const void *blob_host, size_t bytes)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games");
@@ -2022,6 +2034,7 @@ extern "C"
 	int agb_think(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *active_host, uint16_t *moves_host,
 			float *root_values_host, int max_steps)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games");
@@ -2076,6 +2089,7 @@ extern "C"
 
 	int agb_set_symmetry_table(AgbEngine *e, const int8_t *table_host, int n)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr or s->sym_counter == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games or without use_symmetries");
@@ -2100,6 +2114,7 @@ extern "C"
 
 	int agb_set_solver_keys(AgbEngine *e, const uint64_t *keys_host, size_t n_words)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		const size_t per_set = static_cast<size_t>(e->cells) * 4;
 		const size_t games = (s != nullptr) ? static_cast<size_t>(s->games) : 0;
@@ -2129,6 +2144,7 @@ extern "C"
 	// diagnostics (not part of the public header): per game, SM clocks and positions visited by the last solver launch
 	int agb_debug_solver_load(AgbEngine *e, unsigned long long *out_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr or s->solver.game_cycles == nullptr)
 			return e->fail(AGB_ESTATE, "solver is off");
@@ -2139,6 +2155,7 @@ extern "C"
 
 	int agb_step(AgbEngine *e, int n_steps)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games");
@@ -2286,7 +2303,11 @@ extern "C"
 			const double solver_work = bias * call_solver_ms * s->solver_sms, net_work = call_nn_ms * s->net_sms;
 			const double target = sms * solver_work / (solver_work + net_work);
 			int next = static_cast<int>(s->solver_sms + 0.75 * (target - s->solver_sms) + 0.5) & ~1;
-			next = std::max(8, std::min(next, sms / 2));
+			// more SMs than about three quarters of what holds every game of a group at once (28 warps per SM) do not shorten a solver launch any
+			// further -- it then ends with its slowest games, not with the queue -- and only starve the network (steady state, 2048 games per group:
+			// 56 SMs 138 ms of K5 per step, 74 SMs 138 ms; K4 102 against 126 ms)
+			const int useful = std::max(8, static_cast<int>(0.77 * per_group / 28.0) & ~1);
+			next = std::max(8, std::min(next, std::min(sms / 2, useful)));
 			s->solver_sms = next;
 			s->net_sms = sms - next;
 		}
@@ -2318,6 +2339,7 @@ extern "C"
 
 	int agb_pop_finished(AgbEngine *e, void *records_host, size_t capacity, size_t *used, int *n_games)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr)
 			return e->fail(AGB_ESTATE, "engine was created without games");
@@ -2344,6 +2366,7 @@ extern "C"
 	}
 	int agb_get_stats(AgbEngine *e, AgbStats *stats)
 	{
+		const agb::DeviceGuard on_device(e);
 		if (stats == nullptr)
 			return AGB_EINVAL;
 		*stats = AgbStats { };
@@ -2376,6 +2399,7 @@ extern "C"
 	}
 	int agb_get_root(AgbEngine *e, int game, int32_t *visits_host, float *priors_host, float *q_host, float *root_value3_host, int32_t *root_visits)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr or game < 0 or game >= s->games)
 			return e->fail(AGB_EINVAL, "bad game index");
@@ -2427,6 +2451,7 @@ extern "C"
 	}
 	int agb_get_root_scores(AgbEngine *e, int game, uint16_t *edge_scores_host, uint16_t *root_score)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr or game < 0 or game >= s->games or edge_scores_host == nullptr or root_score == nullptr)
 			return e->fail(AGB_EINVAL, "bad game index or null pointer");
@@ -2449,6 +2474,7 @@ extern "C"
 	}
 	int agb_get_root_noise(AgbEngine *e, int game, float *noisy_policy_host)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr or game < 0 or game >= s->games or noisy_policy_host == nullptr)
 			return e->fail(AGB_EINVAL, "bad game index or null pointer");
@@ -2475,6 +2501,7 @@ extern "C"
 	}
 	int agb_get_board(AgbEngine *e, int game, int8_t *board_host, int8_t *sign_to_move, int32_t *move_number)
 	{
+		const agb::DeviceGuard on_device(e);
 		SelfplayState *s = e->selfplay;
 		if (s == nullptr or game < 0 or game >= s->games)
 			return e->fail(AGB_EINVAL, "bad game index");

@@ -373,6 +373,7 @@ namespace agb
 extern "C" int agb_solve(AgbEngine *e, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, int max_positions, uint16_t *scores_host,
 		int32_t *n_actions_host, uint16_t *moves_host, uint16_t *action_scores_host, int32_t *flags_host)
 {
+	const agb::DeviceGuard on_device(e);
 	using namespace agb;
 	if (boards_host == nullptr or sign_to_move_host == nullptr or scores_host == nullptr)
 		return e->fail(AGB_EINVAL, "null pointer");

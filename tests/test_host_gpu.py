@@ -40,8 +40,9 @@ def test_reference_generator_thread_on_the_b200_evaluator(tmp_path):
     a, b = str(tmp_path / "b200.bin"), str(tmp_path / "shadow.bin")
     out_a = _run(B200, "generator", weights, a, "6")
     out_b = _run(SHADOW, "generator", weights, b, "6")
-    assert out_a == out_b and out_a.startswith("games "), (out_a, out_b)
-    assert int(out_a.split()[1]) >= 6
+    last_a, last_b = out_a.strip().splitlines()[-1], out_b.strip().splitlines()[-1]  # the rest is GeneratorManager::printStats (timings differ)
+    assert last_a == last_b and last_a.startswith("games "), (last_a, last_b)
+    assert int(last_a.split()[1]) >= 6
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
@@ -51,13 +52,14 @@ def test_generator_manager_over_the_device_engine(tmp_path, ref):
     import refapi
     weights = _weights(tmp_path)
     out = _run(B200, "device", weights, str(tmp_path / "work"), "48")
-    lines = out.strip().splitlines()
+    lines = [line for line in out.strip().splitlines() if line.startswith(("first half", "resumed with"))]
     assert lines[0].startswith("first half: games ") and lines[1].startswith("resumed with ")
     first = int(lines[0].split()[3])
-    resumed_with, final = int(lines[1].split()[2]), int(lines[1].split()[8])
+    resumed_with, final = int(lines[1].split()[2]), int(lines[1].split()[7])
     assert first >= 24 and resumed_with == first and final >= 48
     for name, expect in (("saved_state/buffer.bin", first), ("buffer_final.bin", final)):
         spg, mpg, outcomes = np.zeros(4096, np.int32), np.zeros(4096, np.int32), np.zeros(4096, np.int32)
-        rows, cols = np.zeros(1, np.int32), np.zeros(1, np.int32)
-        n = ref.lib.agref_buffer_load(str(tmp_path / "work" / name).encode(), refapi._p(spg), refapi._p(mpg), refapi._p(outcomes), 4096, refapi._p(rows), refapi._p(cols))
-        assert n == expect and (spg[:n] > 0).all() and (outcomes[:n] >= 1).all()
+        rows, cols, rules = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32)
+        n = ref.lib.agref_buffer_load(str(tmp_path / "work" / name).encode(), refapi._p(spg), refapi._p(mpg), refapi._p(outcomes), 4096, refapi._p(rows), refapi._p(cols),
+                                      refapi._p(rules))
+        assert n == expect and (spg[:n] > 0).all() and (outcomes[:n] >= 1).all() and rows[0] == 15 and rules[0] == 1
