@@ -1934,10 +1934,31 @@ extern "C"
 			return e->fail(AGB_EINVAL, "null pointer");
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		const size_t G = s->games, cells = s->cells;
+		{ // finished games still on the device would be lost by a save / load round trip: the host pops them first (like the reference, whose
+		  // finished games are already in the manager's buffer when saveState runs, GeneratorManager.cpp:240-263)
+			unsigned long long pending = 0;
+			AGB_CUDA_CHECK(e, cudaMemcpy(&pending, s->fin_used, 8, cudaMemcpyDeviceToHost));
+			if (pending != 0)
+				return e->fail(AGB_ESTATE, "finished games are waiting on the device: call agb_pop_finished before agb_save_games");
+		}
 		std::vector<int8_t> boards(G * cells), stm(G);
 		std::vector<int32_t> n_moves(G), rec_len(G), rec_samples(G);
 		std::vector<uint16_t> moves(G * cells);
 		std::vector<uint8_t> rec(G * s->rec_cap);
+		// version 2: the per-game random streams (evaluation symmetries, root noise, opening choice) and the openings pool, so that a resumed run
+		// continues exactly like an uninterrupted one
+		std::vector<uint32_t> sym_counter(G, 0), noise_counter(G, 0), opening_cursor(G, 0);
+		std::vector<int8_t> openings(static_cast<size_t>(s->n_openings) * cells), opening_stm(s->n_openings);
+		if (s->sym_counter != nullptr)
+			AGB_CUDA_CHECK(e, cudaMemcpy(sym_counter.data(), s->sym_counter, G * 4, cudaMemcpyDeviceToHost));
+		if (s->noise_counter != nullptr)
+			AGB_CUDA_CHECK(e, cudaMemcpy(noise_counter.data(), s->noise_counter, G * 4, cudaMemcpyDeviceToHost));
+		AGB_CUDA_CHECK(e, cudaMemcpy(opening_cursor.data(), s->opening_cursor, G * 4, cudaMemcpyDeviceToHost));
+		if (s->n_openings > 0)
+		{
+			AGB_CUDA_CHECK(e, cudaMemcpy(openings.data(), s->openings, openings.size(), cudaMemcpyDeviceToHost));
+			AGB_CUDA_CHECK(e, cudaMemcpy(opening_stm.data(), s->opening_stm, opening_stm.size(), cudaMemcpyDeviceToHost));
+		}
 		AGB_CUDA_CHECK(e, cudaMemcpy(boards.data(), s->root_board, boards.size(), cudaMemcpyDeviceToHost));
 		AGB_CUDA_CHECK(e, cudaMemcpy(stm.data(), s->root_stm, G, cudaMemcpyDeviceToHost));
 		AGB_CUDA_CHECK(e, cudaMemcpy(n_moves.data(), s->n_moves, G * 4, cudaMemcpyDeviceToHost));
@@ -1951,7 +1972,7 @@ extern "C"
 			const uint8_t *b = static_cast<const uint8_t*>(ptr);
 			out.insert(out.end(), b, b + bytes);
 		};
-		const AgbSavedHeader header { 0x53424741u /* "AGBS" */, 1u, s->games, e->cfg.rows, e->cfg.cols, e->cfg.rules };
+		const AgbSavedHeader header { 0x53424741u /* "AGBS" */, 2u, s->games, e->cfg.rows, e->cfg.cols, e->cfg.rules };
 		put(&header, sizeof(header));
 		for (size_t g = 0; g < G; g++)
 		{
@@ -1963,6 +1984,13 @@ extern "C"
 			put(&rec_len[g], 4);
 			put(rec.data() + g * s->rec_cap, rec_len[g]);
 		}
+		put(sym_counter.data(), G * 4);
+		put(noise_counter.data(), G * 4);
+		put(opening_cursor.data(), G * 4);
+		const int32_t n_openings = s->n_openings;
+		put(&n_openings, 4);
+		put(openings.data(), openings.size());
+		put(opening_stm.data(), opening_stm.size());
 		*used = out.size();
 		if (blob_host == nullptr or capacity < out.size())
 			return e->fail(AGB_ENOMEM, "state buffer too small: need " + std::to_string(out.size()) + " bytes");
@@ -1981,7 +2009,7 @@ extern "C"
 			return e->fail(AGB_EINVAL, "saved state is truncated");
 		std::memcpy(&header, cur, sizeof(header));
 		cur += sizeof(header);
-		if (header.magic != 0x53424741u or header.version != 1u)
+		if (header.magic != 0x53424741u or (header.version != 1u and header.version != 2u))
 			return e->fail(AGB_EINVAL, "not a saved-games blob of this library");
 		if (header.games != s->games or header.rows != e->cfg.rows or header.cols != e->cfg.cols or header.rules != e->cfg.rules)
 			return e->fail(AGB_EINVAL, "saved state was written for another configuration (games, board or rules differ)");
@@ -2006,7 +2034,42 @@ extern "C"
 			if (not ok)
 				return e->fail(AGB_EINVAL, "saved state is truncated or corrupt at game " + std::to_string(g));
 		}
+		std::vector<uint32_t> sym_counter(G, 0), noise_counter(G, 0), opening_cursor(G, 0);
+		std::vector<int8_t> openings, opening_stm;
+		int32_t n_openings = -1;
+		if (header.version >= 2u)
+		{
+			bool ok = get(sym_counter.data(), G * 4) and get(noise_counter.data(), G * 4) and get(opening_cursor.data(), G * 4) and get(&n_openings, 4);
+			ok = ok and n_openings >= 0 and n_openings <= static_cast<int32_t>(G);
+			if (ok)
+			{
+				openings.resize(static_cast<size_t>(n_openings) * cells);
+				opening_stm.resize(n_openings);
+				ok = get(openings.data(), openings.size()) and get(opening_stm.data(), opening_stm.size());
+			}
+			if (not ok)
+				return e->fail(AGB_EINVAL, "saved state is truncated or corrupt in its random-stream section");
+		}
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		if (header.version >= 2u)
+		{
+			if (s->sym_counter != nullptr)
+				AGB_CUDA_CHECK(e, cudaMemcpy(s->sym_counter, sym_counter.data(), G * 4, cudaMemcpyHostToDevice));
+			if (s->noise_counter != nullptr)
+				AGB_CUDA_CHECK(e, cudaMemcpy(s->noise_counter, noise_counter.data(), G * 4, cudaMemcpyHostToDevice));
+			AGB_CUDA_CHECK(e, cudaMemcpy(s->opening_cursor, opening_cursor.data(), G * 4, cudaMemcpyHostToDevice));
+			if (n_openings > 0)
+			{
+				if (s->openings == nullptr)
+				{
+					AGB_CUDA_CHECK(e, cudaMalloc(&s->openings, G * cells));
+					AGB_CUDA_CHECK(e, cudaMalloc(&s->opening_stm, G));
+				}
+				AGB_CUDA_CHECK(e, cudaMemcpy(s->openings, openings.data(), openings.size(), cudaMemcpyHostToDevice));
+				AGB_CUDA_CHECK(e, cudaMemcpy(s->opening_stm, opening_stm.data(), opening_stm.size(), cudaMemcpyHostToDevice));
+			}
+			s->n_openings = n_openings;
+		}
 		AGB_CUDA_CHECK(e, cudaMemcpy(s->root_board, boards.data(), boards.size(), cudaMemcpyHostToDevice));
 		AGB_CUDA_CHECK(e, cudaMemcpy(s->root_stm, stm.data(), G, cudaMemcpyHostToDevice));
 		AGB_CUDA_CHECK(e, cudaMemcpy(s->n_moves, n_moves.data(), G * 4, cudaMemcpyHostToDevice));

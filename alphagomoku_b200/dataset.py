@@ -176,6 +176,99 @@ def training_targets_visits(sample):
             "sign_to_move": sign, "moves_left": float(sample["moves_left"])}
 
 
+_libm = None
+
+
+def _expf_logf():
+    """glibc's expf / logf: SamplerValues calls std::exp / std::log on floats, and bit-identical targets need the same routines."""
+    global _libm
+    if _libm is None:
+        import ctypes
+        import ctypes.util
+        lib = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        lib.expf.restype = lib.logf.restype = ctypes.c_float
+        lib.expf.argtypes = lib.logf.argtypes = [ctypes.c_float]
+        _libm = (lib.expf, lib.logf)
+    return _libm
+
+
+def _score_distance(s):
+    """Score::getDistance (search/Score.hpp:101-114)."""
+    pv, ev = (s >> 13) & 3, (s & 8191) - 4000
+    return ev if pv in (0, 1) else (-ev if pv == 3 else 0)
+
+
+def training_targets_values(sample):
+    """SamplerValues::prepare_training_data (src/dataset/Sampler.cpp:138-216): the policy target is a softmax over 50 * Q + log(prior) of the
+    empty cells (proven moves get +-1 / distance terms, unvisited ones the prior-weighted mean), in float32 step by step."""
+    import numpy as np
+    f32 = np.float32
+    expf, logf = _expf_logf()
+    cells = sample["rows"] * sample["cols"]
+    board, scores, prior = sample["board"], sample["action_scores"], sample["policy_prior"]
+    visits = sample["visit_count"].copy()
+    values = sample["action_values"]
+    action_targets = np.zeros((cells, 2), np.float32)
+    policy = np.zeros(cells, np.float32)
+
+    def value_of(v, sc):  # get_value (Sampler.cpp:21-24)
+        return _score_to_value(sc) if _score_is_proven(sc) else (v[0], v[1])
+
+    def expectation(v):
+        return f32(f32(v[0]) + f32(0.5) * f32(v[1]))
+
+    unvisited, max_n = 0, 0
+    sum_pq, sum_p = f32(0), f32(0)
+    for i in range(cells):
+        if board[i] == 0:
+            sc = int(scores[i])
+            if sample["visit_count"][i] > 0 or _score_is_proven(sc):
+                q = value_of(values[i], sc)
+                sum_pq = f32(sum_pq + f32(prior[i] * expectation(q)))
+                sum_p = f32(sum_p + prior[i])
+                max_n = max(max_n, int(sample["visit_count"][i]))
+                visits[i] = max(1, visits[i])
+            else:
+                unvisited += 1
+    minimax_v = expectation(value_of(sample["minimax_value"], sample["minimax_score"]))
+    sum_pq = f32(f32(sum_p * sum_pq) + f32(f32(f32(1.0) - sum_p) * minimax_v))
+    max_value = f32(np.finfo(np.float32).min)
+    eps = f32(np.finfo(np.float32).eps)
+    for i in range(cells):
+        if board[i] == 0:
+            q = sum_pq
+            with np.errstate(divide="ignore", invalid="ignore"):
+                p = max(f32(0.0), f32(f32(f32(1.0) - sum_p) / f32(unvisited)))
+            if visits[i] > 0:
+                sc = int(scores[i])
+                pv = (sc >> 13) & 3  # Score::getProvenValue
+                if pv == 0:
+                    q = f32(f32(-1.0) / f32(f32(1.0) + f32(_score_distance(sc))))
+                elif pv == 1:
+                    q = f32(0.5)
+                elif pv == 3:
+                    q = f32(f32(1.0) + f32(f32(2.0) / f32(f32(1.0) + f32(_score_distance(sc)))))
+                else:
+                    q = expectation(values[i])
+                action_targets[i] = value_of(values[i], sc)
+                p = prior[i]
+            policy[i] = f32(f32(f32(50.0) * q) + f32(logf(f32(eps + f32(p)))))
+            max_value = max(max_value, policy[i])
+    total = f32(0)
+    for i in range(cells):
+        if board[i] == 0:
+            policy[i] = f32(expf(max(f32(-20.0), f32(policy[i] - max_value))))
+            total = f32(total + policy[i])
+    for i in range(cells):
+        if board[i] == 0:
+            policy[i] = f32(policy[i] / total)
+    sign = sample["played_move"] & 3
+    outcome = sample["game_outcome"]
+    value = (0.0, 1.0) if outcome == 1 else ((1.0, 0.0) if (outcome == 2) == (sign == 1) else (0.0, 0.0))
+    return {"policy_target": policy, "action_values_target": action_targets, "visit_count": visits, "value_target": value,
+            "sign_to_move": sign, "moves_left": float(sample["moves_left"])}
+
+
 def _normalize(x):
     """normalize(matrix<float>&) of the reference (utils/misc.cpp): divide by the sequential float sum."""
     import numpy as np

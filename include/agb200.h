@@ -206,7 +206,8 @@ int agb_think(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_t
 		float *root_values_host, int max_steps);
 
 /* games in flight (GeneratorManager::saveState / loadState, src/selfplay/GeneratorManager.cpp:240-290): every game's position, move
- * list and the samples recorded so far. *used receives the size; AGB_ENOMEM when capacity is too small (call once with NULL to size the
+ * list and the samples recorded so far, plus the per-game random streams (evaluation symmetries, root noise, opening choice) and the openings
+ * pool, so that a resumed run continues like an uninterrupted one. Finished games must have been popped first (AGB_ESTATE otherwise). *used receives the size; AGB_ENOMEM when capacity is too small (call once with NULL to size the
  * buffer). Loading needs an engine with the same games / board / rules; the search trees start empty, as after the reference's
  * GameGenerator::load -> prepare_search. */
 int agb_save_games(AgbEngine *engine, void *blob_host, size_t capacity, size_t *used);

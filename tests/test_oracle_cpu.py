@@ -523,5 +523,14 @@ def test_trainer_side_reader_matches_the_reference(ref, tmp_path):
             assert (targets["visit_count"] == visits_t.astype(np.int32)).all()
             assert np.float32(targets["value_target"][0]) == scalars_t[0] and np.float32(targets["value_target"][1]) == scalars_t[1]
             assert targets["moves_left"] == scalars_t[4] and targets["sign_to_move"] == int(scalars_t[5])
+            # SamplerValues (the default sampler_type of the reference's TrainingConfig, configs.hpp:170)
+            rc = lib.agref_buffer_sample_with(path.encode(), g, k, _p(board), _p(visits), _p(prior), _p(values), _p(scores), _p(scalars), _p(policy_t), _p(value_t),
+                                              _p(visits_t), _p(scalars_t), 1)
+            assert rc == 0
+            targets = dataset.training_targets_values(mine)
+            assert (targets["policy_target"].view(np.uint32) == policy_t.view(np.uint32)).all(), np.abs(targets["policy_target"] - policy_t).max()
+            assert (targets["action_values_target"].view(np.uint32) == value_t.view(np.uint32)).all()
+            assert (targets["visit_count"] == visits_t.astype(np.int32)).all()
+            assert np.float32(targets["value_target"][0]) == scalars_t[0] and np.float32(targets["value_target"][1]) == scalars_t[1]
             checked += 1
     assert checked >= 10
