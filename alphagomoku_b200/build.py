@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
-SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu", "partition.cu"]
+SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu", "solver_plain.cu", "partition.cu"]
 # host-only sources, compiled by g++ with the reference's floating-point flags (no FMA contraction, libm overloads as in the reference)
 HOST_SOURCES = ["openings.cpp", "config_json.cpp"]
 HOST_FLAGS = ["-O2", "-std=c++17", "-msse2", "-fPIC", "-I/usr/local/cuda/include"]
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         extra = ["-fmad=false"] if src == "selfplay.cu" else []  # tree arithmetic follows the reference op by op (no FMA contraction)
         if src == "resnet.cu" and os.environ.get("AGB_NET_FLAGS"):
             extra = os.environ["AGB_NET_FLAGS"].split()  # experiments with the network kernel's code generation
-        if src == "solver.cu" and os.environ.get("AGB_SOLVER_FLAGS"):
+        if src in ("solver.cu", "solver_plain.cu") and os.environ.get("AGB_SOLVER_FLAGS"):
             extra = os.environ["AGB_SOLVER_FLAGS"].split()  # experiments with the solver kernel's code generation
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

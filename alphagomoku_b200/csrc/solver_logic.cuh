@@ -13,9 +13,12 @@
 #pragma once
 #include "patterns_logic.cuh"
 
+#ifndef AGB_SOLVER_NS
+#define AGB_SOLVER_NS solver // solver_plain in the build without renju (solver_kernel.cuh)
+#endif
 namespace agb
 {
-	namespace solver
+	namespace AGB_SOLVER_NS
 	{
 		using namespace plogic;
 
@@ -35,33 +38,36 @@ namespace agb
 		// layout: [group 0..14][neighbour index 0..255][defender colour 0 cross / 1 circle]; groups 0-4 five, 5-8 open four,
 		// 9-14 double four
 		constexpr int kDefGroups = 15;
+		// stone patterns (as 2-bit-per-cell words) that identify where the threat sits in the 13-cell window, for cross as attacker. The tables
+		// live in constant memory on the device (a function-local array would be rebuilt on the stack by every call)
+#ifdef __CUDA_ARCH__
+#define AGB_MASK_TABLE static __constant__ const
+#else
+#define AGB_MASK_TABLE static const
+#endif
+		namespace mask_tables
+		{
+			AGB_MASK_TABLE uint32_t five[5] = { 85u, 277u, 325u, 337u, 340u };
+			AGB_MASK_TABLE uint32_t open_four[4] = { 84u, 276u, 324u, 336u };
+			AGB_MASK_TABLE uint32_t double_four[6] = { 4177u, 4369u, 4417u, 20549u, 20741u, 86037u };
+			AGB_MASK_TABLE uint8_t double_four_len[6] = { 7, 7, 7, 8, 8, 9 };
+			AGB_MASK_TABLE uint8_t double_four_off[6] = { 2, 3, 4, 2, 3, 2 };
+			AGB_MASK_TABLE uint32_t half_open_four[20] = { 21u, 69u, 81u, 84u, 21u, 261u, 273u, 276u, 69u, 261u, 321u, 324u, 81u, 273u, 321u, 336u, 84u, 276u, 324u, 336u };
+			AGB_MASK_TABLE uint8_t half_open_four_off[20] = { 3, 4, 5, 6, 2, 4, 5, 6, 2, 3, 5, 6, 2, 3, 4, 6, 2, 3, 4, 5 };
+			AGB_MASK_TABLE uint32_t open_three[12] = { 20u, 68u, 80u, 20u, 260u, 272u, 68u, 260u, 320u, 80u, 272u, 320u };
+			AGB_MASK_TABLE uint8_t open_three_off[12] = { 3, 4, 5, 2, 4, 5, 2, 3, 5, 2, 3, 4 };
+		}
 		struct DefMasks
-		{ // stone patterns (as 2-bit-per-cell words) that identify where the threat sits in the 13-cell window, for cross as attacker
-				static AGB_HD uint32_t five(int i) { const uint32_t m[5] = { 85u, 277u, 325u, 337u, 340u }; return m[i]; }
-				static AGB_HD uint32_t open_four(int i) { const uint32_t m[4] = { 84u, 276u, 324u, 336u }; return m[i]; }
-				static AGB_HD uint32_t double_four(int i) { const uint32_t m[6] = { 4177u, 4369u, 4417u, 20549u, 20741u, 86037u }; return m[i]; }
-				static AGB_HD int double_four_len(int i) { const int l[6] = { 7, 7, 7, 8, 8, 9 }; return l[i]; }
-				static AGB_HD int double_four_off(int i) { const int o[6] = { 2, 3, 4, 2, 3, 2 }; return o[i]; }
-				static AGB_HD uint32_t half_open_four(int i)
-				{
-					const uint32_t m[20] = { 21u, 69u, 81u, 84u, 21u, 261u, 273u, 276u, 69u, 261u, 321u, 324u, 81u, 273u, 321u, 336u, 84u, 276u, 324u, 336u };
-					return m[i];
-				}
-				static AGB_HD int half_open_four_off(int i)
-				{
-					const int o[20] = { 3, 4, 5, 6, 2, 4, 5, 6, 2, 3, 5, 6, 2, 3, 4, 6, 2, 3, 4, 5 };
-					return o[i];
-				}
-				static AGB_HD uint32_t open_three(int i)
-				{
-					const uint32_t m[12] = { 20u, 68u, 80u, 20u, 260u, 272u, 68u, 260u, 320u, 80u, 272u, 320u };
-					return m[i];
-				}
-				static AGB_HD int open_three_off(int i)
-				{
-					const int o[12] = { 3, 4, 5, 2, 4, 5, 2, 3, 5, 2, 3, 4 };
-					return o[i];
-				}
+		{
+				static AGB_HD uint32_t five(int i) { return mask_tables::five[i]; }
+				static AGB_HD uint32_t open_four(int i) { return mask_tables::open_four[i]; }
+				static AGB_HD uint32_t double_four(int i) { return mask_tables::double_four[i]; }
+				static AGB_HD int double_four_len(int i) { return mask_tables::double_four_len[i]; }
+				static AGB_HD int double_four_off(int i) { return mask_tables::double_four_off[i]; }
+				static AGB_HD uint32_t half_open_four(int i) { return mask_tables::half_open_four[i]; }
+				static AGB_HD int half_open_four_off(int i) { return mask_tables::half_open_four_off[i]; }
+				static AGB_HD uint32_t open_three(int i) { return mask_tables::open_three[i]; }
+				static AGB_HD int open_three_off(int i) { return mask_tables::open_three_off[i]; }
 		};
 		AGB_HD inline uint32_t sub_pattern(uint32_t line, int start, int length)
 		{
@@ -274,7 +280,11 @@ namespace agb
 							return d;
 					return 0;
 				}
+#ifdef AGB_SOLVER_NO_RENJU
+				AGB_HD bool anything_forbidden_for(int) const { return false; } // this build of the solver serves the rule sets without forbidden moves
+#else
 				AGB_HD bool anything_forbidden_for(int sign) const { return rules == RULE_RENJU and sign == CROSS; }
+#endif
 				AGB_HD bool is_forbidden(int sign, int r, int c) const
 				{
 					if (dyn != nullptr)
@@ -498,8 +508,8 @@ namespace agb
 						added[r] |= mask[r];
 					}
 				}
-				AGB_HD void legal_mask(uint32_t *mask) const
-				{
+				AGB_HD_NOINLINE void legal_mask(uint32_t *mask) const
+				{ // cold: used one move before the draw, and by the host form of the stencil
 					for (int r = 0; r < v.S; r++)
 					{
 						uint32_t m = 0;
@@ -512,33 +522,41 @@ namespace agb
 				AGB_HD_NOINLINE void stencil_mask(uint32_t *mask, int sign) const
 				{
 #ifdef __CUDA_ARCH__
-					// lockstep warp (solver_search.cuh): lane r builds row r of the mask from the stones of rows r-3..r+3, then every lane
+					// lockstep warp (solver_search.cuh): lane r packs row r into bit masks (stones of interest, empty cells), takes the stone masks of
+					// rows r-3..r+3 from its neighbours, and ORs each of them in shifted by every offset its stencil row has; then every lane
 					// collects all rows
-					const unsigned long long box = 0x493E3E773E3E49ull, star = 0x492A1C771C2A49ull; // the 7 stencil rows, one byte each
+					const unsigned long long box = 0x493E3E773E3E49ull, star = 0x492A1C771C2A49ull; // the 7 stencil rows, one byte each (bit k: offset k - 3)
+					const unsigned long long stencil = (sign == 0) ? box : star;
 					const int lane = threadIdx.x & 31;
-					uint32_t mine = 0;
+					uint32_t stones = 0, legal = 0;
 					if (lane < v.S)
-					{
-						uint32_t legal = 0;
+#pragma unroll 1
 						for (int c = 0; c < v.S; c++)
-							legal |= static_cast<uint32_t>(v.board[lane * v.S + c] == NONE) << c;
-						for (int i = 0; i < 7; i++)
 						{
-							const int sr = lane + 3 - i; // a stone in row sr puts stencil row i on this row
-							if (sr < 0 or sr >= v.S)
-								continue;
-							const uint32_t m = static_cast<uint32_t>(((sign == 0) ? box : star) >> (8 * i)) << 25 & 0xFE000000u;
-							for (int c = 0; c < v.S; c++)
-							{
-								const int s = v.board[sr * v.S + c];
-								if ((sign == 0) ? (s != NONE) : (s == sign))
-									mine |= m >> (28 - c);
-							}
+							const int s = v.board[lane * v.S + c];
+							stones |= static_cast<uint32_t>((sign == 0) ? (s != NONE) : (s == sign)) << c;
+							legal |= static_cast<uint32_t>(s == NONE) << c;
 						}
-						if (sign == 0 and v.stones == 0 and lane == v.S / 2)
-							mine |= 1u << (v.S / 2);
-						mine &= legal;
+					uint32_t mine = 0;
+#pragma unroll 1
+					for (int i = 0; i < 7; i++)
+					{ // a stone in row lane + 3 - i puts stencil row i on this row
+						const int sr = lane + 3 - i;
+						const uint32_t theirs = __shfl_sync(0xFFFFFFFFu, stones, sr & 31);
+						if (sr < 0 or sr >= v.S)
+							continue;
+						const uint32_t pattern = static_cast<uint32_t>(stencil >> (8 * i)) & 0x7Fu;
+						uint64_t spread = 0; // bit c + k of it: a stone at column c seen through pattern bit k, i.e. column c + k - 3
+#pragma unroll
+						for (int k = 0; k < 7; k++)
+							spread |= ((pattern >> k) & 1u) ? (static_cast<uint64_t>(theirs) << k) : 0ull;
+						mine |= static_cast<uint32_t>((spread << 3) >> 6); // columns below 0 fall off, those beyond the board are masked below
 					}
+					if (sign == 0 and v.stones == 0 and lane == v.S / 2)
+						mine |= 1u << (v.S / 2);
+					mine &= legal & ((1u << v.S) - 1u);
+					if (lane >= v.S)
+						mine = 0;
 					for (int r = 0; r < v.S; r++)
 						mask[r] = __shfl_sync(0xFFFFFFFFu, mine, r);
 #else

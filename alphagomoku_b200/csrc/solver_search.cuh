@@ -15,9 +15,12 @@
 #pragma once
 #include "solver_logic.cuh"
 
+#ifndef AGB_SOLVER_NS
+#define AGB_SOLVER_NS solver // solver_plain in the build without renju (solver_kernel.cuh)
+#endif
 namespace agb
 {
-	namespace solver
+	namespace AGB_SOLVER_NS
 	{
 		// ---- mutable position ----------------------------------------------------------------------------------------------------
 		struct DynState
@@ -91,7 +94,7 @@ namespace agb
 		// work: lane q (and q + 32) owns entry q = 4 * k + dir of the 40 neighbour cells (k-th offset of -5..-1, 1..5, like K2), so a lane only
 		// ever needs the line word of ITS direction (dir = lane & 3). The list changes are then replayed by the whole warp in the visiting
 		// order of update_around (PatternCalculator.cpp:320-330), which is the order of q.
-		__device__ __forceinline__ void dyn_update_neighbours_warp(DynState &d, int S, int r, int c, int dir, uint64_t my_line, int my_pos)
+		__device__ __noinline__ void dyn_update_neighbours_warp(DynState &d, int S, int r, int c, int dir, uint64_t my_line, int my_pos)
 		{
 			const int lane = threadIdx.x & 31;
 			// the state's pointers in registers: the byte stores below could alias the fields of `d` and would force a reload after each
@@ -348,6 +351,9 @@ namespace agb
 		}
 		AGB_HD inline bool dyn_calc_is_forbidden(DynState &d, int r, int c, int depth)
 		{ // PatternCalculator::isForbidden(CROSS, r, c) (PatternCalculator.hpp:173-189)
+#ifdef AGB_SOLVER_NO_RENJU
+			return false;
+#endif
 			if (d.v.rules != RULE_RENJU)
 				return false;
 			if (d.board[r * d.v.S + c] != NONE)
@@ -361,6 +367,9 @@ namespace agb
 		}
 		AGB_HD_NOINLINE inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c)
 		{ // MoveGenerator::is_forbidden (MoveGenerator.cpp:1167-1180): cached per generate() call
+#ifdef AGB_SOLVER_NO_RENJU
+			return false;
+#endif
 			if (not (d->v.rules == RULE_RENJU and sign == CROSS))
 				return false;
 			const uint16_t loc = mk_loc(r, c);
@@ -383,6 +392,9 @@ namespace agb
 		// effect on the list order matters here (the feature words themselves come from K3)
 		AGB_HD_NOINLINE inline void encode_forbidden_pass(DynState &d)
 		{
+#ifdef AGB_SOLVER_NO_RENJU
+			return;
+#endif
 			if (d.v.rules != RULE_RENJU or d.v.stm != CROSS)
 				return;
 			const int n = d.v.count(CROSS, TT_FORK_3x3);
@@ -600,19 +612,14 @@ namespace agb
 						return false;
 			return true;
 		}
+		namespace eval_tables
+		{ // AlphaBetaSearch::evaluate's weights per ThreatType (AlphaBetaSearch.cpp:345-365), for the side to move and for the other side
+			AGB_MASK_TABLE int16_t own[kHistTypes] = { 0, 0, 19, 49, 76, 170, 33, 159, 252, 0 };
+			AGB_MASK_TABLE int16_t other[kHistTypes] = { 0, 0, -1, -50, -45, -135, -14, -154, -496, 0 };
+		}
 		AGB_HD inline int eval_weight(int type, bool own)
 		{
-			switch (type)
-			{
-				case TT_OPEN_3: return own ? 19 : -1;
-				case TT_FORK_3x3: return own ? 49 : -50;
-				case TT_HALF_OPEN_4: return own ? 76 : -45;
-				case TT_FORK_4x3: return own ? 170 : -135;
-				case TT_FORK_4x4: return own ? 33 : -14;
-				case TT_OPEN_4: return own ? 159 : -154;
-				case TT_FIVE: return own ? 252 : -496;
-				default: return 0;
-			}
+			return own ? eval_tables::own[type] : eval_tables::other[type];
 		}
 		AGB_HD inline void preview_child(const DynState &d, uint16_t move, ChildInfo &out)
 		{ // valid for a calm parent only (the strong lists are empty, so "quiet" is "no strong threat appears")
