@@ -19,24 +19,16 @@ namespace agb
 
 		AGB_HD inline int line_count(int S) { return 6 * S - 2; }
 		AGB_HD inline int line_index(int dir, int r, int c, int S)
-		{
-			switch (dir)
-			{
-				case 0: return r;
-				case 1: return S + c;
-				case 2: return 2 * S + (c - r + S - 1);
-				default: return 4 * S - 1 + (r + c);
-			}
+		{ // rows, then columns, then diagonals (by c - r), then antidiagonals (by r + c); written without branches: the solver calls it per move
+			const int diagonal = (dir == 2) ? (3 * S - 1 - r + c) : (4 * S - 1 + r + c);
+			const int straight = (dir == 0) ? r : (S + c);
+			return (dir < 2) ? straight : diagonal;
 		}
 		AGB_HD inline int pos_in_line(int dir, int r, int c, int S)
 		{
-			switch (dir)
-			{
-				case 0: return c;
-				case 1: return r;
-				case 2: return imin(r, c);
-				default: return imin(r, S - 1 - c);
-			}
+			const int a = (dir == 0) ? c : r;
+			const int b = (dir == 3) ? (S - 1 - c) : ((dir == 1) ? r : c);
+			return imin(a, b);
 		}
 		// first cell, direction and length of line l
 		AGB_HD inline void line_geometry(int l, int S, int &r0, int &c0, int &dr, int &dc, int &len)

@@ -2360,9 +2360,10 @@ extern "C"
 		{ // automatic partition: both kernels scale with their SMs, so split the SMs in proportion to the SM-time each needed in this
 		  // call (K5 and K4 launches then take equally long); move three quarters of the way, in whole TPCs. Results do not depend on it.
 			const int sms = s->solver_sms + s->net_sms;
-			// the solver's side also carries the small kernels of its group (expand, make-move, select, K1), and a group whose solver ends late
-			// stalls the network stream, the critical chain: lean 15 % towards the solver (flat optimum: 1.1-1.35 measure the same)
-			static const double bias = getenv("AGB_BALANCE_BIAS") != nullptr ? atof(getenv("AGB_BALANCE_BIAS")) : 1.15;
+			// Lean 15 % towards the network: measured on the steady-state workload the step is shortest when the solver's launches take about that
+			// much longer than the network's (bias 0.85: 237 k evaluations/s on 46 solver SMs, 1.0: 232 k on 50, 1.15: 227 k on 56) -- a network
+			// launch that waits a little for its solver loses less than network CTAs that lack SMs all the time. Early game: 345 / 339 / 335 k.
+			static const double bias = getenv("AGB_BALANCE_BIAS") != nullptr ? atof(getenv("AGB_BALANCE_BIAS")) : 0.85;
 			const double solver_work = bias * call_solver_ms * s->solver_sms, net_work = call_nn_ms * s->net_sms;
 			const double target = sms * solver_work / (solver_work + net_work);
 			int next = static_cast<int>(s->solver_sms + 0.75 * (target - s->solver_sms) + 0.5) & ~1;

@@ -397,8 +397,8 @@ namespace agb
 
 				AGB_HD MoveGenerator(const View &view, uint16_t *m, uint16_t *s) : v(view), moves(m), scores(s)
 				{
-#pragma unroll 1
-					for (int i = 0; i < kMaxSize; i++)
+#pragma unroll
+					for (int i = 0; i < kMaxSize; i++) // 20 words, unrolled into a few wide stores
 						added[i] = 0;
 				}
 				AGB_HD uint16_t wire(uint16_t loc) const { return static_cast<uint16_t>(v.own() | (loc_row(loc) << 2) | (loc_col(loc) << 9)); }
