@@ -2,7 +2,10 @@
 restatement in oracle/nn_oracle.py. Floating point: tolerances are stated here.
 
   * vs the fp32 oracle (north star: "policy/value within a stated bf16 tolerance of the fp32 CPU evaluator"):
-        policy |err| <= 2e-3 + 3 % of the reference probability, value |err| <= 3e-2, q |err| <= 4e-2
+        policy |err| <= 5e-4 + 3 % of the reference probability, value |err| <= 1.5e-2, q |err| <= 2.5e-2
+        (observed on B200 with the BASELINE networks, profiles/r02_k4_observed_errors.txt: policy 2.0e-4 max / 2.3e-5 mean, value 3.8e-3;
+        test_observed_errors_against_the_fp32_evaluator bounds those, KL and best-move agreement at about twice the observed values, also
+        for peaked outputs)
   * vs the same oracle with every stored activation and conv weight rounded to bf16 (what the kernel stores), which
     leaves only accumulation-order differences (which still compound over 40 layers): policy |err| <= 5e-4 + 1.5 %,
     value / q |err| <= 2e-2
@@ -19,13 +22,31 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 pytestmark = pytest.mark.gpu
 
 
-def _run(blocks, filters, q_head, n, seed, size=15, rules=None):
+def _metrics(policy, value, ref_policy, ref_value):
+    """What the comparison with the fp32 evaluator looks like as numbers: absolute errors, KL(reference || device) per board and how often the
+    device agrees on the best move / keeps the reference's best move among its five best."""
+    err = np.abs(policy - ref_policy)
+    eps = 1e-12
+    kl = (ref_policy * (np.log(ref_policy + eps) - np.log(policy + eps))).sum(1)
+    top1 = (policy.argmax(1) == ref_policy.argmax(1)).mean()
+    top5 = np.mean([ref_policy[i].argmax() in np.argsort(-policy[i])[:5] for i in range(policy.shape[0])])
+    rel = (err / np.maximum(ref_policy, 1e-6))[ref_policy > 1e-3]
+    return {"policy_max_abs": float(err.max()), "policy_mean_abs": float(err.mean()), "policy_max_rel_where_p>1e-3": float(rel.max()) if rel.size else 0.0,
+            "kl_max": float(kl.max()), "kl_mean": float(kl.mean()), "top1_agreement": float(top1), "top5_agreement": float(top5),
+            "value_max_abs": float(np.abs(value - ref_value).max()), "value_mean_abs": float(np.abs(value - ref_value).mean()),
+            "reference_policy_max_mean": float(ref_policy.max(1).mean())}
+
+
+def _run(blocks, filters, q_head, n, seed, size=15, rules=None, sharpen=1.0):
     import torch
     import alphagomoku_b200 as agb
     from alphagomoku_b200 import netblob
     import nn_oracle
     eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD if rules is None else agb.GameRules(rules), size, size), max_boards=n, blocks=blocks, filters=filters, q_head=q_head)
     tensors = netblob.random_tensors(size, size, blocks, filters, q_head, seed=seed)
+    if sharpen != 1.0:  # trained-scale outputs: larger logits in the policy's 1x1 convolution and the value's last layer give peaked distributions
+        tensors["policy.w1"] = tensors["policy.w1"] * np.float32(sharpen)
+        tensors["value.wd2"] = tensors["value.wd2"] * np.float32(sharpen)
     blob = netblob.pack(tensors, size, size, blocks, filters, q_head)
     assert eng.weights_size() == blob.nbytes
     eng.load_weights(blob)
@@ -44,12 +65,12 @@ def _check(out, ref32, ref16):
     policy, value, q = out
     assert np.isfinite(policy).all() and np.isfinite(value).all()
     assert np.abs(policy.sum(1) - 1).max() < 1e-4 and np.abs(value.sum(1) - 1).max() < 1e-5
-    assert (np.abs(policy - ref32[0]) <= 2e-3 + 0.03 * ref32[0]).all(), np.abs(policy - ref32[0]).max()
-    assert np.abs(value - ref32[1]).max() <= 3e-2
+    assert (np.abs(policy - ref32[0]) <= 5e-4 + 0.03 * ref32[0]).all(), np.abs(policy - ref32[0]).max()
+    assert np.abs(value - ref32[1]).max() <= 1.5e-2
     assert (np.abs(policy - ref16[0]) <= 5e-4 + 0.015 * ref16[0]).all(), np.abs(policy - ref16[0]).max()
     assert np.abs(value - ref16[1]).max() <= 2e-2
     if q is not None:
-        assert np.abs(q - ref32[2]).max() <= 4e-2
+        assert np.abs(q - ref32[2]).max() <= 2.5e-2
         assert np.abs(q - ref16[2]).max() <= 2e-2
 
 
@@ -79,3 +100,28 @@ def test_large_boards_split_over_the_cta_pair(size, blocks, filters, q_head):
 def test_caro_20x20_baseline_network():
     """BASELINE configs[3]: caro 20x20, 20 blocks x 128 channels; more boards than CTA pairs."""
     _check(*_run(20, 128, True, n=150, seed=21, size=20, rules=3))
+
+
+@pytest.mark.parametrize("blocks,filters,sharpen", [(20, 128, 1.0), (10, 64, 1.0), (20, 128, 6.0), (10, 64, 6.0)])
+def test_observed_errors_against_the_fp32_evaluator(blocks, filters, sharpen):
+    """The numbers behind the tolerance (report what is observed, then bound it): errors, KL and move agreement of the bf16 kernel
+    against the fp32 evaluator on the two BASELINE networks, with the synthetic weights as they are (flat outputs) and with sharpened heads
+    (peaked, trained-like outputs: the reference's best move holds 20-60 % of the probability). Bounds = about twice what was observed on B200."""
+    out, ref32, _ = _run(blocks, filters, False, n=256, seed=31 + blocks, sharpen=sharpen)
+    m = _metrics(out[0], out[1], ref32[0], ref32[1])
+    print(f"K4 vs fp32 evaluator, {blocks}x{filters}, heads x{sharpen}: " + ", ".join(f"{k} {v:.3g}" for k, v in m.items()))
+    bounds = OBSERVED_BOUNDS[(blocks, filters, sharpen)]
+    for key, bound in bounds.items():
+        if key.endswith("agreement"):
+            assert m[key] >= bound, (key, m[key], bound)
+        else:
+            assert m[key] <= bound, (key, m[key], bound)
+
+
+# filled from a run on B200 (profiles/r02_k4_observed_errors.txt): about twice the observed values
+OBSERVED_BOUNDS = {
+    (20, 128, 1.0): {"policy_max_abs": 4e-4, "kl_max": 6e-5, "top1_agreement": 0.94, "top5_agreement": 0.99, "value_max_abs": 8e-3},
+    (10, 64, 1.0): {"policy_max_abs": 2.2e-4, "kl_max": 2.2e-5, "top1_agreement": 0.92, "top5_agreement": 0.99, "value_max_abs": 6e-3},
+    (20, 128, 6.0): {"policy_max_abs": 4.7e-2, "kl_max": 3.7e-3, "top1_agreement": 0.94, "top5_agreement": 0.99, "value_max_abs": 5e-4},
+    (10, 64, 6.0): {"policy_max_abs": 1.4e-2, "kl_max": 9e-4, "top1_agreement": 0.92, "top5_agreement": 0.99, "value_max_abs": 1e-2},
+}
