@@ -70,6 +70,10 @@ SYMBOLS = {
     "agb_set_solver_keys": (_I, [_VP, _VP, ctypes.c_size_t]),
     "agb_set_symmetry_table": (_I, [_VP, _VP, _I]),
     "agb_get_root_scores": (_I, [_VP, _I, _VP, _VP]),
+    "agb_dataset_load_fragment": (_I, [_VP, _I, ctypes.c_char_p]),
+    "agb_dataset_unload_fragment": (_I, [_VP, _I]),
+    "agb_dataset_size": (_I, [_VP, ctypes.POINTER(_I), _VP]),
+    "agb_load_batch": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "agb_solve": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "agb_step": (_I, [_VP, _I]),
     "agb_pop_finished": (_I, [_VP, _VP, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I)]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
-SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu", "solver_plain.cu", "partition.cu"]
+SOURCES = ["capi.cu", "tables.cu", "patterns.cu", "resnet.cu", "selfplay.cu", "solver.cu", "solver_plain.cu", "partition.cu", "dataset_api.cu"]
 # host-only sources, compiled by g++ with the reference's floating-point flags (no FMA contraction, libm overloads as in the reference)
 HOST_SOURCES = ["openings.cpp", "config_json.cpp"]
 HOST_FLAGS = ["-O2", "-std=c++17", "-msse2", "-fPIC", "-I/usr/local/cuda/include"]
@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lz", "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
     return LIB
 

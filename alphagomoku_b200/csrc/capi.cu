@@ -171,6 +171,7 @@ extern "C"
 		agb::selfplay_destroy(e);
 		agb::solve_scratch_destroy(e);
 		agb::openings_destroy(e);
+		agb::dataset_destroy(e);
 		agb::net_destroy(e);
 		agb::BoardStore &s = e->store;
 		void *ptrs[] = { s.board, s.sign_to_move, s.lines, s.ptypes, s.threats, s.forbidden, s.hist_count, s.hist_cells, e->d_features, e->d_features2,

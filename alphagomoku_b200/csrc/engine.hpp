@@ -15,6 +15,7 @@ namespace agb
 namespace agb
 {
 	struct SolveScratch;
+	struct DatasetStore; // dataset_api.cu: GameDataBuffer fragments loaded for agb_load_batch
 }
 struct AgbEngine
 {
@@ -47,6 +48,7 @@ struct AgbEngine
 		agb::SelfplayState *selfplay = nullptr;
 		agb::SolveScratch *solve_scratch = nullptr; // agb_solve: solver memory for positions outside the lockstep engine
 		std::vector<uint64_t> solver_keys_host; // Zobrist words given through agb_set_solver_keys (applied to every solver state)
+		agb::DatasetStore *dataset = nullptr;
 		void *opening_rng = nullptr; // std::mt19937 of the opening generator (openings.cu)
 		bool think_mode = false; // agb_think in progress: games stop at their decision
 
@@ -164,6 +166,7 @@ namespace agb
 	void solver_state_destroy(SolverState *st);
 	void solve_scratch_destroy(AgbEngine *e);
 	void openings_destroy(AgbEngine *e);
+	void dataset_destroy(AgbEngine *e);
 	// solver_sms > 0: run on that many SMs only (side by side with the network kernel, see AgbConfig::solver_sms). green: the stream belongs to a
 	// green context of that many SMs, any block shape stays inside it; otherwise the launch uses blocks that take whole SMs
 	int launch_solve_games(AgbEngine *e, const SolverState &st, int game_begin, int game_count, const SolverOutputs &out, const uint8_t *slot_is_root, int *nn_list,

@@ -1630,6 +1630,8 @@ namespace agb
 			return e->fail(AGB_EINVAL, "self-play needs a network (blocks > 0)");
 		if (c.max_batch_size <= 0 or c.games * c.max_batch_size > c.max_boards)
 			return e->fail(AGB_EINVAL, "games * max_batch_size must fit in max_boards");
+		if (c.max_simulations < 50) // the reference asserts it (get_simulations_for_move, src/utils/misc.cpp:171-179): a drawish root is searched for
+			return e->fail(AGB_EINVAL, "max_simulations must be at least 50 (the simulation budget of a drawish position)"); // 50 simulations, which select never reaches with fewer
 		SelfplayState *s = new SelfplayState();
 		e->selfplay = s;
 		s->games = c.games;

@@ -270,6 +270,31 @@ class Engine:
         t = np.ascontiguousarray(table, np.int8).reshape(-1)
         self._check(self._lib.agb_set_symmetry_table(self._h, _ptr(t) if t.size else None, int(t.size)))
 
+    # ---- the trainer's batch loader (torch_api.h) ---------------------------------------------------------------------
+    def load_dataset_fragment(self, index, path):
+        self._check(self._lib.agb_dataset_load_fragment(self._h, index, path.encode()))
+
+    def unload_dataset_fragment(self, index):
+        self._check(self._lib.agb_dataset_unload_fragment(self._h, index))
+
+    def dataset_size(self):
+        """[(fragment, game, samples, symmetries)] for every loaded game (get_dataset_size)."""
+        n = ctypes.c_int(0)
+        self._check(self._lib.agb_dataset_size(self._h, ctypes.byref(n), None))
+        sizes = np.zeros((n.value, 4), np.int32)
+        self._check(self._lib.agb_dataset_size(self._h, ctypes.byref(n), _ptr(sizes)))
+        return sizes
+
+    def load_batch(self, samples):
+        """load_batch: samples int32 [batch, 4] = (fragment, game, sample, augmentation) -> input [batch, rows, cols, 32], policy target
+        [batch, rows, cols], value target [batch, 3], moves-left target [batch], action-value target [rows, cols, 3] (see agb200.h)."""
+        s = np.ascontiguousarray(samples, np.int32).reshape(-1, 4)
+        n, g = s.shape[0], self.game
+        out = (np.zeros((n, g.rows, g.cols, 32), np.float32), np.zeros((n, g.rows, g.cols), np.float32), np.zeros((n, 3), np.float32),
+               np.zeros(n, np.float32), np.zeros((g.rows, g.cols, 3), np.float32))
+        self._check(self._lib.agb_load_batch(self._h, n, _ptr(s), *[_ptr(a) for a in out]))
+        return out
+
     def step(self, n_steps=1):
         self._check(self._lib.agb_step(self._h, n_steps))
 

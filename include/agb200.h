@@ -229,6 +229,24 @@ int agb_step(AgbEngine *engine, int n_steps);
 /* pop finished-game records (GameDataStorage::serialize, src/dataset/GameDataStorage.cpp:217-251, format 201) */
 int agb_pop_finished(AgbEngine *engine, void *records_host, size_t capacity, size_t *used, int *n_games);
 
+/* ---- the trainer's batch loader (include/alphagomoku/dataset/torch_api.h:14-41, src/dataset/torch_api.cpp:130-281) ------------------------
+ * GameDataBuffer files (what GeneratorManager::getGameBuffer().save writes, format 201) are loaded into numbered fragments; a batch is a list
+ * of (fragment, game, sample, augmentation) like the reference's Sample_t. agb_load_batch fills the same five float arrays as load_batch:
+ * input[batch][rows][cols][32] (bit c of NNInputFeatures::encode's word as channel c; computed by K1 + K3 on the device for the whole batch),
+ * policy_target[batch][rows][cols] (visit counts, proven wins / losses overridden, normalised), value_target[batch][3] (win, draw, loss of the
+ * side to move), moves_left_target[batch], action_values_target[rows][cols][3] (the reference does not advance this pointer between samples,
+ * torch_api.cpp:251-280: one board's worth, written by every sample in turn; kept as it is). */
+typedef struct AgbSample
+{
+	int32_t buffer_index, game_index, sample_index, augmentation; /* Sample_t, torch_api.h:16-22 */
+} AgbSample;
+int agb_dataset_load_fragment(AgbEngine *engine, int index, const char *path); /* load_dataset_fragment */
+int agb_dataset_unload_fragment(AgbEngine *engine, int index); /* unload_dataset_fragment */
+/* get_dataset_size: *n_games = games over all fragments; sizes[n_games][4] = fragment, game, samples, available symmetries (may be NULL) */
+int agb_dataset_size(AgbEngine *engine, int *n_games, int32_t *sizes_host);
+int agb_load_batch(AgbEngine *engine, int batch_size, const AgbSample *samples, float *input_host, float *policy_target_host, float *value_target_host,
+		float *moves_left_target_host, float *action_values_target_host);
+
 typedef struct AgbStats
 {
 	/* SearchStats / NNEvaluatorStats (Search.hpp:33-54, NNEvaluator.hpp:28-40) */

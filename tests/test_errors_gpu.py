@@ -28,7 +28,7 @@ def test_misuse_is_reported():
     policy, value, _ = eng.evaluate(boards[:2], stm[:2])
     assert np.isfinite(policy).all() and abs(float(value[0].sum()) - 1.0) < 1e-5
     eng.close()
-    for bad in (dict(filters=48, blocks=1), dict(games=4, max_batch_size=4, blocks=1, filters=64, max_boards=8), dict(pipeline_groups=9, games=16, blocks=1, filters=64, max_boards=128),
+    for bad in (dict(filters=48, blocks=1), dict(games=4, max_batch_size=2, blocks=1, filters=64, max_boards=8, max_simulations=40), dict(games=4, max_batch_size=4, blocks=1, filters=64, max_boards=8), dict(pipeline_groups=9, games=16, blocks=1, filters=64, max_boards=128),
                 dict(solver_table_entries=1000, solver_max_positions=10, games=2, blocks=1, filters=64, max_boards=64)):
         kwargs = dict(max_boards=8)
         kwargs.update(bad)
@@ -112,7 +112,7 @@ def test_full_finished_queue_keeps_the_records(monkeypatch):
     monkeypatch.setenv("AGB_FINISHED_QUEUE_BYTES", "6000")  # two or three short games
     size, games = 9, 16
     eng = agb.Engine(agb.GameConfig(agb.GameRules.FREESTYLE, size, size), max_boards=games * 4, blocks=1, filters=64, games=games, max_batch_size=4,
-                     max_simulations=20, max_nodes_per_game=400, max_edges_per_game=400 * 81)
+                     max_simulations=50, max_nodes_per_game=400, max_edges_per_game=400 * 81)
     eng.load_weights(netblob.pack(netblob.random_tensors(size, size, 1, 64, False), size, size, 1, 64, False))
     eng.selfplay_reset()
     popped, reports = 0, 0

@@ -202,7 +202,7 @@ def test_scheduling_of_solver_and_network_is_invisible(games):
     for kwargs in (dict(pipeline_groups=1), dict(pipeline_groups=2), dict(pipeline_groups=3, solver_sms=8), dict(pipeline_groups=2, solver_sms=-1),
                    dict(pipeline_groups=4, solver_sms=146)):
         eng = agb.Engine(agb.GameConfig(agb.GameRules.RENJU, size, size, 40), max_boards=games * 4, blocks=blocks, filters=filters, games=games,
-                         max_batch_size=4, max_simulations=40, solver_max_positions=60, use_symmetries=True, seed=3, **kwargs)
+                         max_batch_size=4, max_simulations=50, solver_max_positions=60, use_symmetries=True, seed=3, **kwargs)
         eng.load_weights(blob)
         eng.selfplay_reset(boards, stm)
         eng.step(60)
