@@ -4,8 +4,9 @@
 Every game has two players, each with its own engine (its own network, search settings and tree). Per ply, the engine whose colour is
 to move searches all of its games at once (Engine.think = Player::setBoard ... getMove) and the host plays the chosen moves, asks the
 device for the outcomes (getOutcome) and flips the side to move. Colours alternate between games like in EvaluationGame (each opening is
-played twice with swapped colours when `swap_colours` is set). Differences from the reference's arena: a player's tree is rebuilt for every
-move instead of being re-rooted, and there is no time control (the search budget is the engine's max_simulations).
+played twice with swapped colours when `swap_colours` is set). Like the reference's Player, a player keeps its search tree from move to move:
+Engine.think re-roots it on the new position (Player::setBoard -> Tree::setBoard -> NodeCache::cleanup), move for move identical to the
+reference's Player on the same network (tests/test_arena_gpu.py). There is no time control: the search budget is the engine's max_simulations.
 
 Returns per-game records (moves, outcome, who played cross) and the score of engine A, ready for an Elo fit or a PGN dump."""
 import numpy as np
@@ -37,6 +38,8 @@ def play_match(engine_a, engine_b, openings, sign_to_move, swap_colours=True, ma
     outcome = np.zeros(n, np.int8)
     moves = [[] for _ in range(n)]
     max_plies = max_plies or cells
+    for engine in (engine_a, engine_b):  # new Player objects for this match: empty trees, cleared solver tables
+        engine.selfplay_reset()
     for _ in range(max_plies):
         running = outcome == 0
         if not running.any():
@@ -66,3 +69,13 @@ def play_match(engine_a, engine_b, openings, sign_to_move, swap_colours=True, ma
         score_a += 0.5 if outcome[g] == 1 else (1.0 if a_won else 0.0)
         games.append({"moves": moves[g], "outcome": OUTCOME_NAMES[int(outcome[g])], "a_plays_cross": bool(a_is_cross[g]), "opening": openings[g % len(openings)].copy()})
     return {"games": games, "score_a": score_a / n, "n_games": n}
+
+
+def generate_pgn(game, rows, cols, rules, first_name="A", second_name="B"):
+    """Game::generatePGN (src/game/Game.cpp): the tags EvaluationManager's pgn files carry, moves as Move::text without the sign."""
+    cross, circle = (first_name, second_name) if game["a_plays_cross"] else (second_name, first_name)
+    result = {"CROSS_WIN": "1-0", "CIRCLE_WIN": "0-1", "DRAW": "1/2-1/2"}.get(game["outcome"], "*")
+    text = [f'[White "{cross}"]', f'[Black "{circle}"]', f'[Result "{result}"]', f'[Variant "{rules}:{rows}x{cols}"]', ""]
+    plies = [chr(ord("a") + ((mv >> 9) & 127)) + str((mv >> 2) & 127) for mv in game["moves"]]
+    text.append(" ".join(f"{i // 2 + 1}. {plies[i]}" + (f" {plies[i + 1]}" if i + 1 < len(plies) else "") for i in range(0, len(plies), 2)) + f" {result}")
+    return "\n".join(text) + "\n"

@@ -160,6 +160,7 @@ namespace agb
 			// the driver cannot provide them the partition falls back to SM-filling solver blocks (solver.cu) and at most 2 groups pay
 			SmPartition partition { };
 			bool green = false;
+			bool reset_done = false; // agb_selfplay_reset / agb_load_games has put every per-game array into a defined state
 			cudaStream_t group_stream[kMaxGroups] = { };
 			cudaStream_t solver_stream[kMaxGroups] = { }; // green partition: K5 of each group on the solver's SMs, everything else of the group on the tree SMs
 			cudaEvent_t solver_go[kMaxGroups] = { }, solver_done[kMaxGroups] = { };
@@ -1199,6 +1200,89 @@ namespace agb
 			}
 		}
 
+		// Tree::setBoard -> NodeCache::cleanup (src/search/monte_carlo/Tree.cpp:128-151, NodeCache.cpp): keep every node whose position can still
+		// occur from the new root position `bits` (all its stones are on the node's board), compact the kept nodes and their edge blocks in place,
+		// rebuild the hash table and look the new root up. The warp of game g runs it: after every move of a self-play game (prepare_search) and when
+		// a player is handed a new position (Player::setBoard, agb_think).
+		__device__ void keep_possible_nodes(const Params &p, int g, int lane, const uint64_t *bits)
+		{
+			NodeD *nodes = p.s.nodes + static_cast<size_t>(g) * p.s.max_nodes;
+			EdgeD *edges = p.s.edges + static_cast<size_t>(g) * p.s.max_edges;
+			// prepare_search -> Tree::setBoard -> NodeCache::cleanup: keep every node whose position can still occur
+			const int n_nodes = p.s.n_nodes[g];
+			int32_t *remap = p.s.remap + static_cast<size_t>(g) * p.s.max_nodes;
+			uint64_t *node_bits = p.s.node_bits + static_cast<size_t>(g) * p.s.max_nodes * kBitWords;
+			uint64_t rb[kBitWords];
+			for (int k = 0; k < kBitWords; k++)
+				rb[k] = bits[k];
+			int kept = 0;
+			for (int i0 = 0; i0 < n_nodes; i0 += 32)
+			{
+				const int i = i0 + lane;
+				bool keep = false;
+				if (i < n_nodes)
+				{
+					keep = true;
+					for (int k = 0; k < kBitWords; k++)
+						keep = keep and ((node_bits[static_cast<size_t>(i) * kBitWords + k] & rb[k]) == rb[k]);
+				}
+				const unsigned km = __ballot_sync(kFullMask, keep);
+				if (i < n_nodes)
+					remap[i] = keep ? kept + __popc(km & ((1u << lane) - 1u)) : -1;
+				kept += __popc(km);
+			}
+			__syncwarp();
+			// compact nodes (ascending, destinations never overtake sources) and their edge blocks
+			int edge_cursor = 0;
+			for (int i = 0; i < n_nodes; i++)
+			{
+				const int dst = remap[i];
+				if (dst < 0)
+					continue;
+				NodeD node = nodes[i];
+				uint64_t nbits = (lane < kBitWords) ? node_bits[static_cast<size_t>(i) * kBitWords + lane] : 0;
+				const int old_begin = node.edge_begin;
+				for (int e0 = 0; e0 < node.n_edges; e0 += 32)
+				{
+					EdgeD e;
+					if (e0 + lane < node.n_edges)
+						e = edges[old_begin + e0 + lane];
+					__syncwarp();
+					if (e0 + lane < node.n_edges)
+						edges[edge_cursor + e0 + lane] = e;
+					__syncwarp();
+				}
+				node.edge_begin = edge_cursor;
+				node.flags &= ~1; // root mark is re-applied below
+				edge_cursor += node.n_edges;
+				__syncwarp();
+				if (lane == 0)
+					nodes[dst] = node;
+				if (lane < kBitWords)
+					node_bits[static_cast<size_t>(dst) * kBitWords + lane] = nbits;
+				__syncwarp();
+			}
+			int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
+			for (int i = lane; i < p.s.table_size; i += 32)
+				table[i] = -1;
+			__syncwarp();
+			if (lane == 0)
+			{
+				for (int i = 0; i < kept; i++)
+					table_insert(p, g, nodes[i].hash, i);
+				p.s.n_nodes[g] = kept;
+				p.s.n_edges[g] = edge_cursor;
+			}
+			__syncwarp();
+			const int new_root = table_seek(p, g, p.s.root_hash[g], bits, p.s.root_stm[g], lane);
+			if (lane == 0)
+			{
+				p.s.root_node[g] = new_root;
+				if (new_root >= 0)
+					nodes[new_root].flags |= 1;
+			}
+		}
+
 		// ---- per-ply driver: final move, record, game end, subtree reuse ------------------------------------------------------
 		__global__ void __launch_bounds__(128) make_move_kernel(const __grid_constant__ Params p)
 		{
@@ -1465,79 +1549,61 @@ namespace agb
 			// prepare_search -> Search::setBoard: the solver's table enters a new generation
 			if (lane == 0 and p.solver_mode != 0)
 				p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64;
-			// prepare_search -> Tree::setBoard -> NodeCache::cleanup: keep every node whose position can still occur
-			const int n_nodes = p.s.n_nodes[g];
-			int32_t *remap = p.s.remap + static_cast<size_t>(g) * p.s.max_nodes;
-			uint64_t *node_bits = p.s.node_bits + static_cast<size_t>(g) * p.s.max_nodes * kBitWords;
-			uint64_t rb[kBitWords];
-			for (int k = 0; k < kBitWords; k++)
-				rb[k] = bits[k];
-			int kept = 0;
-			for (int i0 = 0; i0 < n_nodes; i0 += 32)
-			{
-				const int i = i0 + lane;
-				bool keep = false;
-				if (i < n_nodes)
-				{
-					keep = true;
-					for (int k = 0; k < kBitWords; k++)
-						keep = keep and ((node_bits[static_cast<size_t>(i) * kBitWords + k] & rb[k]) == rb[k]);
-				}
-				const unsigned km = __ballot_sync(kFullMask, keep);
-				if (i < n_nodes)
-					remap[i] = keep ? kept + __popc(km & ((1u << lane) - 1u)) : -1;
-				kept += __popc(km);
-			}
-			__syncwarp();
-			// compact nodes (ascending, destinations never overtake sources) and their edge blocks
-			int edge_cursor = 0;
-			for (int i = 0; i < n_nodes; i++)
-			{
-				const int dst = remap[i];
-				if (dst < 0)
-					continue;
-				NodeD node = nodes[i];
-				uint64_t nbits = (lane < kBitWords) ? node_bits[static_cast<size_t>(i) * kBitWords + lane] : 0;
-				const int old_begin = node.edge_begin;
-				for (int e0 = 0; e0 < node.n_edges; e0 += 32)
-				{
-					EdgeD e;
-					if (e0 + lane < node.n_edges)
-						e = edges[old_begin + e0 + lane];
-					__syncwarp();
-					if (e0 + lane < node.n_edges)
-						edges[edge_cursor + e0 + lane] = e;
-					__syncwarp();
-				}
-				node.edge_begin = edge_cursor;
-				node.flags &= ~1; // root mark is re-applied below
-				edge_cursor += node.n_edges;
-				__syncwarp();
-				if (lane == 0)
-					nodes[dst] = node;
-				if (lane < kBitWords)
-					node_bits[static_cast<size_t>(dst) * kBitWords + lane] = nbits;
-				__syncwarp();
-			}
-			int32_t *table = p.s.table + static_cast<size_t>(g) * p.s.table_size;
-			for (int i = lane; i < p.s.table_size; i += 32)
-				table[i] = -1;
-			__syncwarp();
+			keep_possible_nodes(p, g, lane, bits);
+		}
+
+		// Player::setBoard (src/evaluation/Player.cpp:98-108) for every game: a new position arrives from the host, the tree keeps what can still
+		// occur (the subtree under the moves played since the last search) and the solver's table enters a new generation. active[g] == 0: the
+		// game sits this round out.
+		__global__ void __launch_bounds__(128) rebase_games_kernel(const __grid_constant__ Params p, const int8_t *__restrict__ boards, const int8_t *__restrict__ stm,
+				const int8_t *__restrict__ active)
+		{
+			const int lane = threadIdx.x & 31;
+			const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+			if (g >= p.s.games)
+				return;
+			const int cells = p.s.cells;
 			if (lane == 0)
 			{
-				for (int i = 0; i < kept; i++)
-					table_insert(p, g, nodes[i].hash, i);
-				p.s.n_nodes[g] = kept;
-				p.s.n_edges[g] = edge_cursor;
+				p.s.paused[g] = active[g] ? 0 : 1;
+				p.s.decision[g] = 0;
+				p.s.n_stored[g] = 0;
 			}
+			if (not active[g])
+				return;
+			int8_t *board = p.s.root_board + static_cast<size_t>(g) * cells;
+			uint64_t *bits = p.s.root_bits + static_cast<size_t>(g) * kBitWords;
+			for (int i = lane; i < cells; i += 32)
+				board[i] = boards[static_cast<size_t>(g) * cells + i];
 			__syncwarp();
-			const int new_root = table_seek(p, g, p.s.root_hash[g], bits, p.s.root_stm[g], lane);
+			uint64_t h = 0;
+			if (lane < kBitWords)
+			{
+				uint64_t w = 0;
+				const int colour = lane / kWordsPerColour, word = lane % kWordsPerColour;
+				for (int i = word * 64; i < min(cells, word * 64 + 64); i++)
+					if (board[i] == colour + 1)
+					{
+						w |= 1ull << (i & 63);
+						h ^= p.s.zobrist[i * 2 + colour];
+					}
+				bits[lane] = w;
+			}
+			for (int o = 8; o > 0; o >>= 1) // lanes kBitWords..15 contribute zero
+				h ^= __shfl_xor_sync(kFullMask, h, o);
+			h = __shfl_sync(kFullMask, h, 0);
 			if (lane == 0)
 			{
-				p.s.root_node[g] = new_root;
-				if (new_root >= 0)
-					nodes[new_root].flags |= 1;
+				p.s.root_stm[g] = stm[g];
+				p.s.root_hash[g] = h ^ p.s.zobrist[cells * 2 + stm[g] - 1];
+				p.s.outcome[g] = 0;
+				if (p.s.noise_ready != nullptr)
+					p.s.noise_ready[g] = 0; // a new EdgeSelector per setBoard: the next search draws new noise
+				if (p.solver_mode != 0)
+					p.s.solver.generation[g] = (p.s.solver.generation[g] + 1) % 64; // Search::setBoard -> increaseGeneration
 			}
+			__syncwarp();
+			keep_possible_nodes(p, g, lane, bits);
 		}
 
 		__global__ void reset_games_kernel(const __grid_constant__ Params p, int keep_history)
@@ -1914,6 +1980,7 @@ extern "C"
 		e->launches++;
 		AGB_CUDA_CHECK(e, cudaGetLastError());
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		s->reset_done = true;
 		return AGB_OK;
 	}
 
@@ -2105,18 +2172,25 @@ extern "C"
 			return e->fail(AGB_ESTATE, "engine was created without games");
 		if (boards_host == nullptr or sign_to_move_host == nullptr or active_host == nullptr or moves_host == nullptr)
 			return e->fail(AGB_EINVAL, "null pointer");
-		int rc = agb_selfplay_reset(e, boards_host, sign_to_move_host);
+		const int G = s->games;
+		int rc = validate_boards(e, boards_host, sign_to_move_host, static_cast<size_t>(G));
+		if (rc == AGB_OK and not s->reset_done)
+			rc = agb_selfplay_reset(e, nullptr, nullptr); // brand-new players: empty trees
 		if (rc != AGB_OK)
 			return rc;
-		const int G = s->games;
-		std::vector<uint8_t> paused(G);
 		int remaining = 0;
 		for (int g = 0; g < G; g++)
-		{
-			paused[g] = active_host[g] ? 0 : 1;
 			remaining += active_host[g] ? 1 : 0;
+		std::vector<uint8_t> paused(G);
+		{ // Player::setBoard for every active game: the trees keep what the new positions can still reach (fresh after agb_selfplay_reset)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->task_boards, boards_host, static_cast<size_t>(G) * s->cells, cudaMemcpyHostToDevice, e->stream));
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->task_stm, sign_to_move_host, G, cudaMemcpyHostToDevice, e->stream));
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(s->slot_is_root, active_host, G, cudaMemcpyHostToDevice, e->stream));
+			const Params p = make_params(e);
+			rebase_games_kernel<<<static_cast<unsigned>((G + 3) / 4), 128, 0, e->stream>>>(p, s->task_boards, s->task_stm, reinterpret_cast<const int8_t*>(s->slot_is_root));
+			e->launches++;
+			AGB_CUDA_CHECK(e, cudaGetLastError());
 		}
-		AGB_CUDA_CHECK(e, cudaMemcpy(s->paused, paused.data(), G, cudaMemcpyHostToDevice));
 		e->think_mode = true;
 		int steps = 0;
 		while (remaining > 0)

@@ -198,10 +198,12 @@ int agb_selfplay_reset(AgbEngine *engine, const int8_t *boards_host, const int8_
 int agb_solve(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, int n, int max_positions, uint16_t *scores_host,
 		int32_t *n_actions_host, uint16_t *moves_host, uint16_t *action_scores_host, int32_t *flags_host);
 /* ---- one move per game on request (Player::setBoard / selectSolveEvaluate / expandBackup / isSearchOver / getMove,
- * src/evaluation/Player.cpp:93-238): every game with active[g] != 0 searches boards[g] from a fresh tree with the engine's search
- * settings and stops at its decision. moves[games]: the chosen Move::toShort (0 for inactive games); root_values[games][2] (optional):
- * win and draw rate of the root. max_steps > 0 bounds the lockstep iterations. The building block of evaluation games between two
- * engines (alphagomoku_b200/arena.py). */
+ * src/evaluation/Player.cpp:93-238): every game with active[g] != 0 is handed boards[g] like Player::setBoard -- its search tree keeps every
+ * node the new position can still reach (Tree::setBoard -> NodeCache::cleanup: the subtree under the moves played since its last search), the
+ * solver's table enters a new generation -- then searches with the engine's settings and stops at its decision. agb_selfplay_reset before the
+ * first call of a match = brand-new Player objects (empty trees). moves[games]: the chosen Move::toShort (0 for inactive games);
+ * root_values[games][2] (optional): win and draw rate of the root. max_steps > 0 bounds the lockstep iterations. The building block of
+ * evaluation games between two engines (alphagomoku_b200/arena.py). */
 int agb_think(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *active_host, uint16_t *moves_host,
 		float *root_values_host, int max_steps);
 

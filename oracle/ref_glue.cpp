@@ -152,3 +152,20 @@ namespace ag
 		}
 	}
 }
+
+// Player (src/evaluation/Player.cpp) holds a MovesLeftEstimator, whose body lives in src/player/TimeManager.cpp next to the tournament engine's
+// settings (out of scope); the two members Player.cpp needs, restated from TimeManager.cpp:65-76. Only time-controlled searches read it.
+#include <alphagomoku/player/TimeManager.hpp>
+namespace ag
+{
+	MovesLeftEstimator::MovesLeftEstimator(const std::vector<std::pair<int, float>> &c0, const std::vector<std::pair<int, float>> &c2) :
+			c0(c0, "linear"),
+			c2(c2, "linear")
+	{
+	}
+	double MovesLeftEstimator::get(int moveNumber, Value eval) const noexcept
+	{
+		const double x = std::abs(eval.getExpectation() - 0.5);
+		return std::max(1.0, static_cast<double>(c0.getValue(moveNumber)) - static_cast<double>(c2.getValue(moveNumber)) * x * x);
+	}
+}

@@ -11,6 +11,8 @@
 #include <alphagomoku/selfplay/GameGenerator.hpp>
 #include <alphagomoku/selfplay/NetworkLoader.hpp>
 #include <alphagomoku/networks/AGNetwork.hpp>
+#include <alphagomoku/evaluation/Player.hpp>
+#include <alphagomoku/search/monte_carlo/NNEvaluator.hpp>
 #include <alphagomoku/utils/configs.hpp>
 
 #include <minml/utils/json.hpp>
@@ -31,8 +33,89 @@ namespace agref
 	extern void *g_eval_ctx;
 }
 
+namespace
+{
+	// one evaluation-game player of the reference with its own evaluator (src/evaluation/Player.cpp; EvaluationGame.cpp:95-150 drives it)
+	struct RefPlayer
+	{
+			NNEvaluator evaluator;
+			Player player;
+			RefPlayer(const GameConfig &gc, const SelfplayConfig &sc) :
+					evaluator(sc.device_config.at(0)),
+					player(gc, sc, evaluator, "player")
+			{
+				evaluator.useSymmetries(false);
+				evaluator.loadGraph(NetworkLoader(""));
+			}
+	};
+}
+
 extern "C"
 {
+	// Player with the network replaced by a callback (the shadow AGNetwork reads the callback installed at loadGraph time)
+	void* agref_player_create(int rules, int rows, int cols, int max_batch_size, int max_simulations, int solver_max_positions, const char *init_to,
+			float exploration_constant, agref_eval_fn eval_fn, void *ctx)
+	{
+		GameConfig gc(static_cast<GameRules>(rules), rows, cols);
+		agref::g_game_config = gc;
+		agref::g_eval_fn = eval_fn;
+		agref::g_eval_ctx = ctx;
+		SelfplayConfig sc;
+		sc.use_symmetries = false;
+		sc.constraints = Constraints::simulations(max_simulations);
+		sc.final_selector.policy = "max_visit";
+		sc.device_config = { DeviceConfig() };
+		sc.device_config[0].batch_size = max_batch_size;
+		sc.search_config.max_batch_size = max_batch_size;
+		sc.search_config.mcts_config.edge_selector_config.policy = "puct";
+		sc.search_config.mcts_config.edge_selector_config.init_to = init_to;
+		sc.search_config.mcts_config.edge_selector_config.exploration_constant = exploration_constant;
+		sc.search_config.tss_config.max_positions = solver_max_positions;
+		return new RefPlayer(gc, sc);
+	}
+	void agref_player_destroy(void *h)
+	{
+		delete static_cast<RefPlayer*>(h);
+	}
+	// the per-move loop of EvaluationGame::generate (EvaluationGame.cpp:95-150): setBoard, then select / solve / evaluate / expand / backup until
+	// isSearchOver, then getMove. Returns Move::toShort; root visits per cell and the root's simulation count for the comparison.
+	int agref_player_move(void *h, const int8_t *board, int sign_to_move, int32_t *root_visits_per_cell, int32_t *simulations)
+	{
+		RefPlayer *rp = static_cast<RefPlayer*>(h);
+		const GameConfig gc = rp->player.game_config;
+		matrix<Sign> b(gc.rows, gc.cols);
+		for (int i = 0; i < b.size(); i++)
+			b[i] = static_cast<Sign>(board[i]);
+		rp->player.setBoard(b, static_cast<Sign>(sign_to_move));
+		do
+		{
+			rp->player.selectSolveEvaluate();
+			rp->evaluator.evaluateGraph();
+			rp->player.expandBackup();
+		} while (not rp->player.isSearchOver());
+		const Node root = rp->player.tree.getInfo( { });
+		for (int i = 0; i < b.size(); i++)
+			root_visits_per_cell[i] = 0;
+		for (Edge *edge = root.begin(); edge < root.end(); edge++)
+			root_visits_per_cell[edge->getMove().row * gc.cols + edge->getMove().col] = edge->getVisits();
+		*simulations = rp->player.tree.getSimulationCount();
+		return rp->player.getMove().toShort();
+	}
+	// the solver's hash keys of this player (FastZobristHashing::m_keys), for the device table's bucket mapping
+	void agref_player_solver_keys(void *h, uint64_t *keys)
+	{
+		RefPlayer *rp = static_cast<RefPlayer*>(h);
+		const GameConfig gc = rp->player.game_config;
+		for (int r = 0; r < gc.rows; r++)
+			for (int c = 0; c < gc.cols; c++)
+				for (int sgn = 1; sgn <= 2; sgn++)
+				{ // like export_keys in ref_shim_search.cpp
+					HashKey128 k;
+					rp->player.search.getSolver().shared_table.getHashFunction().updateHash(k, Move(r, c, static_cast<Sign>(sgn)));
+					keys[2 * (2 * (r * gc.cols + c) + sgn - 1) + 0] = k.getLow();
+					keys[2 * (2 * (r * gc.cols + c) + sgn - 1) + 1] = k.getHigh();
+				}
+	}
 	// the reference's own parse of a config.json text: GameConfig(json["game_config"]) and SelfplayConfig(json["generation_config"])
 	// (src/utils/configs.cpp:44-50, 253-268), flattened for the comparison with agb_config_from_json. Returns 0, or -1 when the reference throws.
 	int agref_parse_config(const char *json_text, int32_t *ints, float *floats)
