@@ -24,7 +24,7 @@ namespace agb
 			int *nn_list, int *nn_count, cudaStream_t stream, int solver_sms, bool green);
 	namespace
 	{
-		constexpr int kSolverSmemPerWarp = kLinePitch * 8 + kMaxCells * 6 + 96; // line words, pattern types (4 B), threats, board, list lengths of one position: 3520 B
+		constexpr int kSolverSmemPerWarp = solver_kernel::position_layout::kBytes; // line words, pattern types (4 B), threats, board, list lengths of one position: 3520 B
 		constexpr int kGreenResidentWarps = 28; // per SM inside the solver's green context (shared by the launches of all pipeline groups)
 		constexpr int kResidentWarps = 10; // per SM, 72-register build: measured best of 4..28 (throughput is flat above ~8, the tail shorter below 28)
 		template<int kSolverWarpsPerBlock, int kMinBlocks>
@@ -56,12 +56,13 @@ namespace agb
 			// tables and stacks (ncu: 66 % L1 hits, 8.8 stalled warp-cycles per instruction on loads), shared memory always hits. The slot's
 			// global copy is never written back: the search leaves the position as it found it and the slot dies with the launch.
 			extern __shared__ __align__(16) uint8_t solver_smem[];
+			namespace layout = solver_kernel::position_layout;
 			uint8_t *const my_smem = solver_smem + (threadIdx.x >> 5) * kSolverSmemPerWarp;
-			uint64_t *const s_lines = reinterpret_cast<uint64_t*>(my_smem);
-			uint32_t *const s_ptypes = reinterpret_cast<uint32_t*>(my_smem + kLinePitch * 8);
-			uint8_t *const s_threats = my_smem + kLinePitch * 8 + kMaxCells * 4;
-			int8_t *const s_board = reinterpret_cast<int8_t*>(my_smem + kLinePitch * 8 + kMaxCells * 5);
-			int32_t *const s_hist_count = reinterpret_cast<int32_t*>(my_smem + kLinePitch * 8 + kMaxCells * 6);
+			uint64_t *const s_lines = reinterpret_cast<uint64_t*>(my_smem + layout::kLines);
+			uint32_t *const s_ptypes = reinterpret_cast<uint32_t*>(my_smem + layout::kPtypes);
+			uint8_t *const s_threats = my_smem + layout::kThreats;
+			int8_t *const s_board = reinterpret_cast<int8_t*>(my_smem + layout::kBoard);
+			int32_t *const s_hist_count = reinterpret_cast<int32_t*>(my_smem + layout::kHistCount);
 			for (int k = 0; k < n_slots; k++)
 			{
 				const int slot = st.game_slots[static_cast<size_t>(g) * st.batch + k];

@@ -229,18 +229,49 @@ namespace agb
 		}
 
 		// ---- view of one analysed position ---------------------------------------------------------------------------------------
+		// On the device the position under search -- line words, pattern types, threats, board, list lengths of ONE position -- sits in the shared
+		// memory of the warp that searches it (solver_kernel.cuh stages it there). The members below that "point" to those arrays are then not
+		// pointers but empty handles whose address is a compile-time offset from the warp's base: every access is a plain LDS / STS instead of a
+		// generic load through a pointer fetched from a stack object (no descriptor set-up, no dependent pointer load). The host build (tests)
+		// keeps ordinary pointers.
+		namespace position_layout
+		{
+			constexpr int kLines = 0, kPtypes = kLinePitch * 8, kThreats = kPtypes + kMaxCells * 4, kBoard = kThreats + kMaxCells, kHistCount = kBoard + kMaxCells,
+					kBytes = kHistCount + 96; // 3520 B per warp
+		}
+#ifdef __CUDA_ARCH__
+		__device__ __forceinline__ unsigned char* warp_position()
+		{
+			extern __shared__ __align__(16) unsigned char solver_smem[];
+			return solver_smem + (threadIdx.x >> 5) * position_layout::kBytes;
+		}
+		template<typename T, int kOffset>
+		struct PositionArray
+		{
+				PositionArray() = default;
+				template<typename U>
+				__device__ __forceinline__ PositionArray(const U&) {} // "assigned" from the staged copy's address: it IS that copy
+				__device__ __forceinline__ T* get() const { return reinterpret_cast<T*>(warp_position() + kOffset); }
+				__device__ __forceinline__ T& operator[](int i) const { return get()[i]; }
+				__device__ __forceinline__ operator T*() const { return get(); }
+				__device__ __forceinline__ T* operator+(int i) const { return get() + i; }
+		};
+#define AGB_POSITION_ARRAY(type, offset) PositionArray<type, position_layout::offset>
+#else
+#define AGB_POSITION_ARRAY(type, offset) type*
+#endif
 		struct DynState;
 		AGB_HD_NOINLINE inline bool dyn_is_forbidden(DynState *d, int sign, int r, int c); // solver_search.cuh: live state, reference side effects
 		enum : int { GEN_BASIC = 0, GEN_THREATS = 1, GEN_OPTIMAL = 2, GEN_REDUCED = 3, GEN_LEGAL = 4 }; // MoveGeneratorMode (MoveGenerator.hpp)
 		struct View
 		{
 				int S, cells, rules, stm, stones, draw_after, pitch; // pitch: cells per list in hist_cells
-				const int8_t *board;
-				const uint64_t *lines;
-				const uint32_t *ptypes;
-				const uint8_t *threats;
+				AGB_POSITION_ARRAY(const int8_t, kBoard) board;
+				AGB_POSITION_ARRAY(const uint64_t, kLines) lines;
+				AGB_POSITION_ARRAY(const uint32_t, kPtypes) ptypes;
+				AGB_POSITION_ARRAY(const uint8_t, kThreats) threats;
 				const uint8_t *forbidden; // renju: PatternCalculator::isForbidden(CROSS, .) per cell
-				const int32_t *hist_count; // [2][10]
+				AGB_POSITION_ARRAY(const int32_t, kHistCount) hist_count; // [2][10]
 				const uint16_t *hist_cells; // [2][10][pitch]
 				const uint8_t *pattern_table;
 				const uint16_t *def_table;

@@ -26,11 +26,11 @@ namespace agb
 		struct DynState
 		{
 				View v; // read side (same memory); stm / stones follow add and undo
-				int8_t *board;
-				uint64_t *lines;
-				uint32_t *ptypes;
-				uint8_t *threats;
-				int32_t *hist_count;
+				AGB_POSITION_ARRAY(int8_t, kBoard) board; // on the device: this warp's shared-memory copy (solver_logic.cuh)
+				AGB_POSITION_ARRAY(uint64_t, kLines) lines;
+				AGB_POSITION_ARRAY(uint32_t, kPtypes) ptypes;
+				AGB_POSITION_ARRAY(uint8_t, kThreats) threats;
+				AGB_POSITION_ARRAY(int32_t, kHistCount) hist_count;
 				uint16_t *hist_cells;
 				const uint8_t *threat_table;
 				// MoveGenerator::forbidden_moves_cache: results of isForbidden within one generate() call
