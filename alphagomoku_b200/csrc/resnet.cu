@@ -102,41 +102,40 @@ namespace agb
 		}
 
 		// Straight-line MMA schedule of one 3x3, F -> F convolution with row pitch P (17: 15x15 board, 22: 20x20 board split over the CTA
-		// pair) (the trunk and head convs: 40 of the
-		// 42 layers of a 20-block net). The issuing lane cannot hide latency, so everything that can be a compile-time constant
-		// is one: tap offsets (row pitch 17), K-slice offsets and the weight-ring geometry (32 KiB stages). Per MMA pair the lane
-		// executes two 64-bit adds and the two tcgen05.mma instructions.
+		// pair) (the trunk and head convs: 40 of the 42 layers of a 20-block net). The issuing lane cannot hide latency, so everything that
+		// can be a compile-time constant is one: tap offsets, K-slice offsets and the weight-ring geometry (one stage = the nine taps of one
+		// 16-channel slice of the input). Per MMA pair the lane executes two 64-bit adds and the two tcgen05.mma instructions.
+		// The K loop runs INPUT-CHANNEL-SLICE major: slice c of the input image is exactly what the previous layer's epilogue produces from
+		// accumulator columns 16c..16c+15, so this layer's MMAs on slice c start as soon as that part of the epilogue is done
+		// (chunk_ready[c]) while the rest of the epilogue is still draining the other accumulator set.
 		template<int F, int P>
-		__device__ __forceinline__ void issue_conv3x3(uint32_t tmem_base, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
-				uint32_t stage_step, uint64_t *w_full, uint64_t *peer_full, uint64_t *w_empty, int &stage, uint32_t &phase, int n_stages)
+		__device__ __forceinline__ void issue_conv3x3(uint32_t tmem_acc, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
+				uint32_t stage_step, uint64_t *w_full, uint64_t *peer_full, uint64_t *w_empty, uint64_t *chunk_ready, uint32_t &ready_phase, int &stage,
+				uint32_t &phase, int n_stages, long long *trace)
 		{
-			constexpr int KC = F / 8; // 8-channel slices per tap
-			constexpr int TPS = 32768 / ((F / 2) * 16 * KC); // taps per 32 KiB stage: 2 (F = 128) or 8 (F = 64)
 #pragma unroll
-			for (int t0 = 0; t0 < 9; t0 += TPS)
+			for (int c = 0; c < F / 16; c++)
 			{
+				// the weights first: they arrived long ago, and at the start of a layer (MMA queue empty) every wait after the image slice is
+				// ready would add to the bubble
 				mbar_wait(&w_full[stage], phase); // our half of the weights
 				mbar_wait_cluster(&peer_full[stage], phase); // the peer's half
+				mbar_wait_cluster(&chunk_ready[c], (ready_phase >> c) & 1u); // input channels 16c..16c+15 written by both CTAs, their accumulator columns drained
+				ready_phase ^= 1u << c;
 				tc_fence_after();
+				if (c == 0 and trace != nullptr)
+					*trace = clock64();
 				const uint64_t b_stage = b_desc0 + static_cast<uint32_t>(stage) * stage_step;
 				if (elect_one())
 				{
 #pragma unroll
-					for (int tt = 0; tt < TPS; tt++)
+					for (int tap = 0; tap < 9; tap++)
 					{
-						const int tap = t0 + tt;
-						if (tap < 9)
-						{
-							const int row0 = (tap / 3) * P + (tap % 3);
-#pragma unroll
-							for (int ks = 0; ks < KC / 2; ks++)
-							{
-								const uint64_t ad = a_desc0 + row0 + static_cast<uint32_t>(2 * ks) * a_kc_step;
-								const uint64_t bd = b_stage + (tt * KC + 2 * ks) * (F / 2);
-								mma_pair_bf16(tmem_base, ad, bd, idesc, (tap | ks) != 0);
-								mma_pair_bf16(tmem_base + F, ad + 128, bd, idesc, (tap | ks) != 0);
-							}
-						}
+						const int row0 = (tap / 3) * P + (tap % 3);
+						const uint64_t ad = a_desc0 + row0 + static_cast<uint32_t>(2 * c) * a_kc_step;
+						const uint64_t bd = b_stage + tap * 2 * (F / 2);
+						mma_pair_bf16(tmem_acc, ad, bd, idesc, (tap | c) != 0);
+						mma_pair_bf16(tmem_acc + F, ad + 128, bd, idesc, (tap | c) != 0);
 					}
 					mma_pair_commit(&w_empty[stage], 3); // both CTAs may refill this stage once these MMAs have read it
 				}
@@ -167,14 +166,13 @@ namespace agb
 			uint8_t *buf_x = smem;
 			uint8_t *buf_h = smem + prm.buf_bytes;
 			uint8_t *stages = smem + 2 * prm.buf_bytes;
-			float *partial = reinterpret_cast<float*>(stages + NS * prm.stage_bytes); // [2][3][256]
-			float *logits = partial + 2 * 3 * 256; // [256]
+			float *logits = reinterpret_cast<float*>(stages + NS * prm.stage_bytes); // [256]
 			float *reduce = logits + 256; // [8]
 			float *sbias2 = reduce + 8; // [2][128]
 			float *xchg = sbias2 + 256; // [2] softmax (max, sum) of the peer's half board (SPLIT)
 			uint64_t *bars = reinterpret_cast<uint64_t*>(xchg + 8);
-			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *img_ready = bars + 17, *peer_full = bars + 18, *xbar = bars + 26;
-			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *peer_full = bars + 18, *xbar = bars + 26, *chunk_ready = bars + 27;
+			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
 			// CTA pair: rank 0 (leader) issues the MMAs for both boards; each CTA loads half of every weight tile
 			const uint32_t rank = cluster_ctarank();
 			const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -183,7 +181,7 @@ namespace agb
 			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 			const uint32_t img_chunk_bytes = prm.img_rows * 16;
 			const uint32_t in_chunk_bytes = prm.in_img_rows * 16;
-			const uint32_t tmem_cols = (2 * F <= 128) ? 128 : 256;
+			const uint32_t tmem_cols = 4 * F; // two accumulator sets (layer parity) of two M-tiles x F columns: 256 (F = 64) or all 512 columns
 
 			if (threadIdx.x == 0)
 			{
@@ -195,7 +193,8 @@ namespace agb
 				}
 				mbar_init(acc_full, 1);
 				mbar_init(xbar, 1);
-				mbar_init(img_ready, 2 * (kEpilogueThreads / 32)); // one arrival per epilogue warp of both CTAs, on the leader's barrier
+				for (int c = 0; c < 8; c++)
+					mbar_init(&chunk_ready[c], 2 * (kEpilogueThreads / 32)); // one arrival per epilogue warp of both CTAs, on the leader's barrier
 				fence_mbar_init();
 			}
 			if (warp == 1)
@@ -244,7 +243,7 @@ namespace agb
 				if (rank == 0)
 				{ // the whole warp walks the (warp-uniform) schedule; one elected lane issues the MMAs and commits
 					int stage = 0;
-					uint32_t phase = 0, img_phase = 0;
+					uint32_t phase = 0, ready_phase = 0;
 					const uint32_t idesc = idesc_bf16_f32(256, F); // M = 256: 128 positions of this CTA's board + 128 of the peer's
 					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
 						for (int l = 0; l < prm.n_layers; l++)
@@ -258,48 +257,50 @@ namespace agb
 							// The same shared-memory offsets are valid in both CTAs of the pair.
 							const uint64_t a_desc0 = smem_desc(a_img, a_lbo, 128), b_desc0 = smem_desc(smem_u32(stages), (F / 2) * 16, 128);
 							const uint32_t a_kc_step = a_lbo >> 4, b_kc_step = F / 2, stage_step = prm.stage_bytes >> 4;
-							mbar_wait_cluster(img_ready, img_phase & 1); // both input images written, both accumulators drained
-							img_phase++;
-							tc_fence_after();
-							if (prm.trace and b0 == 0 and lane == 0)
-								prm.trace[6 * l + 0] = clock64();
-							int kin = 0, ky = 0, kx = 0; // position in the layer's stream of 8-channel weight slices
-							long long wait_own = 0, wait_peer = 0;
-							const bool fast = (S == (SPLIT ? 20 : 15) and L.radius == 1 and cin_chunks == F / 8 and prm.stage_bytes == 32768);
+							const uint32_t tmem_acc = tmem_base + (l & 1) * 2 * F; // accumulator sets alternate: the previous layer's is still being drained
+							long long *trace0 = (prm.trace and b0 == 0 and lane == 0) ? prm.trace + 6 * l : nullptr;
+							int chunk = 0, tap = 0, ky = 0, kx = 0; // position in the layer's stream of weight slices: 16-channel slice of the input, then tap
+							const bool fast = (S == (SPLIT ? 20 : 15) and L.radius == 1 and cin_chunks == F / 8 and prm.kc_per_stage == 18);
 							if (fast)
-								issue_conv3x3<F, SPLIT ? 22 : 17>(tmem_base, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, stage, phase, NS);
+								issue_conv3x3<F, SPLIT ? 22 : 17>(tmem_acc, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, chunk_ready, ready_phase,
+										stage, phase, NS, trace0);
 							else
 							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
 								const int nkc = min(prm.kc_per_stage, total_kc - kc0);
-								const long long tw0 = clock64();
 								mbar_wait(&w_full[stage], phase); // our half of the weights
-								const long long tw1 = clock64();
 								mbar_wait_cluster(&peer_full[stage], phase); // the peer's half
-								wait_own += tw1 - tw0;
-								wait_peer += clock64() - tw1;
 								tc_fence_after();
 								uint64_t bd = b_desc0 + stage * stage_step;
 								for (int j = 0; j < nkc; j += 2)
 								{ // one K=16 step: two 8-channel slices of one tap, for both M-tiles of both boards
-									const uint64_t ad = a_desc0 + (ky * P + kx) + kin * a_kc_step;
+									if (tap == 0)
+									{ // a new 16-channel slice of the input image: wait until both CTAs have written it
+										mbar_wait_cluster(&chunk_ready[chunk], (ready_phase >> chunk) & 1u);
+										ready_phase ^= 1u << chunk;
+										tc_fence_after();
+										if (chunk == 0 and trace0 != nullptr)
+											*trace0 = clock64();
+									}
+									const uint64_t ad = a_desc0 + (ky * P + kx) + 2 * chunk * a_kc_step;
 									const bool acc = (kc0 + j) != 0;
 									if (elect_one())
 									{
-										mma_pair_bf16(tmem_base, ad, bd, idesc, acc);
-										mma_pair_bf16(tmem_base + F, ad + 128, bd, idesc, acc);
+										mma_pair_bf16(tmem_acc, ad, bd, idesc, acc);
+										mma_pair_bf16(tmem_acc + F, ad + 128, bd, idesc, acc);
 									}
 									__syncwarp();
 									bd += 2 * b_kc_step;
-									kin += 2;
-									if (kin == cin_chunks)
+									if (++kx == KW)
 									{
-										kin = 0;
-										if (++kx == KW)
-										{
-											kx = 0;
-											ky++;
-										}
+										kx = 0;
+										ky++;
+									}
+									if (++tap == L.n_taps)
+									{
+										tap = 0;
+										ky = 0;
+										chunk++;
 									}
 								}
 								if (elect_one())
@@ -314,8 +315,6 @@ namespace agb
 							if (prm.trace and b0 == 0 and lane == 0)
 							{
 								prm.trace[6 * l + 1] = clock64();
-								prm.trace[6 * l + 4] = wait_own;
-								prm.trace[6 * l + 5] = wait_peer;
 							}
 							if (elect_one())
 								mma_pair_commit(acc_full, 3);
@@ -347,7 +346,7 @@ namespace agb
 			{ // ===== epilogue warps (also build the input image and run the fused heads) =====
 				const int et = threadIdx.x - 64;
 				const int quadrant = warp & 3; // TMEM lanes 32*quadrant .. +31 are the ones this warp may read
-				const int half = (warp - 2) >> 2; // which half of the output channels
+				const int tile = (warp - 2) >> 2; // which of the board's two 128-row M-tiles this warp drains (all F channels of its 32 rows)
 				const int cells = S * S;
 				uint32_t acc_phase = 0, xchg_phase = 0;
 				// rows of the board this CTA computes: all of them, or (SPLIT) the upper / lower part
@@ -388,12 +387,22 @@ namespace agb
 					tc_fence_before();
 					__syncwarp(); // the lane that arrives publishes the whole warp's writes
 					if (lane == 0)
-					{
-						if (rank == 0)
-							mbar_arrive(img_ready);
-						else
-							mbar_arrive_remote(img_ready, 0);
+					{ // the stem reads 32 input channels = two 16-channel slices
+						for (int c = 0; c < 2; c++)
+						{
+							if (rank == 0)
+								mbar_arrive(&chunk_ready[c]);
+							else
+								mbar_arrive_remote(&chunk_ready[c], 0);
+						}
 					}
+					// this warp's 32 accumulator rows = 32 positions of the padded board image
+					const int p = tile * 128 + quadrant * 32 + lane;
+					const int y = p / P, x = p - y * P;
+					const bool valid = (y < my_rows) and (x < S);
+					const uint32_t out_idx = p + P + 1;
+					const bool send = SPLIT and valid and (rank == 0 ? (y == my_rows - 1) : (y == 0));
+					const uint32_t peer_idx = (rank == 0) ? (x + 1) : ((rows0 + 1) * P + x + 1);
 
 					for (int l = 0; l < prm.n_layers; l++)
 					{
@@ -404,103 +413,128 @@ namespace agb
 						if (et < F)
 							sbias[et] = __ldg(prm.bias + L.bias_offset + et);
 						named_barrier_epilogue();
-						mbar_wait_backoff(acc_full, acc_phase & 1, 32);
+						mbar_wait(acc_full, acc_phase & 1); // try_wait suspends the warp in hardware: no polling load next to the MMA-issuing lane
 						acc_phase++;
 						tc_fence_after();
+						const long long t_epilogue = (prm.trace and bi == 0 and et == 0) ? clock64() : 0;
 						if (prm.trace and bi == 0 and et == 0)
-							prm.trace[6 * l + 2] = clock64();
+							prm.trace[6 * l + 2] = t_epilogue;
 						if (L.mode == MODE_STEM)
 						{ // the stem image is dead now: give the h buffer its zero halo back
 							for (uint32_t i = et; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kEpilogueThreads)
 								reinterpret_cast<uint4*>(buf_h)[i] = make_uint4(0, 0, 0, 0);
 						}
 						uint8_t *out_img = (L.mode == MODE_CONV1) ? buf_h : buf_x;
-						float head[2][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
-						constexpr int HC = F / 2; // output channels handled by this warp (its half), as HC/16 TMEM loads of 16 columns
+						float head[3] = { 0.f, 0.f, 0.f };
 						// SPLIT: the row next to the other part also goes into the peer's halo row of the same image (distributed shared memory)
 						const uint32_t peer_img = SPLIT ? map_to_rank(smem_u32(out_img), rank ^ 1u) : 0u;
-						for (int tile = 0; tile < 2; tile++)
-						{
-							const int p = tile * 128 + quadrant * 32 + lane;
-							const int y = p / P, x = p - y * P;
-							const bool valid = (y < my_rows) and (x < S);
-							const uint32_t out_idx = p + P + 1;
-							const bool send = SPLIT and valid and (rank == 0 ? (y == my_rows - 1) : (y == 0));
-							const uint32_t peer_idx = (rank == 0) ? (x + 1) : ((rows0 + 1) * P + x + 1);
-							// all TMEM loads of this tile are issued back to back and waited for once
-							uint32_t v[HC];
+						const bool hand_over = l + 1 < prm.n_layers;
+						// The accumulator is drained 16 columns (= 16 output channels = one K slice of the next layer) at a time; after each slice the
+						// warp publishes it (chunk_ready), so the next layer's MMAs on that slice run while the rest is still being drained. The TMEM load
+						// of slice c+1 is in flight while slice c is processed.
+						const uint32_t taddr = tmem_base + ((quadrant * 32u) << 16) + (l & 1) * 2 * F + tile * F;
+						uint32_t v[2][16];
+						tmem_ld16(taddr, v[0]);
 #pragma unroll
-							for (int cb = 0; cb < HC; cb += 16)
-								tmem_ld16(tmem_base + ((quadrant * 32u) << 16) + tile * F + half * HC + cb, *reinterpret_cast<uint32_t (*)[16]>(&v[cb]));
-							uint4 res[HC / 8];
+						for (int cb = 0; cb < F / 16; cb++)
+						{
+							const int c0 = cb * 16;
+							uint4 res[2];
 							if (L.mode == MODE_CONV2)
 							{ // residual operand: x is updated in place
-#pragma unroll
-								for (int h8 = 0; h8 < HC / 8; h8++)
-									res[h8] = *reinterpret_cast<const uint4*>(buf_x + ((half * HC) / 8 + h8) * img_chunk_bytes + out_idx * 16);
+								res[0] = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8) * img_chunk_bytes + out_idx * 16);
+								res[1] = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8 + 1) * img_chunk_bytes + out_idx * 16);
 							}
 							tmem_ld_wait();
+							long long t_ld = 0, t_st = 0, t_fence = 0;
+							if (cb == 0 and prm.trace and bi == 0 and et == 0)
+								t_ld = clock64();
+							if (cb + 1 < F / 16)
+								tmem_ld16(taddr + c0 + 16, v[(cb + 1) & 1]);
+							float a[16];
 #pragma unroll
-							for (int cb = 0; cb < HC; cb += 16)
+							for (int j = 0; j < 16; j += 4)
 							{
-								const int c0 = half * HC + cb;
-								float a[16];
+								const float4 bj = *reinterpret_cast<const float4*>(sbias + c0 + j);
+								a[j] = __uint_as_float(v[cb & 1][j]) + bj.x;
+								a[j + 1] = __uint_as_float(v[cb & 1][j + 1]) + bj.y;
+								a[j + 2] = __uint_as_float(v[cb & 1][j + 2]) + bj.z;
+								a[j + 3] = __uint_as_float(v[cb & 1][j + 3]) + bj.w;
+							}
+							if (L.mode == MODE_CONV2)
+							{
 #pragma unroll
-								for (int j = 0; j < 16; j += 4)
+								for (int h8 = 0; h8 < 2; h8++)
 								{
-									const float4 bj = *reinterpret_cast<const float4*>(sbias + c0 + j);
-									a[j] = __uint_as_float(v[cb + j]) + bj.x;
-									a[j + 1] = __uint_as_float(v[cb + j + 1]) + bj.y;
-									a[j + 2] = __uint_as_float(v[cb + j + 2]) + bj.z;
-									a[j + 3] = __uint_as_float(v[cb + j + 3]) + bj.w;
+									const uint4 r = res[h8];
+									float lo, hi;
+									unpack_bf16(r.x, lo, hi); a[8 * h8 + 0] += lo; a[8 * h8 + 1] += hi;
+									unpack_bf16(r.y, lo, hi); a[8 * h8 + 2] += lo; a[8 * h8 + 3] += hi;
+									unpack_bf16(r.z, lo, hi); a[8 * h8 + 4] += lo; a[8 * h8 + 5] += hi;
+									unpack_bf16(r.w, lo, hi); a[8 * h8 + 6] += lo; a[8 * h8 + 7] += hi;
 								}
-								if (L.mode == MODE_CONV2)
-								{
+							}
+							if (L.mode == MODE_QHEAD)
+							{
 #pragma unroll
-									for (int h8 = 0; h8 < 2; h8++)
-									{
-										const uint4 r = res[cb / 8 + h8];
-										float lo, hi;
-										unpack_bf16(r.x, lo, hi); a[8 * h8 + 0] += lo; a[8 * h8 + 1] += hi;
-										unpack_bf16(r.y, lo, hi); a[8 * h8 + 2] += lo; a[8 * h8 + 3] += hi;
-										unpack_bf16(r.z, lo, hi); a[8 * h8 + 4] += lo; a[8 * h8 + 5] += hi;
-										unpack_bf16(r.w, lo, hi); a[8 * h8 + 6] += lo; a[8 * h8 + 7] += hi;
-									}
-								}
-								if (L.mode == MODE_QHEAD)
+								for (int j = 0; j < 16; j++)
 								{
-#pragma unroll
-									for (int j = 0; j < 16; j++)
-									{
-										const float t = tanhf(a[j]);
-										head[tile][0] += t * __ldg(prm.q_w1 + c0 + j);
-										head[tile][1] += t * __ldg(prm.q_w1 + F + c0 + j);
-										head[tile][2] += t * __ldg(prm.q_w1 + 2 * F + c0 + j);
-									}
+									const float t = tanhf(a[j]);
+									head[0] += t * __ldg(prm.q_w1 + c0 + j);
+									head[1] += t * __ldg(prm.q_w1 + F + c0 + j);
+									head[2] += t * __ldg(prm.q_w1 + 2 * F + c0 + j);
 								}
+							}
+							else if (L.mode == MODE_POLICY)
+							{
+#pragma unroll
+								for (int j = 0; j < 16; j++)
+									head[0] += fmaxf(a[j], 0.0f) * __ldg(prm.policy_w1 + c0 + j);
+							}
+							else if (valid)
+							{
+#pragma unroll
+								for (int h8 = 0; h8 < 2; h8++)
+								{
+									uint4 o;
+									o.x = pack_bf16_relu(a[8 * h8 + 0], a[8 * h8 + 1]);
+									o.y = pack_bf16_relu(a[8 * h8 + 2], a[8 * h8 + 3]);
+									o.z = pack_bf16_relu(a[8 * h8 + 4], a[8 * h8 + 5]);
+									o.w = pack_bf16_relu(a[8 * h8 + 6], a[8 * h8 + 7]);
+									*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
+									if (send)
+										st_peer_v4(peer_img + (c0 / 8 + h8) * img_chunk_bytes + peer_idx * 16, o);
+								}
+							}
+							if (cb == 0 and prm.trace and bi == 0 and et == 0)
+								t_st = clock64();
+							if (hand_over)
+							{ // hand this slice of the image (and the drained accumulator columns) to the MMA warp
+								tc_fence_before();
+								if constexpr (SPLIT)
+									fence_proxy_async_all(); // covers the rows written into the peer's image
 								else
+									fence_proxy_async();
+								__syncwarp(); // the lane that arrives publishes the whole warp's writes
+								if (cb == 0 and prm.trace and bi == 0 and et == 0)
+									t_fence = clock64();
+								if (lane == 0)
 								{
-									if (L.mode == MODE_POLICY)
+									if (rank == 0)
 									{
-#pragma unroll
-										for (int j = 0; j < 16; j++)
-											head[tile][0] += fmaxf(a[j], 0.0f) * __ldg(prm.policy_w1 + c0 + j);
+										if constexpr (SPLIT)
+											mbar_arrive_cluster(&chunk_ready[cb]);
+										else
+											mbar_arrive(&chunk_ready[cb]);
 									}
-									else if (valid)
-									{
-#pragma unroll
-										for (int h8 = 0; h8 < 2; h8++)
-										{
-											uint4 o;
-											o.x = pack_bf16_relu(a[8 * h8 + 0], a[8 * h8 + 1]);
-											o.y = pack_bf16_relu(a[8 * h8 + 2], a[8 * h8 + 3]);
-											o.z = pack_bf16_relu(a[8 * h8 + 4], a[8 * h8 + 5]);
-											o.w = pack_bf16_relu(a[8 * h8 + 6], a[8 * h8 + 7]);
-											*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
-											if (send)
-												st_peer_v4(peer_img + (c0 / 8 + h8) * img_chunk_bytes + peer_idx * 16, o);
-										}
-									}
+									else
+										mbar_arrive_remote(&chunk_ready[cb], 0);
+								}
+								if (cb == 0 and prm.trace and bi == 0 and et == 0)
+								{ // AGB_NET_TRACE: where the hand-over of the first slice spends its time (relative to the epilogue's start)
+									const long long t0 = t_epilogue;
+									prm.trace[6 * l + 4] = ((t_ld - t0) << 32) | (t_st - t0);
+									prm.trace[6 * l + 5] = ((t_fence - t0) << 32) | (clock64() - t0);
 								}
 							}
 						}
@@ -508,14 +542,7 @@ namespace agb
 
 						if (L.mode == MODE_POLICY)
 						{ // 1x1 conv to one logit per cell, softmax over the board (createPolicyHead, blocks.cpp:99-107)
-							for (int tile = 0; tile < 2; tile++)
-								partial[half * 256 + tile * 128 + quadrant * 32 + lane] = head[tile][0];
-							named_barrier_epilogue();
-							{
-								const int p = et, y = p / P, x = p - y * P;
-								const bool valid = (y < my_rows) and (x < S);
-								logits[p] = valid ? (partial[p] + partial[256 + p] + __ldg(prm.policy_w1 + F)) : -INFINITY;
-							}
+							logits[p] = valid ? (head[0] + __ldg(prm.policy_w1 + F)) : -INFINITY;
 							named_barrier_epilogue();
 							float m = logits[et];
 							for (int o = 16; o > 0; o >>= 1)
@@ -554,23 +581,20 @@ namespace agb
 								const float scale = expf(m - m_all);
 								out = e * scale / (s * scale + s_peer * expf(m_peer - m_all));
 							}
-							const int p = et, y = p / P, x = p - y * P;
-							if (live and y < my_rows and x < S)
-								prm.policy[static_cast<size_t>(b) * cells + (row_begin + y) * S + x] = out;
+							{
+								const int pe = et, ye = pe / P, xe = pe - ye * P;
+								if (live and ye < my_rows and xe < S)
+									prm.policy[static_cast<size_t>(b) * cells + (row_begin + ye) * S + xe] = out;
+							}
 							named_barrier_epilogue();
 						}
 						else if (L.mode == MODE_QHEAD)
 						{ // 1x1 conv to 3 logits per cell, softmax over them (createActionValuesHead, blocks.cpp:119-127)
-							for (int tile = 0; tile < 2; tile++)
-								for (int k = 0; k < 3; k++)
-									partial[(half * 3 + k) * 256 + tile * 128 + quadrant * 32 + lane] = head[tile][k];
-							named_barrier_epilogue();
-							const int p = et, y = p / P, x = p - y * P;
-							if (live and y < my_rows and x < S and prm.q != nullptr)
+							if (live and valid and prm.q != nullptr)
 							{
 								float z[3];
 								for (int k = 0; k < 3; k++)
-									z[k] = partial[k * 256 + p] + partial[(3 + k) * 256 + p] + __ldg(prm.q_w1 + 3 * F + k);
+									z[k] = head[k] + __ldg(prm.q_w1 + 3 * F + k);
 								const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
 								const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
 								const float inv = 1.0f / (e0 + e1 + e2);
@@ -579,16 +603,15 @@ namespace agb
 								dst[1] = e1 * inv;
 								dst[2] = e2 * inv;
 							}
-							named_barrier_epilogue();
 						}
 						else if (L.last_trunk)
 						{ // value head 1x1 conv F -> 4 + ReLU on the final trunk output (createValueHead, blocks.cpp:108-111)
 							named_barrier_epilogue();
 							for (int lc = et; lc < my_rows * S; lc += kEpilogueThreads)
 							{
-								const int y = lc / S, x = lc - y * S;
-								const int cell = (row_begin + y) * S + x;
-								const uint32_t idx = (y + 1) * P + x + 1;
+								const int yv = lc / S, xv0 = lc - yv * S;
+								const int cell = (row_begin + yv) * S + xv0;
+								const uint32_t idx = (yv + 1) * P + xv0 + 1;
 								float s4[4] = { 0.f, 0.f, 0.f, 0.f };
 								for (int ch = 0; ch < F / 8; ch++)
 								{
@@ -615,26 +638,6 @@ namespace agb
 						}
 						if (prm.trace and bi == 0 and et == 0)
 							prm.trace[6 * l + 3] = clock64();
-						if (l + 1 < prm.n_layers)
-						{ // hand the image (and the drained accumulators) to the MMA warp
-							if constexpr (SPLIT)
-								fence_proxy_async_all(); // covers the rows written into the peer's image
-							else
-								fence_proxy_async();
-							__syncwarp();
-							if (lane == 0)
-							{
-								if (rank == 0)
-								{
-									if constexpr (SPLIT)
-										mbar_arrive_cluster(img_ready);
-									else
-										mbar_arrive(img_ready);
-								}
-								else
-									mbar_arrive_remote(img_ready, 0);
-							}
-						}
 					}
 				}
 			}
@@ -734,7 +737,8 @@ namespace agb
 				n += f * 9 * f + f + 3 * f + 3;
 			return n;
 		}
-		// fp32 W[F][k][k][cin] -> bf16 tap images [half][tap][cin/8][F/2][8]
+		// fp32 W[F][k][k][cin] -> bf16 weight slices [half][cin/16][tap][2][F/2][8]: 16 input channels at a time (what one part of the previous
+		// layer's epilogue produces), all taps of those, each as the two 8-channel core-matrix columns of one K = 16 MMA step
 		void append_conv_image(std::vector<uint16_t> &img, const float *w, int F, int k, int cin)
 		{
 			const auto to_bf16 = [](float x)
@@ -744,13 +748,14 @@ namespace agb
 				const uint32_t rounded = u + 0x7FFFu + ((u >> 16) & 1u); // round to nearest even
 				return static_cast<uint16_t>(rounded >> 16);
 			};
-			// half-major: CTA `half` of a pair streams [tap][cin/8][F/2 rows][8] for output channels half*F/2 ..
+			// half-major: CTA `half` of a pair streams the slices for output channels half*F/2 ..
 			for (int half = 0; half < 2; half++)
-				for (int tap = 0; tap < k * k; tap++)
-					for (int kc = 0; kc < cin / 8; kc++)
-						for (int co = half * (F / 2); co < (half + 1) * (F / 2); co++)
-							for (int e = 0; e < 8; e++)
-								img.push_back(to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]));
+				for (int c16 = 0; c16 < cin / 16; c16++)
+					for (int tap = 0; tap < k * k; tap++)
+						for (int kc = 2 * c16; kc < 2 * c16 + 2; kc++)
+							for (int co = half * (F / 2); co < (half + 1) * (F / 2); co++)
+								for (int e = 0; e < 8; e++)
+									img.push_back(to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]));
 		}
 	}
 
@@ -796,11 +801,12 @@ namespace agb
 		p.img_rows = ((256 + 2 * p.P + 2) + 7) / 8 * 8;
 		p.in_img_rows = ((256 + 4 * p.P + 4) + 7) / 8 * 8;
 		p.buf_bytes = (F / 8) * p.img_rows * 16;
-		{ // weight ring geometry (tunable: AGB_NET_STAGE_KB / AGB_NET_STAGES)
-			const char *kb = getenv("AGB_NET_STAGE_KB"), *ns = getenv("AGB_NET_STAGES");
-			p.stage_bytes = (kb ? atoi(kb) : 32) * 1024; // measured best on B200 (profiles/r01_k4_weight_ring.txt)
-			p.kc_per_stage = p.stage_bytes / ((F / 2) * 16);
-			p.n_stages = ns ? atoi(ns) : ((F == 128) ? 2 : 4);
+		{ // weight ring geometry (tunable: AGB_NET_STAGE_SLICES / AGB_NET_STAGES). One stage = 18 slices = the nine taps of one 16-channel part
+			// of a 3x3 layer's input (18 KiB per CTA at 128 filters), which is the unit the straight-line MMA schedule consumes.
+			const char *sl = getenv("AGB_NET_STAGE_SLICES"), *ns = getenv("AGB_NET_STAGES");
+			p.kc_per_stage = sl ? atoi(sl) : 18;
+			p.stage_bytes = p.kc_per_stage * (F / 2) * 16;
+			p.n_stages = ns ? atoi(ns) : ((F == 128) ? ((S * (S + 2) > 256) ? 3 : 4) : 6);
 			if (p.kc_per_stage < 2 or p.kc_per_stage % 2 != 0 or p.n_stages < 2 or p.n_stages > kMaxStages)
 				return e->fail(AGB_EINVAL, "bad weight ring geometry");
 		}
@@ -885,7 +891,7 @@ namespace agb
 		p.q_w1 = c.q_head ? n->d_small + q_w1_off : nullptr;
 		p.value_hidden = n->d_value_hidden;
 		n->dense_width = D;
-		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (2 * 3 * 256 + 256 + 8 + 256 + 8) * 4 + 32 * 8;
+		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (256 + 8 + 256 + 8) * 4 + 48 * 8;
 		n->split = S * (S + 2) > 256; // the board does not fit one CTA's 256 accumulator rows: one board per CTA pair
 		if (n->smem_bytes > 232448)
 			return e->fail(AGB_EINVAL, "network kernel needs " + std::to_string(n->smem_bytes) + " bytes of shared memory per CTA, more than the device has");
@@ -949,8 +955,8 @@ namespace agb
 			if (f)
 			{
 				for (int l = 0; l < p.n_layers; l++)
-					fprintf(f, "%d %lld %lld %lld %lld  wait_own=%lld wait_peer=%lld\n", l, h[6 * l] - h[0], h[6 * l + 1] - h[0], h[6 * l + 2] - h[0], h[6 * l + 3] - h[0],
-							h[6 * l + 4], h[6 * l + 5]);
+					fprintf(f, "%d %lld %lld %lld %lld  first_slice: ld=%lld stored=%lld fenced=%lld arrived=%lld\n", l, h[6 * l] - h[0], h[6 * l + 1] - h[0], h[6 * l + 2] - h[0],
+							h[6 * l + 3] - h[0], h[6 * l + 4] >> 32, h[6 * l + 4] & 0xFFFFFFFFll, h[6 * l + 5] >> 32, h[6 * l + 5] & 0xFFFFFFFFll);
 				fclose(f);
 			}
 		}
