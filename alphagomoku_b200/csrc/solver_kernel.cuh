@@ -24,7 +24,7 @@ namespace agb
 			int *nn_list, int *nn_count, cudaStream_t stream, int solver_sms, bool green);
 	namespace
 	{
-		constexpr int kSolverSmemPerWarp = solver_kernel::position_layout::kBytes; // line words, pattern types (4 B), threats, board, list lengths of one position: 3520 B
+		constexpr int kSolverSmemPerWarp = solver_kernel::position_layout::kBytes; // line words, pattern types (4 B), threats, board, list lengths and list index of one position: 5120 B
 		constexpr int kGreenResidentWarps = 28; // per SM inside the solver's green context (shared by the launches of all pipeline groups)
 		constexpr int kResidentWarps = 10; // per SM, 72-register build: measured best of 4..28 (throughput is flat above ~8, the tail shorter below 28)
 		template<int kSolverWarpsPerBlock, int kMinBlocks>
@@ -94,6 +94,9 @@ namespace agb
 				d.threat_table = tables.threat;
 				d.v = solver_kernel::View { S, cells, rules, store.sign_to_move[slot], stones, draw_after, kCellPitch, d.board, d.lines, d.ptypes, d.threats,
 						store.forbidden + cbase, d.hist_count, d.hist_cells, tables.pattern, st.def_table, &d };
+#ifdef __CUDA_ARCH__
+				solver_kernel::dyn_build_list_index(d);
+#endif
 				solver_kernel::encode_forbidden_pass(d);
 				const solver_kernel::SearchOutput res = solver_kernel::solve_position(d, tt, mem, max_nodes, 100);
 				uint16_t *om = out.moves + static_cast<size_t>(slot) * out.pitch;

@@ -236,8 +236,10 @@ namespace agb
 		// keeps ordinary pointers.
 		namespace position_layout
 		{
+			// kListIndex: for every cell and colour, where the cell sits in the threat list it is on ([row * kMaxSize + col][colour], uint16): removing a
+			// cell from a list is then "move the last entry into its place" without searching for it
 			constexpr int kLines = 0, kPtypes = kLinePitch * 8, kThreats = kPtypes + kMaxCells * 4, kBoard = kThreats + kMaxCells, kHistCount = kBoard + kMaxCells,
-					kBytes = kHistCount + 96; // 3520 B per warp
+					kListIndex = kHistCount + 96, kBytes = kListIndex + kMaxCells * 4; // 5120 B per warp
 		}
 #ifdef __CUDA_ARCH__
 		__device__ __forceinline__ unsigned char* warp_position()

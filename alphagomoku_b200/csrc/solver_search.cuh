@@ -31,6 +31,7 @@ namespace agb
 				AGB_POSITION_ARRAY(uint32_t, kPtypes) ptypes;
 				AGB_POSITION_ARRAY(uint8_t, kThreats) threats;
 				AGB_POSITION_ARRAY(int32_t, kHistCount) hist_count;
+				AGB_POSITION_ARRAY(uint16_t, kListIndex) list_index; // device only: see position_layout
 				uint16_t *hist_cells;
 				const uint8_t *threat_table;
 				// MoveGenerator::forbidden_moves_cache: results of isForbidden within one generate() call
@@ -45,33 +46,56 @@ namespace agb
 		// only through threat_at / the pattern table; AlphaBetaSearch::evaluate gives the type weight 0), and the slot's lists die with the
 		// launch, so the search keeps only the lists of OPEN_3 and stronger in step: the longest list of a mid-game position costs nothing.
 		AGB_HD inline bool list_is_kept(int type) { return type > TT_HALF_OPEN_3; }
+#ifdef __CUDA_ARCH__
+		// All lanes of the game's warp run these with identical arguments (lockstep); every lane does all of it, so each lane only ever depends on
+		// its own earlier loads and stores. A cell is on at most one list per colour, and d.list_index remembers where: ThreatHistogram::remove's
+		// linear search (the reference finds the FIRST match; a cell occurs once) becomes one load.
+		__device__ __forceinline__ int list_index_of(uint16_t loc, int colour) { return 2 * ((loc & 255) * kMaxSize + (loc >> 8)) + colour; }
+		__device__ __forceinline__ void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
+		{ // ThreatHistogram::remove (ThreatHistogram.hpp:74-91)
+			if (not list_is_kept(type))
+				return;
+			int32_t &count = d.hist_count[colour * kHistTypes + type];
+			uint16_t *list = d.hist_cells + (colour * kHistTypes + type) * kCellPitch;
+			const int len = count;
+			const int found = d.list_index[list_index_of(loc, colour)];
+			if (found < len)
+			{
+				const uint16_t last = list[len - 1];
+				list[found] = last;
+				d.list_index[list_index_of(last, colour)] = static_cast<uint16_t>(found);
+				count = len - 1;
+			}
+		}
+		__device__ __forceinline__ void dyn_hist_add(DynState &d, int colour, int type, uint16_t loc)
+		{
+			if (not list_is_kept(type))
+				return;
+			int32_t &count = d.hist_count[colour * kHistTypes + type];
+			const int len = count;
+			d.hist_cells[(colour * kHistTypes + type) * kCellPitch + len] = loc;
+			d.list_index[list_index_of(loc, colour)] = static_cast<uint16_t>(len);
+			count = len + 1;
+		}
+		// the index of the lists as K1 left them (the kept ones): lanes take interleaved entries
+		__device__ __forceinline__ void dyn_build_list_index(DynState &d)
+		{
+			for (int k = 0; k < 2 * kHistTypes; k++)
+				if (list_is_kept(k % kHistTypes))
+				{
+					const int len = d.hist_count[k];
+					for (int i = threadIdx.x & 31; i < len; i += 32)
+						d.list_index[list_index_of(d.hist_cells[k * kCellPitch + i], k / kHistTypes)] = static_cast<uint16_t>(i);
+				}
+			__syncwarp();
+		}
+#else
 		AGB_HD_NOINLINE inline void dyn_hist_remove(DynState &d, int colour, int type, uint16_t loc)
 		{ // ThreatHistogram::remove (ThreatHistogram.hpp:74-91)
 			if (not list_is_kept(type))
 				return;
 			int32_t &count = d.hist_count[colour * kHistTypes + type];
 			uint16_t *list = d.hist_cells + (colour * kHistTypes + type) * d.v.pitch;
-#ifdef __CUDA_ARCH__
-			// lockstep warp: the lanes search interleaved slices, the first match wins like in the sequential scan
-			const int len = count;
-			const int lane = threadIdx.x & 31;
-			int found = -1;
-			for (int base = 0; base < len and found < 0; base += 32)
-			{
-				const int i = base + lane;
-				const unsigned hit = __ballot_sync(0xFFFFFFFFu, i < len and list[i] == loc);
-				if (hit)
-					found = base + __ffs(hit) - 1;
-			}
-			if (found >= 0)
-			{
-				const uint16_t last = list[len - 1];
-				__syncwarp();
-				list[found] = last;
-				count = len - 1;
-			}
-			__syncwarp();
-#else
 			for (int i = 0; i < count; i++)
 				if (list[i] == loc)
 				{
@@ -79,7 +103,6 @@ namespace agb
 					count--;
 					return;
 				}
-#endif
 		}
 		AGB_HD inline void dyn_hist_add(DynState &d, int colour, int type, uint16_t loc)
 		{
@@ -89,6 +112,7 @@ namespace agb
 			d.hist_cells[(colour * kHistTypes + type) * d.v.pitch + count] = loc;
 			count++;
 		}
+#endif
 #ifdef __CUDA_ARCH__
 		// Device form of addMove / undoMove. All 32 lanes of the game's warp run the solver in lockstep on identical data; here they split the
 		// work: lane q (and q + 32) owns entry q = 4 * k + dir of the 40 neighbour cells (k-th offset of -5..-1, 1..5, like K2), so a lane only
