@@ -31,6 +31,7 @@ namespace agb
 	constexpr int kMaxStages = 8;
 	constexpr int kThreads = 320; // warp 0: weight producer, warp 1: MMA issuer, warps 2..9: epilogue
 	constexpr int kEpilogueThreads = 256;
+	constexpr int kTicketCounters = 32;
 
 	struct ConvDesc
 	{
@@ -66,6 +67,7 @@ namespace agb
 			const int *n_boards_dev; // if set, the batch size is read from device memory
 			const int *gather; // if set, board i of this launch lives in slot gather[i] of the feature / output arrays
 			int slot_base; // otherwise board i lives in slot slot_base + i
+			int *ticket; // zeroed before the launch: the CTA pairs draw their boards from it (see draw_ticket in the kernel)
 			long long *trace; // optional [n_layers][4] clock64 stamps of CTA 0's first board (AGB_NET_TRACE)
 	};
 
@@ -77,6 +79,8 @@ namespace agb
 			float *d_wd1 = nullptr, *d_bd1 = nullptr, *d_wd2 = nullptr, *d_bd2 = nullptr;
 			float *d_value_hidden = nullptr;
 			float *d_policy = nullptr, *d_value = nullptr, *d_q = nullptr; // staging for host entry point
+			int *d_tickets = nullptr; // [kTicketCounters]: launch i draws its boards from counter i % kTicketCounters (launches on different streams may overlap)
+			unsigned launch_counter = 0;
 			int dense_width = 0;
 			size_t smem_bytes = 0;
 			bool split = false; // one board per CTA pair (boards of more than 15 rows)
@@ -173,10 +177,32 @@ namespace agb
 			uint64_t *bars = reinterpret_cast<uint64_t*>(xchg + 8);
 			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *peer_full = bars + 18, *xbar = bars + 26, *chunk_ready = bars + 27;
 			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
+			uint64_t *ticket_ready = bars + 36; // [4]
+			int *tickets = reinterpret_cast<int*>(bars + 40); // [4]
 			// CTA pair: rank 0 (leader) issues the MMAs for both boards; each CTA loads half of every weight tile
 			const uint32_t rank = cluster_ctarank();
-			const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-			const int board_first = SPLIT ? pair : 2 * pair, board_step = SPLIT ? n_pairs : 2 * n_pairs;
+			// Boards are handed out dynamically, one unit (two boards; SPLIT: one) per draw from a global counter: a pair whose SMs become free late
+			// (the solver's blocks of another pipeline group may sit on them when the launch starts) simply takes fewer units instead of holding the
+			// whole launch up with a fixed share. The leader's producer lane draws, writes the ticket into a 4-slot ring in both CTAs and arrives
+			// on the slot's barrier; every other role of the pair reads iteration i's ticket from slot i % 4. No role can be two iterations ahead
+			// of another (the weight ring holds less than a layer, the MMA warp waits for the epilogue's image), so four slots never wrap.
+			const int n_units = SPLIT ? n_boards : (n_boards + 1) / 2;
+			const auto draw_ticket = [&](int it) -> int
+			{ // leader CTA, warp 0, lane 0
+				const int t = atomicAdd(prm.ticket, 1);
+				const int slot = it & 3;
+				tickets[slot] = t;
+				st_peer_u32(map_to_rank(smem_u32(&tickets[slot]), 1), static_cast<uint32_t>(t));
+				mbar_arrive(&ticket_ready[slot]);
+				mbar_arrive_remote(&ticket_ready[slot], 1);
+				return t;
+			};
+			const auto read_ticket = [&](int it) -> int
+			{
+				const int slot = it & 3;
+				mbar_wait_cluster(&ticket_ready[slot], (it >> 2) & 1);
+				return tickets[slot];
+			};
 
 			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 			const uint32_t img_chunk_bytes = prm.img_rows * 16;
@@ -191,6 +217,8 @@ namespace agb
 					mbar_init(&w_empty[s], 1);
 					mbar_init(&peer_full[s], 1);
 				}
+				for (int i = 0; i < 4; i++)
+					mbar_init(&ticket_ready[i], 1);
 				mbar_init(acc_full, 1);
 				mbar_init(xbar, 1);
 				for (int c = 0; c < 8; c++)
@@ -217,7 +245,7 @@ namespace agb
 				{
 					int stage = 0;
 					uint32_t phase = 0;
-					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
+					for (int it = 0; (rank == 0 ? draw_ticket(it) : read_ticket(it)) < n_units; it++)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -245,7 +273,12 @@ namespace agb
 					int stage = 0;
 					uint32_t phase = 0, ready_phase = 0;
 					const uint32_t idesc = idesc_bf16_f32(256, F); // M = 256: 128 positions of this CTA's board + 128 of the peer's
-					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
+					for (int it = 0;; it++)
+					{
+						const int ticket = read_ticket(it);
+						if (ticket >= n_units)
+							break;
+						const int b0 = SPLIT ? ticket : 2 * ticket;
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const ConvDesc &L = prm.layers[l];
@@ -320,12 +353,13 @@ namespace agb
 								mma_pair_commit(acc_full, 3);
 							__syncwarp();
 						}
+					}
 				}
 				else if (lane == 0)
 				{ // peer CTA: tell the leader when our half of each weight stage has landed
 					int stage = 0;
 					uint32_t phase = 0;
-					for (int b0 = board_first; b0 < n_boards; b0 += board_step)
+					for (int it = 0; read_ticket(it) < n_units; it++)
 						for (int l = 0; l < prm.n_layers; l++)
 						{
 							const int total_kc = prm.layers[l].n_taps * prm.layers[l].cin_chunks;
@@ -354,8 +388,12 @@ namespace agb
 				const int my_rows = SPLIT ? (rank == 0 ? rows0 : S - rows0) : S;
 				const int row_begin = (SPLIT and rank == 1) ? rows0 : 0;
 				const int halo_in = SPLIT ? 2 : 0; // rows of the neighbouring part that the 5x5 stem reads: taken from the features directly
-				for (int b0 = board_first; b0 < n_boards; b0 += board_step)
+				for (int it = 0;; it++)
 				{
+					const int ticket = read_ticket(it);
+					if (ticket >= n_units)
+						break;
+					const int b0 = SPLIT ? ticket : 2 * ticket;
 					const int bi = SPLIT ? b0 : b0 + rank; // this CTA's board in the launch
 					const bool live = bi < n_boards;
 					const int b = (live and prm.gather != nullptr) ? prm.gather[bi] : bi + prm.slot_base; // its slot in the feature / output arrays // an odd batch leaves the last peer without a board: it still runs every barrier
@@ -776,7 +814,7 @@ namespace agb
 		if (e->net == nullptr)
 			return;
 		NetWeights *n = e->net;
-		void *ptrs[] = { n->d_w_images, n->d_small, n->d_wd1, n->d_bd1, n->d_wd2, n->d_bd2, n->d_value_hidden, n->d_policy, n->d_value, n->d_q };
+		void *ptrs[] = { n->d_w_images, n->d_small, n->d_wd1, n->d_bd1, n->d_wd2, n->d_bd2, n->d_value_hidden, n->d_policy, n->d_value, n->d_q, n->d_tickets };
 		for (void *p : ptrs)
 			if (p)
 				cudaFree(p);
@@ -883,6 +921,7 @@ namespace agb
 		AGB_CUDA_CHECK(e, upload(&n->d_policy, nullptr, cap * cells * 4));
 		AGB_CUDA_CHECK(e, upload(&n->d_value, nullptr, cap * 3 * 4));
 		AGB_CUDA_CHECK(e, upload(&n->d_q, nullptr, cap * cells * 3 * 4));
+		AGB_CUDA_CHECK(e, upload(&n->d_tickets, nullptr, kTicketCounters * sizeof(int)));
 		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
 		p.w_images = n->d_w_images;
 		p.bias = n->d_small;
@@ -919,6 +958,8 @@ namespace agb
 		p.n_boards_dev = n_dev;
 		p.gather = gather_dev;
 		p.slot_base = slot_base;
+		p.ticket = n->d_tickets + (n->launch_counter++ % kTicketCounters);
+		AGB_CUDA_CHECK(e, cudaMemsetAsync(p.ticket, 0, sizeof(int), stream));
 		static long long *d_trace = nullptr;
 		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
 		if (trace and d_trace == nullptr)

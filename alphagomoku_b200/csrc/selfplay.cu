@@ -18,10 +18,12 @@
 #include "patterns_logic.cuh"
 #include "records.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 namespace agb
@@ -1811,7 +1813,9 @@ namespace agb
 		}
 		// groups: with green contexts the launches of several groups share the solver's SMs, so more groups hide each launch's tail (6: measured
 		// best of 2..8 at steady state); without them the solver runs in SM-filling blocks and more than 2 groups only get in each other's way
-		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : (pipelined ? (s->green ? 6 : 2) : 1);
+		// three groups once each still has a thousand games: a group's cycle is solver launch + network launch + tree kernels, and with two groups
+		// that chain, not the SMs, bounds the step as soon as both kernels are balanced (steady state: 2 groups 262-270 k, 3 groups 280 k evaluations/s)
+		s->groups = c.pipeline_groups > 0 ? c.pipeline_groups : (pipelined ? (s->green ? 6 : (c.games >= 3072 ? 3 : 2)) : 1);
 		s->solver_sms = 0;
 		if (s->green)
 		{
@@ -2432,8 +2436,54 @@ extern "C"
 				call_solver_ms += ms;
 			}
 		}
-		if (s->solver_sms > 0 and not s->green and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0)
-		{ // automatic partition: both kernels scale with their SMs, so split the SMs in proportion to the SM-time each needed in this
+		if (s->solver_sms > 0 and not s->green and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0 and groups >= 3)
+		{ // automatic partition with three or more groups: the solver launches of different groups queue behind each other on the solver's SMs (a
+		  // launch's tail runs next to the next group's games) and the network launches follow each other on the network stream, so either side
+		  // can be kept busy all the time. Measure how long each side had NOTHING queued or running during this call and move SMs from the idler
+		  // side to the busier one, half of what the difference suggests, in whole TPCs. Results do not depend on it.
+			const int sms = s->solver_sms + s->net_sms;
+			std::vector<std::pair<float, float>> solver_spans;
+			float first = 0.0f, last = 0.0f, net_busy = 0.0f;
+			bool ok = true;
+			for (int i = 0; i < n_steps * groups and ok; i++)
+			{
+				float t[4] = { 0, 0, 0, 0 };
+				for (int k = 0; k < 4 and ok; k++)
+					ok = cudaEventElapsedTime(&t[k], e->events[0], e->events[4 * i + k]) == cudaSuccess;
+				solver_spans.emplace_back(t[0], t[1]);
+				net_busy += t[3] - t[2];
+				first = (i == 0) ? t[0] : std::min(first, t[0]);
+				last = std::max(last, t[3]);
+			}
+			const float wall = last - first;
+			if (ok and wall > 0.0f)
+			{
+				std::sort(solver_spans.begin(), solver_spans.end());
+				float solver_busy = 0.0f, open_from = solver_spans[0].first, open_to = solver_spans[0].second;
+				for (const auto &span : solver_spans)
+				{
+					if (span.first > open_to)
+					{
+						solver_busy += open_to - open_from;
+						open_from = span.first;
+						open_to = span.second;
+					}
+					else
+						open_to = std::max(open_to, span.second);
+				}
+				solver_busy += open_to - open_from;
+				const double solver_idle = std::max(0.0, 1.0 - solver_busy / wall), net_idle = std::max(0.0, 1.0 - net_busy / wall);
+				const double delta = 0.5 * (net_idle * s->net_sms - solver_idle * s->solver_sms);
+				int next = (s->solver_sms + static_cast<int>(delta > 0 ? delta + 0.5 : delta - 0.5)) & ~1;
+				// more SMs than hold the games of all the other groups at once (28 warps per SM) cannot be filled
+				const int useful = std::max(8, static_cast<int>(0.77 * (groups - 1) * per_group / 28.0) & ~1);
+				next = std::max(8, std::min(next, std::min(sms / 2, useful)));
+				s->solver_sms = next;
+				s->net_sms = sms - next;
+			}
+		}
+		else if (s->solver_sms > 0 and not s->green and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0)
+		{ // automatic partition, two groups: both kernels scale with their SMs, so split the SMs in proportion to the SM-time each needed in this
 		  // call (K5 and K4 launches then take equally long); move three quarters of the way, in whole TPCs. Results do not depend on it.
 			const int sms = s->solver_sms + s->net_sms;
 			// Lean 15 % towards the network: measured on the steady-state workload the step is shortest when the solver's launches take about that

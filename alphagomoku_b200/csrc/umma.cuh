@@ -197,6 +197,10 @@ namespace agb
 		{
 			asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 		}
+		__device__ __forceinline__ void st_peer_u32(uint32_t cluster_addr, uint32_t v)
+		{
+			asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(cluster_addr), "r"(v) : "memory");
+		}
 		__device__ __forceinline__ void st_peer_f32(uint32_t cluster_addr, float v)
 		{
 			asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(cluster_addr), "f"(v) : "memory");

@@ -97,7 +97,8 @@ typedef struct AgbConfig
 	                                 AlphaBetaSearch.cpp:55) */
 	int32_t pipeline_groups; /* 1: all games advance together; 2..8: that many groups of games on their own streams, so that the solver and tree
 	                            kernels of some groups overlap another group's network kernel; 0 = automatic (with the alpha-beta solver on and at
-	                            least 1024 games: 6 when the SM partition is made of green contexts, else 2; otherwise 1). Per-game results do not
+	                            least 1024 games: 6 when the SM partition is made of green contexts, else 3 from 3072 games on and 2 below;
+	                            otherwise 1). Per-game results do not
 	                            depend on it */
 	int32_t final_selector; /* SelfplayConfig::final_selector.policy: AGB_FINAL_* (EdgeSelector::create, EdgeSelector.cpp:680-711) */
 	float final_exploration_constant; /* its exploration_constant (used by AGB_FINAL_LCB) */
