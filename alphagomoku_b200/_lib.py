@@ -60,6 +60,7 @@ SYMBOLS = {
     "agb_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "agb_forward_dev": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "agb_evaluate": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
+    "agb_evaluate_features": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "agb_seed_openings": (_I, [_VP, ctypes.c_uint32]),
     "agb_prepare_opening": (_I, [_VP, _I, _VP, _VP]),
     "agb_generate_openings": (_I, [_VP, _I, _VP, _VP]),

@@ -1020,7 +1020,26 @@ namespace agb
 {
 	int net_forward_dev(AgbEngine *e, const uint32_t *features_dev, int n_boards, float *policy_dev, float *value_dev, float *q_dev)
 	{
-		return net_forward_impl(e, features_dev, n_boards, nullptr, nullptr, policy_dev, value_dev, q_dev);
+		const int rc = net_forward_impl(e, features_dev, n_boards, nullptr, nullptr, policy_dev, value_dev, q_dev);
+		if (const char *dump = getenv("AGB_NET_DUMP"))
+		{ // diagnostics: every call's inputs and raw outputs appended to a file (n, features, policy, value)
+			const size_t cells = e->cells;
+			std::vector<uint32_t> f(n_boards * cells);
+			std::vector<float> pol(n_boards * cells), val(n_boards * 3);
+			cudaStreamSynchronize(e->stream);
+			cudaMemcpy(f.data(), features_dev, f.size() * 4, cudaMemcpyDeviceToHost);
+			cudaMemcpy(pol.data(), policy_dev, pol.size() * 4, cudaMemcpyDeviceToHost);
+			cudaMemcpy(val.data(), value_dev, val.size() * 4, cudaMemcpyDeviceToHost);
+			if (FILE *out = fopen(dump, "ab"))
+			{
+				fwrite(&n_boards, 4, 1, out);
+				fwrite(f.data(), 4, f.size(), out);
+				fwrite(pol.data(), 4, pol.size(), out);
+				fwrite(val.data(), 4, val.size(), out);
+				fclose(out);
+			}
+		}
+		return rc;
 	}
 	int net_forward_dev_gather(AgbEngine *e, const uint32_t *features_dev, const int *count_dev, const int *gather_dev, int max_boards, float *policy_dev,
 			float *value_dev, float *q_dev, int slot_base, cudaStream_t stream, int max_sms, cudaStream_t tail_stream, cudaEvent_t trunk_done)
@@ -1095,6 +1114,66 @@ extern "C"
 		if (symmetry_host != nullptr)
 		{ // unpack_from_network: inverse symmetry on policy and action values
 			float *tmp_policy = reinterpret_cast<float*>(e->d_features); // features are dead now: reuse as scratch
+			rc = agb::launch_symmetry_f32(e, net->d_policy, tmp_policy, e->d_io8b, n, 1, true);
+			if (rc != AGB_OK)
+				return rc;
+			policy = tmp_policy;
+			if (want_q)
+			{
+				rc = agb::launch_symmetry_f32(e, net->d_q, net->d_value_hidden, e->d_io8b, n, 3, true); // value_hidden [n][cells*4] is free again
+				if (rc != AGB_OK)
+					return rc;
+				q = net->d_value_hidden;
+			}
+		}
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(policy_host, policy, n * cells * 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(value_host, net->d_value, n * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+		if (want_q)
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(q_host, q, n * cells * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+		AGB_CUDA_CHECK(e, cudaStreamSynchronize(e->stream));
+		if (const char *dump = getenv("AGB_EVAL_DUMP"))
+		{ // diagnostics: what the caller gave and got (n, boards, sides to move, symmetries, policy, value)
+			if (FILE *out = fopen(dump, "ab"))
+			{
+				std::vector<int8_t> zeros(n, 0);
+				fwrite(&n, 4, 1, out);
+				fwrite(boards_host, 1, n * cells, out);
+				fwrite(sign_to_move_host, 1, n, out);
+				fwrite(symmetry_host != nullptr ? symmetry_host : zeros.data(), 1, n, out);
+				fwrite(policy_host, 4, n * cells, out);
+				fwrite(value_host, 4, n * 3, out);
+				fclose(out);
+			}
+		}
+		return AGB_OK;
+	}
+	int agb_evaluate_features(AgbEngine *e, const uint32_t *features_host, const int8_t *symmetry_host, int n, float *policy_host, float *value_host, float *q_host)
+	{ // NNEvaluator::pack_to_network's first branch (NNEvaluator.cpp:246-251): the caller's feature words go to the network as they are
+		const agb::DeviceGuard on_device(e);
+		if (n < 0 or n > e->store.capacity)
+			return e->fail(AGB_EINVAL, "n exceeds max_boards");
+		if (features_host == nullptr or policy_host == nullptr or value_host == nullptr)
+			return e->fail(AGB_EINVAL, "null pointer");
+		if (n == 0)
+			return AGB_OK;
+		agb::NetWeights *net = e->net;
+		if (net == nullptr or not net->loaded)
+			return e->fail(AGB_ESTATE, "no weights loaded");
+		const size_t cells = e->cells;
+		const bool want_q = (q_host != nullptr and e->cfg.q_head);
+		if (symmetry_host != nullptr)
+			for (int i = 0; i < n; i++)
+				if (symmetry_host[i] < 0 or symmetry_host[i] > 7)
+					return e->fail(AGB_EINVAL, "symmetry must be in 0..7");
+		AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_features2, features_host, n * cells * 4, cudaMemcpyHostToDevice, e->stream));
+		int rc = agb::net_forward_dev(e, e->d_features2, n, net->d_policy, net->d_value, net->d_q);
+		if (rc != AGB_OK)
+			return rc;
+		const float *policy = net->d_policy, *q = net->d_q;
+		if (symmetry_host != nullptr)
+		{ // unpack_from_network: inverse symmetry on policy and action values
+			AGB_CUDA_CHECK(e, cudaMemcpyAsync(e->d_io8b, symmetry_host, n, cudaMemcpyHostToDevice, e->stream));
+			float *tmp_policy = reinterpret_cast<float*>(e->d_features); // scratch
 			rc = agb::launch_symmetry_f32(e, net->d_policy, tmp_policy, e->d_io8b, n, 1, true);
 			if (rc != AGB_OK)
 				return rc;

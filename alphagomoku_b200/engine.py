@@ -204,6 +204,17 @@ class Engine:
         self._check(self._lib.agb_evaluate(self._h, _ptr(boards), _ptr(stm), _ptr(sym), n, _ptr(policy), _ptr(value), _ptr(q)))
         return policy, value, q
 
+    def evaluate_features(self, features, symmetry=None, want_q=False):
+        """NNEvaluator::evaluateGraph for tasks that carry their (already augmented) feature words: forward (K4) -> inverse symmetry."""
+        features = np.ascontiguousarray(features, np.uint32).reshape(-1, self.cells)
+        sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8).reshape(-1)
+        n = features.shape[0]
+        policy = np.zeros((n, self.cells), np.float32)
+        value = np.zeros((n, 3), np.float32)
+        q = np.zeros((n, self.cells, 3), np.float32) if want_q else None
+        self._check(self._lib.agb_evaluate_features(self._h, _ptr(features), _ptr(sym), n, _ptr(policy), _ptr(value), _ptr(q)))
+        return policy, value, q
+
     # ---- openings (OpeningGenerator) ------------------------------------------------------------------------------------
     def seed_openings(self, seed):
         self._check(self._lib.agb_seed_openings(self._h, seed))

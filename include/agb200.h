@@ -177,6 +177,12 @@ int agb_forward_dev(AgbEngine *engine, const uint32_t *features_dev, int n, floa
  * like NNEvaluator::pack_to_network / unpack_from_network (NNEvaluator.cpp:244-286). */
 int agb_evaluate(AgbEngine *engine, const int8_t *boards_host, const int8_t *sign_to_move_host, const int8_t *symmetry_host, int n,
 		float *policy_host, float *value_host, float *q_host);
+/* The same for positions whose feature words the caller already holds -- NNEvaluator::pack_to_network's first branch (NNEvaluator.cpp:246-251:
+ * a task the solver has processed carries its NNInputFeatures, which the reference augments IN PLACE and packs): features_host[n][cells] go to
+ * the network as they are (already augmented by the caller), symmetry[n] (or NULL) is only inverted on policy / q afterwards. A task that sits
+ * in the queue twice is augmented twice by the reference; taking its features from the caller reproduces that. */
+int agb_evaluate_features(AgbEngine *engine, const uint32_t *features_host, const int8_t *symmetry_host, int n, float *policy_host, float *value_host,
+		float *q_host);
 
 /* ---- opening generation (OpeningGenerator, src/selfplay/OpeningGenerator.cpp:21-78; prepareOpening, src/utils/misc.cpp:142-170) -----
  * The generator's std::mt19937 starts from the low 32 bits of AgbConfig::seed; agb_seed_openings restarts it. */

@@ -4,7 +4,7 @@
 // ag::NNEvaluator (include/alphagomoku/search/monte_carlo/NNEvaluator.hpp:42-83). A drop-in therefore has to BE that class: this file
 // defines every member function the header declares (and NNEvaluatorStats), with the same queue semantics, random draws, statistics and
 // exceptions, but the evaluation itself -- pack_to_network -> AGNetwork::forward -> unpack_from_network -- is one call of the B200 engine's C ABI
-// (agb_evaluate: K1 + K3 + augment + K4 + inverse symmetry on the device). A maintainer compiles this file INSTEAD of NNEvaluator.cpp
+// (agb_evaluate_features: K4 + inverse symmetry for tasks that carry their feature words, agb_evaluate: K1 + K3 + augment + K4 + inverse symmetry for the others). A maintainer compiles this file INSTEAD of NNEvaluator.cpp
 // and links libagb200.so; nothing else in the reference changes. tests/host builds exactly that and runs the
 // reference's own GeneratorThread::run loop on it.
 //
@@ -49,8 +49,23 @@ namespace agb200
 				AgbEngine *handle = nullptr;
 				int cells = 0;
 				bool q_head = false;
-				std::vector<int8_t> boards, sign_to_move, symmetry;
+				// a batch in two parts, like NNEvaluator::pack_to_network's two branches: tasks the solver has processed carry their feature words
+				// (results [0, n_features)), the others are sent as boards and encoded on the device (results [n_features, n))
+				std::vector<uint32_t> features;
+				std::vector<int8_t> boards, sign_to_move, symmetry_features, symmetry_boards;
+				std::vector<int> result_of; // batch index -> row of policy / value / q
+				int n_features = 0, n_boards = 0;
 				std::vector<float> policy, value, q;
+				int evaluate()
+				{ // pack_to_network -> forward -> unpack_from_network's device half, for both parts
+					int rc = AGB_OK;
+					if (n_features > 0)
+						rc = agb_evaluate_features(handle, features.data(), symmetry_features.data(), n_features, policy.data(), value.data(), q_head ? q.data() : nullptr);
+					if (rc == AGB_OK and n_boards > 0)
+						rc = agb_evaluate(handle, boards.data(), sign_to_move.data(), symmetry_boards.data(), n_boards, policy.data() + static_cast<size_t>(n_features) * cells,
+								value.data() + static_cast<size_t>(n_features) * 3, q_head ? q.data() + static_cast<size_t>(n_features) * cells * 3 : nullptr);
+					return rc;
+				}
 				std::future<int> pending;
 				double time_per_sample = 1.0e-4; // PerfEstimator's role: seconds per position, refreshed after every batch
 				double launch_time = 0.0;
@@ -174,9 +189,12 @@ namespace ag
 		engine->cells = net.game.rows * net.game.cols;
 		engine->q_head = net.q_head;
 		const size_t n = config.batch_size;
+		engine->features.resize(n * engine->cells);
 		engine->boards.resize(n * engine->cells);
 		engine->sign_to_move.resize(n);
-		engine->symmetry.resize(n);
+		engine->symmetry_features.resize(n);
+		engine->symmetry_boards.resize(n);
+		engine->result_of.resize(n);
 		engine->policy.resize(n * engine->cells);
 		engine->value.resize(n * 3);
 		engine->q.resize(n * engine->cells * 3);
@@ -213,8 +231,7 @@ namespace ag
 			pack_to_network();
 			stats.compute.startTimer();
 			const double t0 = getTime();
-			const int rc = agb_evaluate(engine->handle, engine->boards.data(), engine->sign_to_move.data(), engine->symmetry.data(), batch_size,
-					engine->policy.data(), engine->value.data(), engine->q_head ? engine->q.data() : nullptr);
+			const int rc = engine->evaluate();
 			stats.compute.stopTimer();
 			if (rc != AGB_OK)
 				throw std::runtime_error(std::string("NNEvaluator::evaluateGraph() : ") + agb_last_error(engine->handle));
@@ -240,10 +257,9 @@ namespace ag
 			stats.compute.startTimer();
 			engine->launch_time = getTime();
 			// the batch is on its way while the caller selects the next one (GeneratorManager.cpp:127-138); results are read in Join
-			engine->pending = std::async(std::launch::async, [engine, batch_size]()
+			engine->pending = std::async(std::launch::async, [engine]()
 			{
-				return agb_evaluate(engine->handle, engine->boards.data(), engine->sign_to_move.data(), engine->symmetry.data(), batch_size,
-						engine->policy.data(), engine->value.data(), engine->q_head ? engine->q.data() : nullptr);
+				return engine->evaluate();
 			});
 		}
 		return getTime() + batch_size * engine->time_per_sample; // estimated end time, like PerfEstimator::getEstimatedEndTime
@@ -278,20 +294,39 @@ namespace ag
 		throw std::logic_error("NNEvaluator::get_network() : the B200 evaluator holds no host-side network");
 	}
 	void NNEvaluator::pack_to_network()
-	{ // boards, sides to move and symmetries of the batch; pattern calculation, feature encoding and the augmentation happen on the device
+	{ // NNEvaluator.cpp:244-262. A task the solver has processed carries its feature words: the reference augments them IN PLACE and packs them,
+	  // so a task that sits in the queue twice goes to the network augmented twice -- taking the words from the task reproduces that. The other
+	  // tasks are sent as boards with their symmetry; pattern calculation, encoding and augmentation then happen on the device.
 		TimerGuard timer(stats.pack);
 		agb200::Engine *engine = agb200::find(this);
-		for (size_t i = 0; i < in_progress_queue.size(); i++)
+		const int n = static_cast<int>(in_progress_queue.size());
+		engine->n_features = 0;
+		for (int i = 0; i < n; i++)
+			engine->n_features += in_progress_queue[i].ptr->wasProcessedBySolver() ? 1 : 0;
+		engine->n_boards = n - engine->n_features;
+		int next_features = 0, next_boards = 0;
+		for (int i = 0; i < n; i++)
 		{
 			const TaskData td = in_progress_queue.at(i);
-			const matrix<Sign> &board = td.ptr->getBoard();
-			int8_t *dst = engine->boards.data() + i * engine->cells;
-			for (int j = 0; j < engine->cells; j++)
-				dst[j] = static_cast<int8_t>(board[j]);
-			engine->sign_to_move[i] = static_cast<int8_t>(td.ptr->getSignToMove());
-			engine->symmetry[i] = static_cast<int8_t>(td.symmetry);
 			if (td.ptr->wasProcessedBySolver())
-				td.ptr->getFeatures().augment(td.symmetry); // the reference leaves the task's features augmented (NNEvaluator.cpp:252-256)
+			{
+				const int k = next_features++;
+				td.ptr->getFeatures().augment(td.symmetry);
+				std::memcpy(engine->features.data() + static_cast<size_t>(k) * engine->cells, td.ptr->getFeatures().data(), engine->cells * sizeof(uint32_t));
+				engine->symmetry_features[k] = static_cast<int8_t>(td.symmetry);
+				engine->result_of[i] = k;
+			}
+			else
+			{
+				const int k = next_boards++;
+				const matrix<Sign> &board = td.ptr->getBoard();
+				int8_t *dst = engine->boards.data() + static_cast<size_t>(k) * engine->cells;
+				for (int j = 0; j < engine->cells; j++)
+					dst[j] = static_cast<int8_t>(board[j]);
+				engine->sign_to_move[k] = static_cast<int8_t>(td.ptr->getSignToMove());
+				engine->symmetry_boards[k] = static_cast<int8_t>(td.symmetry);
+				engine->result_of[i] = engine->n_features + k;
+			}
 		}
 	}
 	void NNEvaluator::unpack_from_network()
@@ -301,14 +336,15 @@ namespace ag
 		for (size_t i = 0; i < in_progress_queue.size(); i++)
 		{
 			const TaskData td = in_progress_queue.at(i);
-			std::memcpy(td.ptr->getPolicy().data(), engine->policy.data() + i * engine->cells, engine->cells * sizeof(float));
+			const size_t row = engine->result_of[i];
+			std::memcpy(td.ptr->getPolicy().data(), engine->policy.data() + row * engine->cells, engine->cells * sizeof(float));
 			matrix<Value> &action_values = td.ptr->getActionValues();
 			for (int j = 0; j < engine->cells; j++)
 			{
-				const float *src = engine->q.data() + (i * engine->cells + j) * 3;
+				const float *src = engine->q.data() + (row * engine->cells + j) * 3;
 				action_values[j] = engine->q_head ? Value(src[0], src[1]) : Value(0.0f, 0.0f); // a "pv" network has no 'q' output
 			}
-			td.ptr->setValue(Value(engine->value[3 * i], engine->value[3 * i + 1]));
+			td.ptr->setValue(Value(engine->value[3 * row], engine->value[3 * row + 1]));
 			if (td.ptr->getScore().isUnproven())
 				td.ptr->setMovesLeft(0.0f); // ResnetPV / PVQ have no moves-left head
 			td.ptr->markAsProcessedByNetwork();

@@ -125,3 +125,50 @@ OBSERVED_BOUNDS = {
     (20, 128, 6.0): {"policy_max_abs": 4.7e-2, "kl_max": 3.7e-3, "top1_agreement": 0.94, "top5_agreement": 0.99, "value_max_abs": 5e-4},
     (10, 64, 6.0): {"policy_max_abs": 1.4e-2, "kl_max": 9e-4, "top1_agreement": 0.92, "top5_agreement": 0.99, "value_max_abs": 1e-2},
 }
+
+
+def test_outputs_do_not_depend_on_the_batch():
+    """K4 hands boards to its CTA pairs dynamically and overlaps consecutive layers; a board's outputs must still be the same bits whatever
+    its place in the batch, the batch size (1, odd, more boards than CTAs) and the entry point. The reference-side drop-in relies on it:
+    the reference's evaluator and the device evaluate the same positions in different batches (tests/test_host_gpu.py)."""
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob
+    size, n = 15, 400
+    eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD, size, size), max_boards=n, blocks=4, filters=64, q_head=True)
+    eng.load_weights(netblob.pack(netblob.random_tensors(size, size, 4, 64, True, seed=11), size, size, 4, 64, True))
+    rng = np.random.default_rng(3)
+    boards = random_boards(rng, size, n)
+    stm = rng.integers(1, 3, n).astype(np.int8)
+    feats = eng.set_boards(boards, stm)
+    base = eng.forward(feats, want_q=True)
+    for m in [1, 2, 3, 7, 8, 9, 33, 64, 147, 148, 149, 297, 400]:
+        idx = rng.permutation(n)[:m]
+        out = eng.forward(np.ascontiguousarray(feats[idx]), want_q=True)
+        ev = eng.evaluate(boards[idx], stm[idx], np.zeros(m, np.int8), want_q=True)
+        for a, b, c in zip(base, out, ev):
+            assert (a[idx].view(np.uint32) == b.view(np.uint32)).all(), m
+            assert (a[idx].view(np.uint32) == c.view(np.uint32)).all(), m
+    eng.close()
+
+
+def test_evaluate_features_is_evaluate_on_augmented_features():
+    """agb_evaluate_features (NNEvaluator::pack_to_network's branch for tasks that carry their feature words, NNEvaluator.cpp:246-251): the
+    caller's augmented words in, inverse symmetry on the way out == agb_evaluate on the boards with the same symmetries, bit for bit."""
+    import alphagomoku_b200 as agb
+    from alphagomoku_b200 import netblob
+    size, n = 15, 96
+    eng = agb.Engine(agb.GameConfig(agb.GameRules.STANDARD, size, size), max_boards=n, blocks=2, filters=64, q_head=True)
+    eng.load_weights(netblob.pack(netblob.random_tensors(size, size, 2, 64, True, seed=5), size, size, 2, 64, True))
+    rng = np.random.default_rng(9)
+    boards = random_boards(rng, size, n)
+    stm = rng.integers(1, 3, n).astype(np.int8)
+    sym = rng.integers(0, 8, n).astype(np.int8)
+    expect = eng.evaluate(boards, stm, sym, want_q=True)
+    got = eng.evaluate_features(eng.augment(eng.set_boards(boards, stm), sym), sym, want_q=True)
+    for a, b in zip(expect, got):
+        assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    raw = eng.forward(eng.set_boards(boards, stm), want_q=True)
+    same = eng.evaluate_features(eng.set_boards(boards, stm), None, want_q=True)
+    for a, b in zip(raw, same):
+        assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    eng.close()
