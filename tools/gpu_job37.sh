@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_n2_final.json 2> gpurun_out/r02_bench_n2_final.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02_bench_n2_final.json').read().strip().splitlines()[-1])
+print('N=2 value',round(d['value']),'ms/step',round(d['ms_per_step'],1),'e2e',round(d['e2e']['value']),d['records'],d['sharding']['per_rank_ms_per_step'])
+PY
