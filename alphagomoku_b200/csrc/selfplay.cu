@@ -2431,10 +2431,45 @@ extern "C"
 				call_nn_ms += ms;
 			}
 			if (e->cfg.solver_max_positions > 0 and cudaEventElapsedTime(&ms, e->events[4 * i], e->events[4 * i + 1]) == cudaSuccess)
-			{
-				e->solver_kernel_ns += static_cast<uint64_t>(ms * 1.0e6);
 				call_solver_ms += ms;
+		}
+		// K5: with three or more groups the solver launches of different groups queue behind each other on the solver's SMs, so their event
+		// intervals overlap; what is reported (and balanced) is the time during which at least one of them was queued or running
+		float call_first = 0.0f, call_last = 0.0f, call_solver_busy = 0.0f;
+		bool spans_ok = false;
+		if (e->cfg.solver_max_positions > 0)
+		{
+			std::vector<std::pair<float, float>> solver_spans;
+			spans_ok = true;
+			for (int i = 0; i < n_steps * groups and spans_ok; i++)
+			{
+				float t[4] = { 0, 0, 0, 0 };
+				for (int k = 0; k < 4 and spans_ok; k++)
+					spans_ok = cudaEventElapsedTime(&t[k], e->events[0], e->events[4 * i + k]) == cudaSuccess;
+				solver_spans.emplace_back(t[0], t[1]);
+				call_first = (i == 0) ? t[0] : std::min(call_first, t[0]);
+				call_last = std::max(call_last, t[3]);
 			}
+			if (spans_ok and not solver_spans.empty())
+			{
+				std::sort(solver_spans.begin(), solver_spans.end());
+				float open_from = solver_spans[0].first, open_to = solver_spans[0].second;
+				for (const auto &span : solver_spans)
+				{
+					if (span.first > open_to)
+					{
+						call_solver_busy += open_to - open_from;
+						open_from = span.first;
+						open_to = span.second;
+					}
+					else
+						open_to = std::max(open_to, span.second);
+				}
+				call_solver_busy += open_to - open_from;
+				e->solver_kernel_ns += static_cast<uint64_t>(call_solver_busy * 1.0e6);
+			}
+			else
+				e->solver_kernel_ns += static_cast<uint64_t>(call_solver_ms * 1.0e6);
 		}
 		if (s->solver_sms > 0 and not s->green and e->cfg.solver_sms == 0 and n_steps >= 2 and call_nn_ms > 0.0 and call_solver_ms > 0.0 and groups >= 3)
 		{ // automatic partition with three or more groups: the solver launches of different groups queue behind each other on the solver's SMs (a
@@ -2442,36 +2477,9 @@ extern "C"
 		  // can be kept busy all the time. Measure how long each side had NOTHING queued or running during this call and move SMs from the idler
 		  // side to the busier one, half of what the difference suggests, in whole TPCs. Results do not depend on it.
 			const int sms = s->solver_sms + s->net_sms;
-			std::vector<std::pair<float, float>> solver_spans;
-			float first = 0.0f, last = 0.0f, net_busy = 0.0f;
-			bool ok = true;
-			for (int i = 0; i < n_steps * groups and ok; i++)
+			const float wall = call_last - call_first, solver_busy = call_solver_busy, net_busy = static_cast<float>(call_nn_ms);
+			if (spans_ok and wall > 0.0f)
 			{
-				float t[4] = { 0, 0, 0, 0 };
-				for (int k = 0; k < 4 and ok; k++)
-					ok = cudaEventElapsedTime(&t[k], e->events[0], e->events[4 * i + k]) == cudaSuccess;
-				solver_spans.emplace_back(t[0], t[1]);
-				net_busy += t[3] - t[2];
-				first = (i == 0) ? t[0] : std::min(first, t[0]);
-				last = std::max(last, t[3]);
-			}
-			const float wall = last - first;
-			if (ok and wall > 0.0f)
-			{
-				std::sort(solver_spans.begin(), solver_spans.end());
-				float solver_busy = 0.0f, open_from = solver_spans[0].first, open_to = solver_spans[0].second;
-				for (const auto &span : solver_spans)
-				{
-					if (span.first > open_to)
-					{
-						solver_busy += open_to - open_from;
-						open_from = span.first;
-						open_to = span.second;
-					}
-					else
-						open_to = std::max(open_to, span.second);
-				}
-				solver_busy += open_to - open_from;
 				const double solver_idle = std::max(0.0, 1.0 - solver_busy / wall), net_idle = std::max(0.0, 1.0 - net_busy / wall);
 				const double delta = 0.5 * (net_idle * s->net_sms - solver_idle * s->solver_sms);
 				int next = (s->solver_sms + static_cast<int>(delta > 0 ? delta + 0.5 : delta - 0.5)) & ~1;

@@ -273,7 +273,8 @@ typedef struct AgbStats
 	uint64_t nn_kernel_ns; /* total CUDA-event time of the network kernel launches issued by agb_step */
 	uint64_t nn_kernel_launches;
 	uint64_t nn_positions; /* positions those launches evaluated */
-	uint64_t solver_kernel_ns; /* total CUDA-event time of the solver kernel (K5) launches issued by agb_step */
+	uint64_t solver_kernel_ns; /* device time during which at least one solver kernel (K5) launch issued by agb_step was queued or running (CUDA events;
+	                              with one or two pipeline groups that is the sum of the launches, with more their intervals overlap) */
 	uint64_t solver_sms; /* SMs the solver kernel currently runs on (AgbConfig::solver_sms; 0 = no partition). In automatic mode the engine
 	                        re-balances it after every agb_step call from the measured K5 and K4 launch times */
 	uint64_t pipeline_groups; /* groups of games the engine advances on their own streams (AgbConfig::pipeline_groups after defaults) */
