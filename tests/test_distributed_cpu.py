@@ -28,7 +28,10 @@ def _worker(rank, world, port, out):
     records = bytes([rank + 1] * (3 + 4 * rank))
     gathered = sharding.gather_records(records)
     total, peak = sharding.reduce_counters([float(last - first), float(rank)])
-    out.put((rank, first, last, float(got.sum()), got.size, [len(g) for g in gathered], [g[:1] for g in gathered], total.tolist(), peak.tolist()))
+    # a pop interval in which only one rank finished games (the bench pops every 10 steps: most intervals look like this at small sizes)
+    sparse = sharding.gather_records(b"" if rank == 0 else b"\x07\x08")
+    out.put((rank, first, last, float(got.sum()), got.size, [len(g) for g in gathered], [g[:1] for g in gathered], total.tolist(), peak.tolist(),
+             [bytes(g) for g in sparse]))
     dist.destroy_process_group()
 
 
@@ -51,6 +54,7 @@ def test_two_rank_sharding_broadcast_gather():
         assert r[4] == expected.size and abs(r[3] - float(expected.sum())) < 1e-3  # identical weights on every rank
         assert r[5] == [3, 7] and r[6] == [b"\x01", b"\x02"]  # ragged records gathered in rank order
         assert r[7] == [10.0, 1.0] and r[8] == [5.0, 1.0]
+        assert r[9] == [b"", b"\x07\x08"]
 
 
 def test_game_range_is_a_partition():
