@@ -32,6 +32,9 @@ namespace agb
 	constexpr int kThreads = 320; // warp 0: weight producer, warp 1: MMA issuer, warps 2..9: epilogue
 	constexpr int kEpilogueThreads = 256;
 	constexpr int kTicketCounters = 32;
+#ifndef AGB_NET_SPLIT_SLICES
+#define AGB_NET_SPLIT_SLICES 4 // boards split over the CTA pair: 16-channel slices per hand-over (measured at 20x20: 1: 21.6, 2: 20.2, 4: see profiles, 8: 21.7 ms per 4096)
+#endif
 
 	struct ConvDesc
 	{
@@ -546,8 +549,12 @@ namespace agb
 							}
 							if (cb == 0 and prm.trace and bi == 0 and et == 0)
 								t_st = clock64();
-							if (hand_over)
-							{ // hand this slice of the image (and the drained accumulator columns) to the MMA warp
+							// SPLIT: publishing also covers the boundary row written into the peer's image, which needs the full proxy fence and a cluster-scope
+							// release (1.5 k cycles against 0.1 k for the local ones): two slices per hand-over there, so that the epilogue stays shorter
+							// than the next layer's MMAs
+							constexpr int kSlicesPerHandOver = SPLIT ? AGB_NET_SPLIT_SLICES : 1;
+							if (hand_over and (cb + 1) % kSlicesPerHandOver == 0)
+							{ // hand these slices of the image (and the drained accumulator columns) to the MMA warp
 								tc_fence_before();
 								if constexpr (SPLIT)
 									fence_proxy_async_all(); // covers the rows written into the peer's image
@@ -558,15 +565,19 @@ namespace agb
 									t_fence = clock64();
 								if (lane == 0)
 								{
-									if (rank == 0)
+#pragma unroll
+									for (int c = cb + 1 - kSlicesPerHandOver; c <= cb; c++)
 									{
-										if constexpr (SPLIT)
-											mbar_arrive_cluster(&chunk_ready[cb]);
+										if (rank == 0)
+										{
+											if constexpr (SPLIT)
+												mbar_arrive_cluster(&chunk_ready[c]);
+											else
+												mbar_arrive(&chunk_ready[c]);
+										}
 										else
-											mbar_arrive(&chunk_ready[cb]);
+											mbar_arrive_remote(&chunk_ready[c], 0);
 									}
-									else
-										mbar_arrive_remote(&chunk_ready[cb], 0);
 								}
 								if (cb == 0 and prm.trace and bi == 0 and et == 0)
 								{ // AGB_NET_TRACE: where the hand-over of the first slice spends its time (relative to the epilogue's start)
