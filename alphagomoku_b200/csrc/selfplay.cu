@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -2482,7 +2483,7 @@ extern "C"
 			{
 				const double solver_idle = std::max(0.0, 1.0 - solver_busy / wall), net_idle = std::max(0.0, 1.0 - net_busy / wall);
 				const double delta = 0.5 * (net_idle * s->net_sms - solver_idle * s->solver_sms);
-				int next = (s->solver_sms + static_cast<int>(delta > 0 ? delta + 0.5 : delta - 0.5)) & ~1;
+				int next = s->solver_sms + 2 * static_cast<int>(std::lround(delta / 2.0)); // whole TPCs, rounded to the nearest (not down)
 				// more SMs than hold the games of all the other groups at once (28 warps per SM) cannot be filled
 				const int useful = std::max(8, static_cast<int>(0.77 * (groups - 1) * per_group / 28.0) & ~1);
 				next = std::max(8, std::min(next, std::min(sms / 2, useful)));
