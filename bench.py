@@ -258,7 +258,7 @@ def main():
     ap.add_argument("--solver", type=int, default=SOLVER_POSITIONS, help="TSSConfig::max_positions of the device solver (0 = off)")
     ap.add_argument("--workload", default="freestyle15", choices=sorted(WORKLOADS), help="freestyle15 = the configuration BASELINE.json's metric names (the headline)")
     ap.add_argument("--start", default="snapshot", choices=["snapshot", "openings"], help="snapshot = steady state (headline); openings = early game only")
-    ap.add_argument("--settle", type=int, default=60, help="untimed steps after the reset to the snapshot (trees refill in 50 steps at 8 of 400 simulations per step)")
+    ap.add_argument("--settle", type=int, default=100, help="untimed steps after the reset to the snapshot (trees refill in 50 steps at 8 of 400 simulations per step; the automatic SM split needs about ten calls of 10 steps to settle)")
     ap.add_argument("--pop-every", type=int, default=10, help="steps between agb_pop_finished + record all-gather + finished-counter all-reduce in the timed region")
     ap.add_argument("--shard", type=int, default=0, help="play the games rank SHARD of a larger job would play (openings, game ids); for variance checks")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
