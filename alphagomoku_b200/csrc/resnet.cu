@@ -476,7 +476,7 @@ namespace agb
 						const uint32_t taddr = tmem_base + ((quadrant * 32u) << 16) + (l & 1) * 2 * F + tile * F;
 						uint32_t v[2][16];
 						tmem_ld16(taddr, v[0]);
-#pragma unroll
+#pragma unroll 2
 						for (int cb = 0; cb < F / 16; cb++)
 						{
 							const int c0 = cb * 16;
