@@ -464,9 +464,8 @@ namespace agb
 						mbar_wait(acc_full, acc_phase & 1); // try_wait suspends the warp in hardware: no polling load next to the MMA-issuing lane
 						acc_phase++;
 						tc_fence_after();
-						const long long t_epilogue = (prm.trace and bi == 0 and et == 0) ? clock64() : 0;
 						if (prm.trace and bi == 0 and et == 0)
-							prm.trace[6 * l + 2] = t_epilogue;
+							prm.trace[6 * l + 2] = clock64();
 						if (L.mode == MODE_STEM)
 						{ // the stem image is dead now: give the h buffer its zero halo back
 							for (uint32_t i = et; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kEpilogueThreads)
@@ -483,93 +482,20 @@ namespace agb
 						const uint32_t taddr = tmem_base + ((quadrant * 32u) << 16) + (l & 1) * 2 * F + tile * F;
 						uint32_t v[2][16];
 						tmem_ld16(taddr, v[0]);
-#pragma unroll 2
-						for (int cb = 0; cb < F / 16; cb++)
-						{
-							const int c0 = cb * 16;
-							uint4 res[2];
-							if (L.mode == MODE_CONV2)
-							{ // residual operand: x is updated in place
-								res[0] = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8) * img_chunk_bytes + out_idx * 16);
-								res[1] = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8 + 1) * img_chunk_bytes + out_idx * 16);
-							}
-							tmem_ld_wait();
-							long long t_ld = 0, t_st = 0, t_fence = 0;
-							if (cb == 0 and prm.trace and bi == 0 and et == 0)
-								t_ld = clock64();
-							if (cb + 1 < F / 16)
-								tmem_ld16(taddr + c0 + 16, v[(cb + 1) & 1]);
-							float a[16];
-#pragma unroll
-							for (int j = 0; j < 16; j += 4)
-							{
-								const float4 bj = *reinterpret_cast<const float4*>(sbias + c0 + j);
-								a[j] = __uint_as_float(v[cb & 1][j]) + bj.x;
-								a[j + 1] = __uint_as_float(v[cb & 1][j + 1]) + bj.y;
-								a[j + 2] = __uint_as_float(v[cb & 1][j + 2]) + bj.z;
-								a[j + 3] = __uint_as_float(v[cb & 1][j + 3]) + bj.w;
-							}
-							if (L.mode == MODE_CONV2)
-							{
-#pragma unroll
-								for (int h8 = 0; h8 < 2; h8++)
-								{
-									const uint4 r = res[h8];
-									float lo, hi;
-									unpack_bf16(r.x, lo, hi); a[8 * h8 + 0] += lo; a[8 * h8 + 1] += hi;
-									unpack_bf16(r.y, lo, hi); a[8 * h8 + 2] += lo; a[8 * h8 + 3] += hi;
-									unpack_bf16(r.z, lo, hi); a[8 * h8 + 4] += lo; a[8 * h8 + 5] += hi;
-									unpack_bf16(r.w, lo, hi); a[8 * h8 + 6] += lo; a[8 * h8 + 7] += hi;
-								}
-							}
-							if (L.mode == MODE_QHEAD)
-							{
-#pragma unroll
-								for (int j = 0; j < 16; j++)
-								{
-									const float t = tanh_fast(a[j]);
-									head[0] += t * __ldg(prm.q_w1 + c0 + j);
-									head[1] += t * __ldg(prm.q_w1 + F + c0 + j);
-									head[2] += t * __ldg(prm.q_w1 + 2 * F + c0 + j);
-								}
-							}
-							else if (L.mode == MODE_POLICY)
-							{
-#pragma unroll
-								for (int j = 0; j < 16; j++)
-									head[0] += fmaxf(a[j], 0.0f) * __ldg(prm.policy_w1 + c0 + j);
-							}
-							else if (valid)
-							{
-#pragma unroll
-								for (int h8 = 0; h8 < 2; h8++)
-								{
-									uint4 o;
-									o.x = pack_bf16_relu(a[8 * h8 + 0], a[8 * h8 + 1]);
-									o.y = pack_bf16_relu(a[8 * h8 + 2], a[8 * h8 + 3]);
-									o.z = pack_bf16_relu(a[8 * h8 + 4], a[8 * h8 + 5]);
-									o.w = pack_bf16_relu(a[8 * h8 + 6], a[8 * h8 + 7]);
-									*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
-									if (send)
-										st_peer_v4(peer_img + (c0 / 8 + h8) * img_chunk_bytes + peer_idx * 16, o);
-								}
-							}
-							if (cb == 0 and prm.trace and bi == 0 and et == 0)
-								t_st = clock64();
-							// SPLIT: publishing also covers the boundary row written into the peer's image, which needs the full proxy fence and a cluster-scope
-							// release (1.5 k cycles against 0.1 k for the local ones): two slices per hand-over there, so that the epilogue stays shorter
-							// than the next layer's MMAs
-							constexpr int kSlicesPerHandOver = SPLIT ? AGB_NET_SPLIT_SLICES : 1;
+						// SPLIT: publishing also covers the boundary row written into the peer's image, which needs the full proxy fence and a cluster-scope
+						// release (1.5 k cycles against 0.1 k for the local ones): several slices per hand-over there, so that the epilogue stays shorter
+						// than the next layer's MMAs
+						constexpr int kSlicesPerHandOver = SPLIT ? AGB_NET_SPLIT_SLICES : 1;
+						const auto publish = [&](int cb)
+						{ // hand these slices of the image (and the drained accumulator columns) to the MMA warp
 							if (hand_over and (cb + 1) % kSlicesPerHandOver == 0)
-							{ // hand these slices of the image (and the drained accumulator columns) to the MMA warp
+							{
 								tc_fence_before();
 								if constexpr (SPLIT)
 									fence_proxy_async_all(); // covers the rows written into the peer's image
 								else
 									fence_proxy_async();
 								__syncwarp(); // the lane that arrives publishes the whole warp's writes
-								if (cb == 0 and prm.trace and bi == 0 and et == 0)
-									t_fence = clock64();
 								if (lane == 0)
 								{
 #pragma unroll
@@ -586,12 +512,94 @@ namespace agb
 											mbar_arrive_remote(&chunk_ready[c], 0);
 									}
 								}
-								if (cb == 0 and prm.trace and bi == 0 and et == 0)
-								{ // AGB_NET_TRACE: where the hand-over of the first slice spends its time (relative to the epilogue's start)
-									const long long t0 = t_epilogue;
-									prm.trace[6 * l + 4] = ((t_ld - t0) << 32) | (t_st - t0);
-									prm.trace[6 * l + 5] = ((t_fence - t0) << 32) | (clock64() - t0);
+							}
+						};
+						// Two loops, each unrolled by two only: the 40 trunk layers run the first, whose body is what every epilogue warp fetches all the
+						// time -- the kernel's code size is felt by K4 itself and, through the L2, by the solver beside it (fully unrolled with the head
+						// code inside: 286 k evaluations/s in the step, like this: see profiles)
+						if (L.mode != MODE_POLICY and L.mode != MODE_QHEAD)
+						{
+#pragma unroll 2
+							for (int cb = 0; cb < F / 16; cb++)
+							{
+								const int c0 = cb * 16;
+								uint4 res[2];
+								if (L.mode == MODE_CONV2)
+								{ // residual operand: x is updated in place
+									res[0] = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8) * img_chunk_bytes + out_idx * 16);
+									res[1] = *reinterpret_cast<const uint4*>(buf_x + (c0 / 8 + 1) * img_chunk_bytes + out_idx * 16);
 								}
+								tmem_ld_wait();
+								if (cb + 1 < F / 16)
+									tmem_ld16(taddr + c0 + 16, v[(cb + 1) & 1]);
+								float a[16];
+#pragma unroll
+								for (int j = 0; j < 16; j += 4)
+								{
+									const float4 bj = *reinterpret_cast<const float4*>(sbias + c0 + j);
+									a[j] = __uint_as_float(v[cb & 1][j]) + bj.x;
+									a[j + 1] = __uint_as_float(v[cb & 1][j + 1]) + bj.y;
+									a[j + 2] = __uint_as_float(v[cb & 1][j + 2]) + bj.z;
+									a[j + 3] = __uint_as_float(v[cb & 1][j + 3]) + bj.w;
+								}
+								if (L.mode == MODE_CONV2)
+								{
+#pragma unroll
+									for (int h8 = 0; h8 < 2; h8++)
+									{
+										const uint4 r = res[h8];
+										float lo, hi;
+										unpack_bf16(r.x, lo, hi); a[8 * h8 + 0] += lo; a[8 * h8 + 1] += hi;
+										unpack_bf16(r.y, lo, hi); a[8 * h8 + 2] += lo; a[8 * h8 + 3] += hi;
+										unpack_bf16(r.z, lo, hi); a[8 * h8 + 4] += lo; a[8 * h8 + 5] += hi;
+										unpack_bf16(r.w, lo, hi); a[8 * h8 + 6] += lo; a[8 * h8 + 7] += hi;
+									}
+								}
+								if (valid)
+								{
+#pragma unroll
+									for (int h8 = 0; h8 < 2; h8++)
+									{
+										uint4 o;
+										o.x = pack_bf16_relu(a[8 * h8 + 0], a[8 * h8 + 1]);
+										o.y = pack_bf16_relu(a[8 * h8 + 2], a[8 * h8 + 3]);
+										o.z = pack_bf16_relu(a[8 * h8 + 4], a[8 * h8 + 5]);
+										o.w = pack_bf16_relu(a[8 * h8 + 6], a[8 * h8 + 7]);
+										*reinterpret_cast<uint4*>(out_img + (c0 / 8 + h8) * img_chunk_bytes + out_idx * 16) = o;
+										if (send)
+											st_peer_v4(peer_img + (c0 / 8 + h8) * img_chunk_bytes + peer_idx * 16, o);
+									}
+								}
+								publish(cb);
+							}
+						}
+						else
+						{ // the two head convolutions: nothing is written to the image, the 1x1 convolutions behind them are accumulated per position
+#pragma unroll 2
+							for (int cb = 0; cb < F / 16; cb++)
+							{
+								const int c0 = cb * 16;
+								tmem_ld_wait();
+								if (cb + 1 < F / 16)
+									tmem_ld16(taddr + c0 + 16, v[(cb + 1) & 1]);
+								if (L.mode == MODE_QHEAD)
+								{
+#pragma unroll
+									for (int j = 0; j < 16; j++)
+									{
+										const float t = tanh_fast(__uint_as_float(v[cb & 1][j]) + sbias[c0 + j]);
+										head[0] += t * __ldg(prm.q_w1 + c0 + j);
+										head[1] += t * __ldg(prm.q_w1 + F + c0 + j);
+										head[2] += t * __ldg(prm.q_w1 + 2 * F + c0 + j);
+									}
+								}
+								else
+								{
+#pragma unroll
+									for (int j = 0; j < 16; j++)
+										head[0] += fmaxf(__uint_as_float(v[cb & 1][j]) + sbias[c0 + j], 0.0f) * __ldg(prm.policy_w1 + c0 + j);
+								}
+								publish(cb);
 							}
 						}
 						tc_fence_before();
@@ -1014,8 +1022,7 @@ namespace agb
 			if (f)
 			{
 				for (int l = 0; l < p.n_layers; l++)
-					fprintf(f, "%d %lld %lld %lld %lld  first_slice: ld=%lld stored=%lld fenced=%lld arrived=%lld\n", l, h[6 * l] - h[0], h[6 * l + 1] - h[0], h[6 * l + 2] - h[0],
-							h[6 * l + 3] - h[0], h[6 * l + 4] >> 32, h[6 * l + 4] & 0xFFFFFFFFll, h[6 * l + 5] >> 32, h[6 * l + 5] & 0xFFFFFFFFll);
+					fprintf(f, "%d %lld %lld %lld %lld\n", l, h[6 * l] - h[0], h[6 * l + 1] - h[0], h[6 * l + 2] - h[0], h[6 * l + 3] - h[0]);
 				fclose(f);
 			}
 		}
