@@ -127,7 +127,9 @@ namespace agb
 				uint32_t stage_step, uint64_t *w_full, uint64_t *peer_full, uint64_t *w_empty, uint64_t *chunk_ready, uint32_t &ready_phase, int &stage,
 				uint32_t &phase, int n_stages, long long *trace)
 		{
-#pragma unroll
+			// the slice loop is NOT unrolled (the nine taps inside are): a few loop instructions per 18 MMAs (1 152 tensor-pipe cycles) cost nothing,
+			// 8 x 100 instructions of straight-line code did -- K4's instruction footprint is felt by its own epilogue warps and, through the L2, by K5
+#pragma unroll 1
 			for (int c = 0; c < F / 16; c++)
 			{
 				// the weights first: they arrived long ago, and at the start of a layer (MMA queue empty) every wait after the image slice is
