@@ -185,7 +185,8 @@ namespace agb
 			float *logits = reinterpret_cast<float*>(stages + NS * prm.stage_bytes); // [256]
 			float *reduce = logits + 256; // [8]
 			float *sbias2 = reduce + 8; // [2][128]
-			float *xchg = sbias2 + 256; // [2] softmax (max, sum) of the peer's half board (SPLIT)
+			float *svalue_w = sbias2 + 256; // [4][F] + [4]: the value head's 1x1 convolution, staged once per kernel
+			float *xchg = svalue_w + 4 * 128 + 8; // [2] softmax (max, sum) of the peer's half board (SPLIT)
 			uint64_t *bars = reinterpret_cast<uint64_t*>(xchg + 8);
 			uint64_t *w_full = bars, *w_empty = bars + 8, *acc_full = bars + 16, *peer_full = bars + 18, *xbar = bars + 26, *chunk_ready = bars + 27;
 			uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
@@ -242,6 +243,8 @@ namespace agb
 				tmem_alloc_pair(tmem_slot, tmem_cols);
 				tmem_relinquish_pair();
 			}
+			for (int i = threadIdx.x; i < 4 * F + 4; i += kThreads)
+				svalue_w[i] = __ldg(prm.value_w + i);
 			// x image: the halo and the two pad columns stay zero for the whole kernel (only valid cells are ever written)
 			for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(prm.buf_bytes) / 16; i += kThreads)
 				reinterpret_cast<uint4*>(buf_x)[i] = make_uint4(0, 0, 0, 0);
@@ -691,13 +694,13 @@ namespace agb
 									for (int k = 0; k < 4; k++)
 #pragma unroll
 										for (int j = 0; j < 8; j++)
-											s4[k] += xv[j] * __ldg(prm.value_w + k * F + ch * 8 + j);
+											s4[k] += xv[j] * svalue_w[k * F + ch * 8 + j];
 								}
 								float4 o;
-								o.x = fmaxf(s4[0] + __ldg(prm.value_w + 4 * F + 0), 0.f);
-								o.y = fmaxf(s4[1] + __ldg(prm.value_w + 4 * F + 1), 0.f);
-								o.z = fmaxf(s4[2] + __ldg(prm.value_w + 4 * F + 2), 0.f);
-								o.w = fmaxf(s4[3] + __ldg(prm.value_w + 4 * F + 3), 0.f);
+								o.x = fmaxf(s4[0] + svalue_w[4 * F + 0], 0.f);
+								o.y = fmaxf(s4[1] + svalue_w[4 * F + 1], 0.f);
+								o.z = fmaxf(s4[2] + svalue_w[4 * F + 2], 0.f);
+								o.w = fmaxf(s4[3] + svalue_w[4 * F + 3], 0.f);
 								if (live)
 									*reinterpret_cast<float4*>(prm.value_hidden + (static_cast<size_t>(b) * cells + cell) * 4) = o;
 							}
@@ -958,7 +961,7 @@ namespace agb
 		p.q_w1 = c.q_head ? n->d_small + q_w1_off : nullptr;
 		p.value_hidden = n->d_value_hidden;
 		n->dense_width = D;
-		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (256 + 8 + 256 + 8) * 4 + 48 * 8;
+		n->smem_bytes = 2 * static_cast<size_t>(p.buf_bytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + (256 + 8 + 256 + 4 * 128 + 8 + 8) * 4 + 48 * 8;
 		n->split = S * (S + 2) > 256; // the board does not fit one CTA's 256 accumulator rows: one board per CTA pair
 		if (n->smem_bytes > 232448)
 			return e->fail(AGB_EINVAL, "network kernel needs " + std::to_string(n->smem_bytes) + " bytes of shared memory per CTA, more than the device has");
