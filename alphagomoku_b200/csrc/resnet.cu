@@ -43,8 +43,8 @@ namespace agb
 			uint16_t cin_chunks; // C_in / 8
 			uint8_t radius; // 1 (3x3) or 2 (5x5)
 			uint8_t mode;
-			uint8_t n_taps;
-			uint8_t unused;
+			uint8_t n_taps; // taps in the weight stream: k * k, rounded up to a multiple of nine with zero weights (one ring stage = nine taps)
+			uint8_t real_taps; // k * k
 			uint8_t last_trunk; // value 1x1 conv runs after this layer's epilogue
 			uint8_t pad;
 	};
@@ -122,44 +122,55 @@ namespace agb
 		// The K loop runs INPUT-CHANNEL-SLICE major: slice c of the input image is exactly what the previous layer's epilogue produces from
 		// accumulator columns 16c..16c+15, so this layer's MMAs on slice c start as soon as that part of the epilogue is done
 		// (chunk_ready[c]) while the rest of the epilogue is still draining the other accumulator set.
-		template<int F, int P>
-		__device__ __forceinline__ void issue_conv3x3(uint32_t tmem_acc, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
+		template<int F, int P, int KS>
+		__device__ __forceinline__ void issue_conv(uint32_t tmem_acc, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc, uint32_t a_kc_step,
 				uint32_t stage_step, uint64_t *w_full, uint64_t *peer_full, uint64_t *w_empty, uint64_t *chunk_ready, uint32_t &ready_phase, int &stage,
-				uint32_t &phase, int n_stages, long long *trace)
+				uint32_t &phase, int n_stages, int n_slices, long long *trace)
 		{
-			// the slice loop is NOT unrolled (the nine taps inside are): a few loop instructions per 18 MMAs (1 152 tensor-pipe cycles) cost nothing,
+			constexpr int kTaps = KS * KS, kStagesPerSlice = (kTaps + 8) / 9; // 3x3: one stage per 16-channel slice; the 5x5 stem: 25 taps + 2 of zero weights = 3
+			// the slice loop is NOT unrolled (the taps inside are): a few loop instructions per 18 MMAs (1 152 tensor-pipe cycles) cost nothing,
 			// 8 x 100 instructions of straight-line code did -- K4's instruction footprint is felt by its own epilogue warps and, through the L2, by K5
 #pragma unroll 1
-			for (int c = 0; c < F / 16; c++)
+			for (int c = 0; c < n_slices; c++)
 			{
-				// the weights first: they arrived long ago, and at the start of a layer (MMA queue empty) every wait after the image slice is
-				// ready would add to the bubble
-				mbar_wait(&w_full[stage], phase); // our half of the weights
-				mbar_wait_cluster(&peer_full[stage], phase); // the peer's half
-				mbar_wait_cluster(&chunk_ready[c], (ready_phase >> c) & 1u); // input channels 16c..16c+15 written by both CTAs, their accumulator columns drained
-				ready_phase ^= 1u << c;
-				tc_fence_after();
-				if (c == 0 and trace != nullptr)
-					*trace = clock64();
-				const uint64_t b_stage = b_desc0 + static_cast<uint32_t>(stage) * stage_step;
-				if (elect_one())
-				{
 #pragma unroll
-					for (int tap = 0; tap < 9; tap++)
-					{
-						const int row0 = (tap / 3) * P + (tap % 3);
-						const uint64_t ad = a_desc0 + row0 + static_cast<uint32_t>(2 * c) * a_kc_step;
-						const uint64_t bd = b_stage + tap * 2 * (F / 2);
-						mma_pair_bf16(tmem_acc, ad, bd, idesc, (tap | c) != 0);
-						mma_pair_bf16(tmem_acc + F, ad + 128, bd, idesc, (tap | c) != 0);
-					}
-					mma_pair_commit(&w_empty[stage], 3); // both CTAs may refill this stage once these MMAs have read it
-				}
-				__syncwarp();
-				if (++stage == n_stages)
+				for (int s = 0; s < kStagesPerSlice; s++)
 				{
-					stage = 0;
-					phase ^= 1;
+					// the weights first: they arrived long ago, and at the start of a layer (MMA queue empty) every wait after the image slice is
+					// ready would add to the bubble
+					mbar_wait(&w_full[stage], phase); // our half of the weights
+					mbar_wait_cluster(&peer_full[stage], phase); // the peer's half
+					if (s == 0)
+					{
+						mbar_wait_cluster(&chunk_ready[c], (ready_phase >> c) & 1u); // input channels 16c..16c+15 written by both CTAs, their accumulator columns drained
+						ready_phase ^= 1u << c;
+					}
+					tc_fence_after();
+					if (s == 0 and c == 0 and trace != nullptr)
+						*trace = clock64();
+					const uint64_t b_stage = b_desc0 + static_cast<uint32_t>(stage) * stage_step;
+					if (elect_one())
+					{
+#pragma unroll
+						for (int tt = 0; tt < 9; tt++)
+						{
+							constexpr int kDummy = 0;
+							const int tap = s * 9 + tt;
+							const int row0 = (tap < kTaps) ? (tap / KS) * P + (tap % KS) : kDummy; // taps past the kernel carry zero weights: any finite rows do
+							const uint64_t ad = a_desc0 + row0 + static_cast<uint32_t>(2 * c) * a_kc_step;
+							const uint64_t bd = b_stage + tt * 2 * (F / 2);
+							const bool acc = (tap != 0) or (c != 0);
+							mma_pair_bf16(tmem_acc, ad, bd, idesc, acc);
+							mma_pair_bf16(tmem_acc + F, ad + 128, bd, idesc, acc);
+						}
+						mma_pair_commit(&w_empty[stage], 3); // both CTAs may refill this stage once these MMAs have read it
+					}
+					__syncwarp();
+					if (++stage == n_stages)
+					{
+						stage = 0;
+						phase ^= 1;
+					}
 				}
 			}
 		}
@@ -308,10 +319,13 @@ namespace agb
 							const uint32_t tmem_acc = tmem_base + (l & 1) * 2 * F; // accumulator sets alternate: the previous layer's is still being drained
 							long long *trace0 = (prm.trace and b0 == 0 and lane == 0) ? prm.trace + 6 * l : nullptr;
 							int chunk = 0, tap = 0, ky = 0, kx = 0; // position in the layer's stream of weight slices: 16-channel slice of the input, then tap
-							const bool fast = (S == (SPLIT ? 20 : 15) and L.radius == 1 and cin_chunks == F / 8 and prm.kc_per_stage == 18);
-							if (fast)
-								issue_conv3x3<F, SPLIT ? 22 : 17>(tmem_acc, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, chunk_ready, ready_phase,
-										stage, phase, NS, trace0);
+							const bool fast = (S == (SPLIT ? 20 : 15) and prm.kc_per_stage == 18 and L.n_taps % 9 == 0);
+							if (fast and L.radius == 1)
+								issue_conv<F, SPLIT ? 22 : 17, 3>(tmem_acc, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, chunk_ready, ready_phase,
+										stage, phase, NS, cin_chunks / 2, trace0);
+							else if (fast and L.radius == 2)
+								issue_conv<F, SPLIT ? 22 : 17, 5>(tmem_acc, a_desc0, b_desc0, idesc, a_kc_step, stage_step, w_full, peer_full, w_empty, chunk_ready, ready_phase,
+										stage, phase, NS, cin_chunks / 2, trace0);
 							else
 							for (int kc0 = 0; kc0 < total_kc; kc0 += prm.kc_per_stage)
 							{
@@ -330,7 +344,7 @@ namespace agb
 										if (chunk == 0 and trace0 != nullptr)
 											*trace0 = clock64();
 									}
-									const uint64_t ad = a_desc0 + (ky * P + kx) + 2 * chunk * a_kc_step;
+									const uint64_t ad = a_desc0 + (tap < L.real_taps ? ky * P + kx : 0) + 2 * chunk * a_kc_step; // taps past the kernel carry zero weights
 									const bool acc = (kc0 + j) != 0;
 									if (elect_one())
 									{
@@ -348,6 +362,7 @@ namespace agb
 									{
 										tap = 0;
 										ky = 0;
+										kx = 0; // the stream's taps past the kernel do not end on a row boundary
 										chunk++;
 									}
 								}
@@ -808,7 +823,7 @@ namespace agb
 		}
 		// fp32 W[F][k][k][cin] -> bf16 weight slices [half][cin/16][tap][2][F/2][8]: 16 input channels at a time (what one part of the previous
 		// layer's epilogue produces), all taps of those, each as the two 8-channel core-matrix columns of one K = 16 MMA step
-		void append_conv_image(std::vector<uint16_t> &img, const float *w, int F, int k, int cin)
+		void append_conv_image(std::vector<uint16_t> &img, const float *w, int F, int k, int cin, int stream_taps)
 		{
 			const auto to_bf16 = [](float x)
 			{
@@ -820,11 +835,11 @@ namespace agb
 			// half-major: CTA `half` of a pair streams the slices for output channels half*F/2 ..
 			for (int half = 0; half < 2; half++)
 				for (int c16 = 0; c16 < cin / 16; c16++)
-					for (int tap = 0; tap < k * k; tap++)
+					for (int tap = 0; tap < stream_taps; tap++)
 						for (int kc = 2 * c16; kc < 2 * c16 + 2; kc++)
 							for (int co = half * (F / 2); co < (half + 1) * (F / 2); co++)
 								for (int e = 0; e < 8; e++)
-									img.push_back(to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]));
+									img.push_back(tap < k * k ? to_bf16(w[(static_cast<size_t>(co) * k * k + tap) * cin + kc * 8 + e]) : static_cast<uint16_t>(0));
 		}
 	}
 
@@ -894,9 +909,10 @@ namespace agb
 			L.cin_chunks = static_cast<uint16_t>(cin / 8);
 			L.radius = static_cast<uint8_t>(k / 2);
 			L.mode = static_cast<uint8_t>(mode);
-			L.n_taps = static_cast<uint8_t>(k * k);
+			L.real_taps = static_cast<uint8_t>(k * k);
+			L.n_taps = static_cast<uint8_t>((k * k + 8) / 9 * 9); // 9, or 27 for the 5x5 stem: whole ring stages per 16-channel slice
 			L.last_trunk = last_trunk;
-			append_conv_image(images, cur, F, k, cin);
+			append_conv_image(images, cur, F, k, cin, L.n_taps);
 			cur += static_cast<size_t>(F) * k * k * cin;
 			small.insert(small.end(), cur, cur + F);
 			cur += F;
