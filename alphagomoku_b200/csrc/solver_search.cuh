@@ -127,10 +127,13 @@ namespace agb
 			uint8_t *const threats = d.threats;
 			const uint8_t *const pattern_table = d.v.pattern_table, *const threat_table = d.threat_table;
 			const int row_step = dir_row_step(dir), col_step = dir_col_step(dir);
-			uint32_t old_t[2] = { 0, 0 }, new_t[2] = { 0, 0 }, loc[2] = { 0, 0 };
-#pragma unroll
+			// Two passes of 32 and 8 entries, NOT unrolled, each: look the entry's cell up, store it, then replay the list changes of the pass in entry
+			// order. A cell appears once among the 40 entries and the list changes depend only on its (old, new) threats, so replaying pass 0 before
+			// pass 1 is looked up gives what "all lookups, then all replays" gave -- in half the code, which is what this kernel is short of.
+#pragma unroll 1
 			for (int half = 0; half < 2; half++)
 			{
+				uint32_t ot = 0, nt = 0, lc = 0;
 				const int q = lane + 32 * half; // q & 3 == dir in both halves
 				if (q < 40)
 				{
@@ -143,20 +146,14 @@ namespace agb
 						const uint32_t window = static_cast<uint32_t>(my_line >> (2 * (my_pos + off) + 2)) & 0x3FFFFFu;
 						const uint32_t byte = pattern_table[narrow_window(window)];
 						const uint32_t p = (ptypes[ncell] & ~(0xFFu << (8 * dir))) | (byte << (8 * dir));
-						old_t[half] = threats[ncell];
-						new_t[half] = threat_of_cell(p, threat_table);
-						loc[half] = mk_loc(nr, nc);
+						ot = threats[ncell];
+						nt = threat_of_cell(p, threat_table);
+						lc = mk_loc(nr, nc);
 						ptypes[ncell] = p;
-						threats[ncell] = static_cast<uint8_t>(new_t[half]);
+						threats[ncell] = static_cast<uint8_t>(nt);
 					}
 				}
-			}
-			__syncwarp();
-#pragma unroll
-			for (int half = 0; half < 2; half++)
-			{
 				// only changes that touch a kept list (OPEN_3 or stronger, either colour) are replayed
-				const uint32_t ot = old_t[half], nt = new_t[half];
 				const bool touches = ((ot & 15u) != (nt & 15u) and (list_is_kept(ot & 15u) or list_is_kept(nt & 15u)))
 						or ((ot >> 4) != (nt >> 4) and (list_is_kept(ot >> 4) or list_is_kept(nt >> 4)));
 				unsigned changed = __ballot_sync(0xFFFFFFFFu, touches);
@@ -165,20 +162,18 @@ namespace agb
 					const int src = __ffs(changed) - 1;
 					changed &= changed - 1;
 					// one shuffle: old threats | new threats << 8 | location << 16
-					const uint32_t packed = __shfl_sync(0xFFFFFFFFu, ot | (nt << 8) | (loc[half] << 16), src);
-					const int o = packed & 255u, nw = (packed >> 8) & 255u;
+					const uint32_t packed = __shfl_sync(0xFFFFFFFFu, ot | (nt << 8) | (lc << 16), src);
 					const uint16_t l = static_cast<uint16_t>(packed >> 16);
-					if ((o & 15) != (nw & 15))
+#pragma unroll 1
+					for (int colour = 0; colour < 2; colour++)
 					{
-						if (list_is_kept(o & 15))
-							dyn_hist_remove(d, 0, o & 15, l);
-						dyn_hist_add(d, 0, nw & 15, l);
-					}
-					if ((o >> 4) != (nw >> 4))
-					{
-						if (list_is_kept(o >> 4))
-							dyn_hist_remove(d, 1, o >> 4, l);
-						dyn_hist_add(d, 1, nw >> 4, l);
+						const int o = (packed >> (4 * colour)) & 15, nw = (packed >> (8 + 4 * colour)) & 15;
+						if (o != nw)
+						{
+							if (list_is_kept(o))
+								dyn_hist_remove(d, colour, o, l);
+							dyn_hist_add(d, colour, nw, l);
+						}
 					}
 				}
 			}
