@@ -629,6 +629,7 @@ namespace agb
 					LocList<7> def = raw_defensive_moves(v.opp(), r, c, dir);
 					def.remove_value(loc);
 					int best = TT_NONE;
+#pragma unroll 1
 					for (int i = 0; i < def.size; i++)
 					{
 						const int tt = v.threat_at(v.opp(), loc_row(def.data[i]), loc_col(def.data[i]));
@@ -658,6 +659,7 @@ namespace agb
 				{
 					uint16_t result = kScoreDefault;
 					const int n = v.count(v.own(), TT_FORK_4x3);
+#pragma unroll 1
 					for (int i = 0; i < n; i++)
 					{
 						const uint16_t loc = v.item(v.own(), TT_FORK_4x3, i);
@@ -675,6 +677,7 @@ namespace agb
 					if (v.anything_forbidden_for(v.own()))
 					{
 						copy_list(v.own(), TT_FORK_3x3);
+#pragma unroll 1
 						for (int i = 0; i < temp_size; i++)
 						{
 							const uint16_t loc = temp[i];
@@ -739,6 +742,7 @@ namespace agb
 					out.must_defend = true;
 					out.baseline = loss_in(2);
 					DefensiveSet defensive;
+#pragma unroll 1
 					for (int i = 0; i < n_fives; i++)
 					{
 						const uint16_t loc = v.item(v.opp(), TT_FIVE, i);
@@ -752,6 +756,7 @@ namespace agb
 						}
 					}
 					uint16_t best = kScoreMin;
+#pragma unroll 1
 					for (int i = 0; i < defensive.list.size; i++)
 					{
 						const uint16_t loc = defensive.list.data[i];
@@ -800,6 +805,7 @@ namespace agb
 					if (v.anything_forbidden_for(v.own()))
 					{
 						copy_list(v.own(), TT_FORK_3x3);
+#pragma unroll 1
 						for (int i = 0; i < temp_size; i++)
 						{
 							const uint16_t loc = temp[i];
@@ -820,6 +826,7 @@ namespace agb
 					if (v.anything_forbidden_for(v.opp()))
 					{ // renju, white to move: a four whose only answer is a forbidden point for black
 						copy_list(v.own(), TT_HALF_OPEN_4);
+#pragma unroll 1
 						for (int i = 0; i < temp_size; i++)
 						{
 							const uint16_t loc = temp[i];
@@ -1085,6 +1092,7 @@ namespace agb
 					add_list(v.own(), TT_OVERLINE, loss_in(1), true);
 					add_list(v.own(), TT_FORK_4x4, loss_in(1), true);
 					copy_list(v.own(), TT_FORK_3x3);
+#pragma unroll 1
 					for (int i = 0; i < temp_size; i++)
 					{
 						const uint16_t loc = temp[i];

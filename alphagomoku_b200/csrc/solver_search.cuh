@@ -80,6 +80,7 @@ namespace agb
 		// the index of the lists as K1 left them (the kept ones): lanes take interleaved entries
 		__device__ __forceinline__ void dyn_build_list_index(DynState &d)
 		{
+#pragma unroll 1
 			for (int k = 0; k < 2 * kHistTypes; k++)
 				if (list_is_kept(k % kHistTypes))
 				{
@@ -593,6 +594,7 @@ namespace agb
 			lo = 0;
 			hi = 0;
 #ifdef __CUDA_ARCH__
+#pragma unroll 1
 			for (int i = threadIdx.x & 31; i < d.v.cells; i += 32) // the lanes of the lockstep warp take interleaved cells
 #else
 			for (int i = 0; i < d.v.cells; i++)
@@ -644,6 +646,7 @@ namespace agb
 			const int child_own = 3 - sign; // side to move after the move
 			// evaluate() of the parent's histogram seen from the child's side to move, then corrected cell by cell
 			int sum = 12;
+#pragma unroll 1
 			for (int t = TT_OPEN_3; t <= TT_FIVE; t++)
 				sum += eval_weight(t, true) * d.v.count(child_own, t) + eval_weight(t, false) * d.v.count(3 - child_own, t);
 			int strong = 0, n_ops = 0;
@@ -652,8 +655,10 @@ namespace agb
 				sum -= eval_weight((centre_t >> (4 * colour)) & 15, colour + 1 == child_own);
 			if ((centre_t & 15) == TT_OPEN_3 or (centre_t >> 4) == TT_OPEN_3)
 				out.ops[n_ops++] = mk_loc(r, c) | (static_cast<uint32_t>(centre_t) << 16);
+#pragma unroll 1
 			for (int off = -5; off <= 5; off++)
 				if (off != 0)
+#pragma unroll 1
 					for (int dir = 0; dir < 4; dir++)
 					{
 						const int nr = r + off * dir_row_step(dir), nc = c + off * dir_col_step(dir);
@@ -672,6 +677,7 @@ namespace agb
 						if (old_t == new_t)
 							continue;
 						bool touches_open3 = false;
+#pragma unroll 1
 						for (int colour = 0; colour < 2; colour++)
 						{
 							const int o = (old_t >> (4 * colour)) & 15, n = (new_t >> (4 * colour)) & 15;
@@ -713,13 +719,16 @@ namespace agb
 		AGB_HD_NOINLINE inline void replay_open3_edits(DynState &d, uint16_t move, const ChildInfo &info)
 		{
 			const uint16_t centre = mk_loc((move >> 2) & 127, (move >> 9) & 127);
+#pragma unroll 1
 			for (int phase = 0; phase < 2; phase++) // 0: addMove, 1: undoMove
+#pragma unroll 1
 				for (int k = 0; k < info.n_ops; k++)
 				{
 					const uint32_t op = info.ops[k];
 					const uint16_t loc = static_cast<uint16_t>(op & 0xFFFFu);
 					const int from = (phase == 0) ? (op >> 16) & 255 : (op >> 24) & 255;
 					const int to = (phase == 0) ? (op >> 24) & 255 : (op >> 16) & 255;
+#pragma unroll 1
 					for (int colour = 0; colour < 2; colour++)
 					{
 						const int o = (from >> (4 * colour)) & 15, n = (to >> (4 * colour)) & 15;
@@ -928,6 +937,7 @@ namespace agb
 							if ((bm & 3) == d.v.stm and br < d.v.S and bc < d.v.S and d.board[br * d.v.S + bc] == NONE)
 							{
 								ordered = true;
+#pragma unroll 1
 								for (int j = 0; j < f.list_size; j++)
 									if (am[j] == bm)
 									{
@@ -947,6 +957,7 @@ namespace agb
 							{ // the lanes of the warp scan interleaved slices; ties go to the lowest index, like the sequential scan
 								const int lane = threadIdx.x & 31;
 								uint32_t best = 0; // (score << 16) | (0xFFFF - index): larger score first, then smaller index
+#pragma unroll 1
 								for (int j = i + lane; j < f.list_size; j += 32)
 								{
 									const uint32_t key = (static_cast<uint32_t>(as[j]) << 16) | static_cast<uint32_t>(0xFFFF - j);
