@@ -9,9 +9,15 @@
 //    conv tap is the same image read at a shifted start address -- implicit GEMM without im2col and without border code.
 //  * per layer: D[256 positions x F] (fp32, TMEM) = sum over taps of A_tap[256 x C] * W_tap[F x C]^T with tcgen05.mma
 //    (M=128 x2 tiles, N=F, K=16), operands K-major / no swizzle (umma.cuh). One elected thread issues.
-//  * weights stream from L2 through a ring of 32 KiB stages filled by cp.async.bulk (mbarrier complete_tx).
-//  * epilogue warps read TMEM (tcgen05.ld), add bias, ReLU (+ residual, in place), and write the next layer's image;
-//    the policy 1x1 + softmax, the value 1x1 and the Q 1x1 + softmax are fused into the epilogues of their convs.
+//  * weights stream from L2 through a ring of stages filled by cp.async.bulk (mbarrier complete_tx); one stage = the nine taps of one
+//    16-channel slice of a layer's input, which is the unit the K loop consumes (it runs input-slice major).
+//  * epilogue warps read TMEM (tcgen05.ld) 16 columns at a time, add bias, ReLU (+ residual, in place), write that slice of the next
+//    layer's image and publish it on its own mbarrier: the next layer's MMAs on the slice start at once, into the other of two TMEM
+//    accumulator sets, while the rest is still being drained. The policy 1x1 + softmax, the value 1x1 and the Q 1x1 + softmax are fused
+//    into the epilogues of their convs.
+//  * the CTA pairs draw their boards from a global ticket counter (a pair whose SMs free up late takes fewer).
+//  * the kernel's code size is kept small on purpose (slice loops are loops, head code sits outside the trunk's loop): ten warps per SM
+//    fetch it, and the solver kernel running beside it fetches its own code through the same L2.
 //  * input: the 32-bit feature words are unpacked into the stem's bf16 image by the same warps (replaces ml::unpackInput).
 #include "engine.hpp"
 #include "umma.cuh"
