@@ -88,8 +88,11 @@ namespace agb
 			float *d_wd1 = nullptr, *d_bd1 = nullptr, *d_wd2 = nullptr, *d_bd2 = nullptr;
 			float *d_value_hidden = nullptr;
 			float *d_policy = nullptr, *d_value = nullptr, *d_q = nullptr; // staging for host entry point
-			int *d_tickets = nullptr; // [kTicketCounters]: launch i draws its boards from counter i % kTicketCounters (launches on different streams may overlap)
-			unsigned launch_counter = 0;
+			// one board-ticket counter per stream K4 is launched on (launches on one stream are ordered, so its counter is free again when the next
+			// launch's memset runs; launches on different streams may overlap and must not share one)
+			int *d_tickets = nullptr; // [kTicketCounters]
+			cudaStream_t ticket_streams[kTicketCounters] = { };
+			int n_ticket_streams = 0;
 			int dense_width = 0;
 			size_t smem_bytes = 0;
 			bool split = false; // one board per CTA pair (boards of more than 15 rows)
@@ -1011,7 +1014,16 @@ namespace agb
 		p.n_boards_dev = n_dev;
 		p.gather = gather_dev;
 		p.slot_base = slot_base;
-		p.ticket = n->d_tickets + (n->launch_counter++ % kTicketCounters);
+		int ticket_slot = 0;
+		while (ticket_slot < n->n_ticket_streams and n->ticket_streams[ticket_slot] != stream)
+			ticket_slot++;
+		if (ticket_slot == n->n_ticket_streams)
+		{
+			if (n->n_ticket_streams == kTicketCounters)
+				return e->fail(AGB_ESTATE, "network kernel launched on more streams than it has board-ticket counters");
+			n->ticket_streams[n->n_ticket_streams++] = stream;
+		}
+		p.ticket = n->d_tickets + ticket_slot;
 		AGB_CUDA_CHECK(e, cudaMemsetAsync(p.ticket, 0, sizeof(int), stream));
 		static long long *d_trace = nullptr;
 		const bool trace = getenv("AGB_NET_TRACE") != nullptr;
